@@ -1,0 +1,77 @@
+"""Pin the CPU oracle against vectors produced by the real reference (tests/golden/make_golden.py)."""
+import numpy as np
+import torch
+
+from oracle import pile_oracle as O
+from dyn_res_pile_manip_b200 import synthetic
+
+
+def _coo(adj):
+    return adj.nonzero().to(torch.int16).numpy()
+
+
+def test_weights_from_seed_match_reference_init(golden_weights):
+    W = O.weights_from_seed(0)
+    assert set(W) == set(golden_weights)
+    for k in W:
+        assert torch.equal(W[k], golden_weights[k]), k
+
+
+def test_s_delta_case_A(golden):
+    sd = O.gen_s_delta(golden["cam_extrinsic"], synthetic.GLOBAL_SCALE,
+                       torch.from_numpy(golden["A/s_cur"]), torch.from_numpy(golden["A/act"]))
+    np.testing.assert_allclose(sd.numpy(), golden["A/s_delta"], rtol=0, atol=1e-7)
+    assert np.abs(golden["A/s_delta"]).max() > 1e-3      # the pushes really hit the pile
+
+
+def test_relations_bit_exact(golden):
+    for case, nums in (("A", None), ("B", None), ("C", golden["C/nums"])):
+        adj = O.adjacency(torch.from_numpy(golden[case + "/s_cur"]), torch.from_numpy(golden[case + "/s_delta"]),
+                          0.08, nums)
+        assert np.array_equal(_coo(adj), golden[case + "/rel"]), case
+
+
+def test_one_step_positions(golden, golden_weights):
+    for case in "ABC":
+        g = {k.split("/")[1]: torch.from_numpy(v) for k, v in golden.items() if k.startswith(case + "/")}
+        B, N, _ = g["s_cur"].shape
+        a = g.get("a_cur", torch.zeros(B, N))
+        nums = g.get("nums")
+        with torch.no_grad():
+            out = O.predict_one_step(golden_weights, 0.08, a, g["s_cur"], g["s_delta"], g["dens"], nums)
+        np.testing.assert_allclose(out.numpy(), g["s_pred"].numpy(), rtol=0, atol=2e-6)
+
+
+def test_rollout_reward_and_action_gradient(golden, golden_weights):
+    acts = torch.tensor(golden["D/acts"], requires_grad=True)
+    goal = torch.from_numpy(synthetic.make_goal(str(golden["D/goal_kind"])))
+    pred, adjs = O.rollout(golden_weights, 0.08, golden["cam_extrinsic"], synthetic.GLOBAL_SCALE,
+                           torch.from_numpy(golden["D/s0"]), torch.from_numpy(golden["D/dens"]),
+                           torch.zeros(2, 60), acts, return_adj=True)
+    for t, adj in enumerate(adjs):
+        assert np.array_equal(_coo(adj), golden["D/rel%d" % t]), t
+    np.testing.assert_allclose(pred.detach().numpy(), golden["D/state_pred"], rtol=0, atol=5e-6)
+    obs = pred.reshape(6, 1, 4, 60, 3).permute(0, 2, 1, 3, 4)
+    reward, next_r = O.evaluate_traj(obs, goal, list(golden["cam_params"]), torch.from_numpy(golden["D/goal_coor"]))
+    np.testing.assert_allclose(reward.detach().numpy(), golden["D/reward"], rtol=1e-5)
+    np.testing.assert_allclose(next_r.detach().numpy(), golden["D/next_r"], rtol=1e-5)
+    torch.sum(-reward).backward()
+    g, ref = acts.grad.numpy(), golden["D/act_grad"]
+    assert np.abs(ref).max() > 0
+    np.testing.assert_allclose(g, ref, rtol=2e-3, atol=2e-4 * np.abs(ref).max())
+
+
+def test_mppi_pieces(golden):
+    env = synthetic.FakeEnv()
+    np.random.seed(12)
+    s = O.sample_action_sequences(golden["E/init"], 16, 0.3 * synthetic.GLOBAL_SCALE / 12.0, 0.7, env.cvx_region)
+    np.testing.assert_allclose(s, golden["E/sampled"], rtol=0, atol=1e-12)
+    a = O.mppi_optimize_action(golden["E/sampled"], golden["E/reward"], 0.1)
+    np.testing.assert_allclose(a, golden["E/optimized"], rtol=1e-12)
+
+
+def test_fps_matches_reference_goal_coords(golden):
+    goal = torch.from_numpy(synthetic.make_goal("bar"))
+    coords = torch.flip((goal < 0.5).nonzero(), dims=(1,)).float().numpy()
+    mine, _ = synthetic.fps_np(coords, min(300, coords.shape[0]), 0)
+    assert np.array_equal(mine.astype(np.float32), golden["D/goal_coor"])
