@@ -1,0 +1,99 @@
+"""ctypes binding of libpilegnn.so (C ABI in include/pile_gnn.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call returns a
+non-zero status the caller gets an exception.  Build with `python __graft_entry__.py` or
+`make -C dyn_res_pile_manip_b200/csrc`.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libpilegnn.so")
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+_LL = C.c_longlong
+
+# name -> (restype, argtypes); mirrors include/pile_gnn.h one to one
+SIGNATURES = {
+    "pile_abi_version": (_I, []),
+    "pile_nf_effect": (_I, []),
+    "pile_max_relations": (_I, []),
+    "pile_error_string": (C.c_char_p, [_I]),
+    "pile_wpack_num_slots": (_I, []),
+    "pile_wpack_slot_offset": (_LL, [_I]),
+    "pile_wpack_slot_size": (_LL, [_I]),
+    "pile_wpack_total": (_LL, []),
+    "pile_gen_s_delta": (_I, [_P, _P, _I, _P, _F, _I, _I, _P, _P]),
+    "pile_gen_s_delta_backward": (_I, [_P, _P, _I, _P, _F, _I, _I, _P, _P, _P, _I, _P]),
+    "pile_build_relations": (_I, [_P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "pile_step_scratch_bytes": (_LL, [_I, _I]),
+    "pile_tape_step_bytes": (_LL, [_I, _I]),
+    "pile_predict_step": (_I, [_P, _P, _P, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P]),
+    "pile_forward_relations": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "pile_relations_view": (_I, [_P, _I, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "pile_rollout_forward": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P, _P]),
+    "pile_bwd_scratch_bytes": (_LL, [_I, _I]),
+    "pile_step_backward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "pile_rollout_backward": (_I, [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "pile_reward": (_I, [_P, _LL, _LL, _I, _P, _I, _I, _P, _I, _P, _F, _F, _I, _P, _P, _P]),
+    "pile_reward_backward": (_I, [_P, _LL, _LL, _I, _P, _I, _I, _P, _I, _P, _F, _F, _I, _P, _P, _P, _LL, _I, _P]),
+    "pile_mppi_num_chunks": (_I, [_I]),
+    "pile_mppi_partials": (_I, [_P, _P, _I, _I, _F, _P, _P]),
+    "pile_mppi_combine": (_I, [_P, _I, _I, _P, _P]),
+}
+
+_lib = None
+
+
+class PileLibraryError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile libpilegnn.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode != 0:
+        raise PileLibraryError("building libpilegnn.so failed")
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise PileLibraryError(
+            "%s is missing -- the CUDA path is the only path (no CPU fallback). "
+            "Build it with `python __graft_entry__.py` or `make -C %s`." % (LIB_PATH, CSRC))
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pile_abi_version() != 1:
+        raise PileLibraryError("libpilegnn ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().pile_error_string(code)
+        raise PileLibraryError("%s failed: CUDA error %d (%s)" % (what, code, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def host_floats(values):
+    arr = (C.c_float * len(values))(*[float(v) for v in values])
+    return arr

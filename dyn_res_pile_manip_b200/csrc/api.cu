@@ -1,0 +1,318 @@
+// extern "C" surface of libpilegnn (declared in include/pile_gnn.h).
+#include "../../include/pile_gnn.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace pile;
+
+namespace {
+
+constexpr size_t ALIGN = 256;
+inline size_t up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t count) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += up(count * sizeof(T));
+    return p;
+  }
+};
+
+struct ScratchView {
+  StepScratch ws;
+  Csr csr;       // relation lists when no tape is recorded
+  size_t bytes;
+};
+
+ScratchView carve_scratch(void* p, int B, int N) {
+  Carver c(p);
+  const size_t R = (size_t)B * N, E = (size_t)B * KMAX * N;
+  ScratchView v;
+  v.ws.s_delta = c.take<float>(R * 3);
+  v.ws.Ce = c.take<float>(E * H);
+  v.ws.Cp = c.take<float>(R * H);
+  v.ws.eff = c.take<float>(R * H);
+  v.ws.Pr[0] = c.take<float>(R * H);
+  v.ws.Pr[1] = c.take<float>(R * H);
+  v.ws.Ps[0] = c.take<float>(R * H);
+  v.ws.Ps[1] = c.take<float>(R * H);
+  v.csr.rowptr = c.take<int>((size_t)B * (N + 1));
+  v.csr.col = c.take<int>(E);
+  v.csr.row = c.take<int>(E);
+  v.csr.trowptr = nullptr;
+  v.csr.trecv = nullptr;
+  v.csr.tedge = nullptr;
+  v.bytes = c.off;
+  return v;
+}
+
+struct TapeView {
+  Csr csr;
+  Masks mk;
+  size_t bytes;
+};
+
+TapeView carve_tape(void* p, int B, int N) {
+  Carver c(p);
+  const size_t R = (size_t)B * N, E = (size_t)B * KMAX * N;
+  TapeView v;
+  v.csr.rowptr = c.take<int>((size_t)B * (N + 1));
+  v.csr.col = c.take<int>(E);
+  v.csr.row = c.take<int>(E);
+  v.csr.trowptr = c.take<int>((size_t)B * (N + 1));
+  v.csr.trecv = c.take<int>(E);
+  v.csr.tedge = c.take<int>(E);
+  v.mk.pe0 = c.take<uint8_t>(R * 8);
+  v.mk.pe1 = c.take<uint8_t>(R * 8);
+  for (int p2 = 0; p2 < PSTEP; ++p2) v.mk.eff[p2] = c.take<uint8_t>(R * 8);
+  v.mk.q = c.take<uint8_t>(R * 8);
+  v.mk.re0 = c.take<uint8_t>(E * 8);
+  v.mk.re1 = c.take<uint8_t>(E * 8);
+  v.mk.re2 = c.take<uint8_t>(E * 8);
+  for (int p2 = 0; p2 < PSTEP; ++p2) v.mk.edge[p2] = c.take<uint8_t>(E * 8);
+  v.bytes = c.off;
+  return v;
+}
+
+PushCam make_cam(const float* m12, float gs) {
+  PushCam c;
+  for (int i = 0; i < 12; ++i) c.m[i] = m12[i];
+  c.global_scale = gs;
+  c.pusher_w = 0.8f / 24.0f;   // planners.py:225
+  c.decay = 0.01f;             // planners.py:251
+  return c;
+}
+
+inline bool bad_dims(int B, int N) { return B <= 0 || N <= 0 || nbr_smem_bytes(N) > 200 * 1024; }
+
+}  // namespace
+
+extern "C" {
+
+int pile_abi_version(void) { return PILE_ABI_VERSION; }
+int pile_nf_effect(void) { return H; }
+int pile_max_relations(void) { return KMAX; }
+const char* pile_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
+
+int pile_wpack_num_slots(void) { return W_NUM; }
+long long pile_wpack_slot_offset(int slot) { return (slot < 0 || slot > W_NUM) ? -1 : wslot_offset(slot); }
+long long pile_wpack_slot_size(int slot) { return (slot < 0 || slot >= W_NUM) ? -1 : wslot_size(slot); }
+long long pile_wpack_total(void) { return wslot_offset(W_NUM); }
+
+int pile_gen_s_delta(const float* s_cur, const float* action, int act_stride, const float* cam_m12,
+                     float global_scale, int B, int N, float* s_delta, void* stream) {
+  if (B <= 0 || N <= 0 || !s_cur || !action || !cam_m12 || !s_delta) return (int)cudaErrorInvalidValue;
+  return launch_gen_s_delta(s_cur, (long long)N * 3, action, act_stride, make_cam(cam_m12, global_scale), B, N,
+                            s_delta, (cudaStream_t)stream);
+}
+
+int pile_build_relations(const float* s_cur, const float* s_delta, const int* particle_nums, int B, int N,
+                         float adj_thresh, int* rowptr, int* col, int* row, int* trowptr, int* trecv,
+                         int* tedge, void* stream) {
+  if (bad_dims(B, N) || !s_cur || !s_delta || !rowptr || !col || !row) return (int)cudaErrorInvalidValue;
+  if (trowptr && (!trecv || !tedge)) return (int)cudaErrorInvalidValue;
+  PushCam none{};
+  Csr csr{rowptr, col, row, trowptr, trecv, tedge};
+  return launch_nbr_search(s_cur, (long long)N * 3, s_delta, nullptr, 0, none, nullptr, particle_nums, B, N,
+                           adj_thresh * adj_thresh, csr, (cudaStream_t)stream);
+}
+
+long long pile_step_scratch_bytes(int B, int N) {
+  if (bad_dims(B, N)) return -1;
+  return (long long)carve_scratch(nullptr, B, N).bytes;
+}
+
+long long pile_tape_step_bytes(int B, int N) {
+  if (bad_dims(B, N)) return -1;
+  return (long long)carve_tape(nullptr, B, N).bytes;
+}
+
+int pile_relations_view(void* p, int is_tape, int B, int N, int** rowptr, int** col, int** row) {
+  if (!p || bad_dims(B, N)) return (int)cudaErrorInvalidValue;
+  const Csr c = is_tape ? carve_tape(p, B, N).csr : carve_scratch(p, B, N).csr;
+  *rowptr = c.rowptr; *col = c.col; *row = c.row;
+  return 0;
+}
+
+int pile_predict_step(const float* wpack, const float* attr, const float* dens, const int* particle_nums,
+                      const float* s_cur, const float* s_delta, float adj_thresh, int B, int N, void* scratch,
+                      void* tape, float* s_pred, void* stream) {
+  if (bad_dims(B, N) || !wpack || !attr || !dens || !s_cur || !s_delta || !scratch || !s_pred)
+    return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  ScratchView sv = carve_scratch(scratch, B, N);
+  TapeView tv;
+  Csr csr = sv.csr;
+  if (tape) { tv = carve_tape(tape, B, N); csr = tv.csr; }
+  PushCam none{};
+  int e = launch_nbr_search(s_cur, (long long)N * 3, s_delta, nullptr, 0, none, nullptr, particle_nums, B, N,
+                            adj_thresh * adj_thresh, csr, st);
+  if (e) return e;
+  return launch_forward(wpack, attr, dens, s_cur, (long long)N * 3, s_delta, csr, sv.ws, tape ? &tv.mk : nullptr,
+                        s_pred, (long long)N * 3, B, N, st);
+}
+
+int pile_rollout_forward(const float* wpack, const float* attr, const float* dens, const float* s0,
+                         const float* actions, const float* cam_m12, float global_scale, float adj_thresh,
+                         int B, int N, int T, void* scratch, void* tape, float* states, void* stream) {
+  if (bad_dims(B, N) || T <= 0 || !wpack || !attr || !dens || !s0 || !actions || !cam_m12 || !scratch || !states)
+    return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  ScratchView sv = carve_scratch(scratch, B, N);
+  const PushCam cam = make_cam(cam_m12, global_scale);
+  const size_t tape_step = carve_tape(nullptr, B, N).bytes;
+  const long long sstride = (long long)T * N * 3;
+  for (int t = 0; t < T; ++t) {
+    const float* s_cur = t == 0 ? s0 : states + (size_t)(t - 1) * N * 3;
+    const long long cur_stride = t == 0 ? (long long)N * 3 : sstride;
+    TapeView tv;
+    Csr csr = sv.csr;
+    if (tape) { tv = carve_tape(static_cast<char*>(tape) + (size_t)t * tape_step, B, N); csr = tv.csr; }
+    int e = launch_nbr_search(s_cur, cur_stride, nullptr, actions + (size_t)t * 4, T * 4, cam, sv.ws.s_delta,
+                              nullptr, B, N, adj_thresh * adj_thresh, csr, st);
+    if (e) return e;
+    e = launch_forward(wpack, attr, dens, s_cur, cur_stride, sv.ws.s_delta, csr, sv.ws, tape ? &tv.mk : nullptr,
+                       states + (size_t)t * N * 3, sstride, B, N, st);
+    if (e) return e;
+  }
+  return 0;
+}
+
+int pile_forward_relations(const float* wpack, const float* attr, const float* dens, const float* s_cur,
+                           const float* s_delta, const int* rowptr, const int* col, const int* row, int B, int N,
+                           void* scratch, void* tape, float* s_pred, void* stream) {
+  if (bad_dims(B, N) || !wpack || !attr || !dens || !s_cur || !s_delta || !rowptr || !col || !row || !scratch ||
+      !s_pred)
+    return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  ScratchView sv = carve_scratch(scratch, B, N);
+  Csr csr{const_cast<int*>(rowptr), const_cast<int*>(col), const_cast<int*>(row), nullptr, nullptr, nullptr};
+  TapeView tv;
+  if (tape) {
+    tv = carve_tape(tape, B, N);
+    const size_t E = (size_t)B * KMAX * N;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(tv.csr.rowptr, rowptr, sizeof(int) * (size_t)B * (N + 1), cudaMemcpyDeviceToDevice, st))) return (int)e;
+    if ((e = cudaMemcpyAsync(tv.csr.col, col, sizeof(int) * E, cudaMemcpyDeviceToDevice, st))) return (int)e;
+    if ((e = cudaMemcpyAsync(tv.csr.row, row, sizeof(int) * E, cudaMemcpyDeviceToDevice, st))) return (int)e;
+    csr = tv.csr;
+    int r = launch_transpose_relations(csr, B, N, st);
+    if (r) return r;
+  }
+  return launch_forward(wpack, attr, dens, s_cur, (long long)N * 3, s_delta, csr, sv.ws, tape ? &tv.mk : nullptr,
+                        s_pred, (long long)N * 3, B, N, st);
+}
+
+int pile_gen_s_delta_backward(const float* s_cur, const float* action, int act_stride, const float* cam_m12,
+                              float global_scale, int B, int N, const float* g_s_delta, float* g_s_cur,
+                              float* g_action, int g_act_stride, void* stream) {
+  if (B <= 0 || N <= 0 || !s_cur || !action || !cam_m12 || !g_s_delta || !g_s_cur || !g_action)
+    return (int)cudaErrorInvalidValue;
+  return launch_gen_s_delta_bwd(s_cur, (long long)N * 3, action, act_stride, make_cam(cam_m12, global_scale), B, N,
+                                g_s_delta, g_s_cur, (long long)N * 3, g_action, g_act_stride, (cudaStream_t)stream);
+}
+
+namespace {
+struct BwdView {
+  void* kernels;      // launch_step_backward scratch
+  float* g_cur;       // [B,N,3]
+  float* g_sd;        // [B,N,3]
+  size_t bytes;
+};
+BwdView carve_bwd_view(void* p, int B, int N) {
+  Carver c(p);
+  BwdView v;
+  v.kernels = c.take<char>(bwd_scratch_bytes(B, N));
+  v.g_cur = c.take<float>((size_t)B * N * 3);
+  v.g_sd = c.take<float>((size_t)B * N * 3);
+  v.bytes = c.off;
+  return v;
+}
+}  // namespace
+
+long long pile_bwd_scratch_bytes(int B, int N) {
+  if (bad_dims(B, N)) return -1;
+  return (long long)carve_bwd_view(nullptr, B, N).bytes;
+}
+
+int pile_step_backward(const float* wpack, const float* dens, const void* tape, int B, int N, const float* g_pred,
+                       float* g_s_cur, float* g_s_delta, void* bwd_scratch, void* stream) {
+  (void)dens;
+  if (bad_dims(B, N) || !wpack || !tape || !g_pred || !g_s_cur || !g_s_delta || !bwd_scratch)
+    return (int)cudaErrorInvalidValue;
+  TapeView tv = carve_tape(const_cast<void*>(tape), B, N);
+  BwdView bv = carve_bwd_view(bwd_scratch, B, N);
+  return launch_step_backward(wpack, tv.csr, tv.mk, g_pred, (long long)N * 3, g_s_cur, g_s_delta, bv.kernels, B, N,
+                              (cudaStream_t)stream);
+}
+
+int pile_rollout_backward(const float* wpack, const float* dens, const float* s0, const float* actions,
+                          const float* cam_m12, float global_scale, int B, int N, int T, const void* tape,
+                          const float* states, float* g_states, void* bwd_scratch, float* g_actions,
+                          void* stream) {
+  (void)dens;
+  if (bad_dims(B, N) || T <= 0 || !wpack || !s0 || !actions || !cam_m12 || !tape || !states || !g_states ||
+      !bwd_scratch || !g_actions)
+    return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  const PushCam cam = make_cam(cam_m12, global_scale);
+  const size_t tape_step = carve_tape(nullptr, B, N).bytes;
+  const long long sstride = (long long)T * N * 3;
+  BwdView bv = carve_bwd_view(bwd_scratch, B, N);
+  for (int t = T - 1; t >= 0; --t) {
+    TapeView tv = carve_tape(const_cast<char*>(static_cast<const char*>(tape)) + (size_t)t * tape_step, B, N);
+    const float* s_cur = t == 0 ? s0 : states + (size_t)(t - 1) * N * 3;
+    const long long cur_stride = t == 0 ? (long long)N * 3 : sstride;
+    int e = launch_step_backward(wpack, tv.csr, tv.mk, g_states + (size_t)t * N * 3, sstride, bv.g_cur, bv.g_sd,
+                                 bv.kernels, B, N, st);
+    if (e) return e;
+    e = launch_gen_s_delta_bwd(s_cur, cur_stride, actions + (size_t)t * 4, T * 4, cam, B, N, bv.g_sd, bv.g_cur,
+                               (long long)N * 3, g_actions + (size_t)t * 4, T * 4, st);
+    if (e) return e;
+    if (t > 0) {   // dL/ds_cur of step t joins the upstream gradient of step t-1's output
+      e = launch_add_strided(g_states + (size_t)(t - 1) * N * 3, sstride, bv.g_cur, (long long)N * 3, B, N * 3, st);
+      if (e) return e;
+    }
+  }
+  return 0;
+}
+
+int pile_reward(const float* states, long long n_states, long long state_stride, int N, const float* goal_img,
+                int Hh, int Ww, const float* goal_coor, int M, const float* cam, float off_x, float off_y,
+                int normalize, float* reward, int* argmin, void* stream) {
+  if (n_states < 0 || N <= 0 || M <= 0 || !states || !goal_img || !goal_coor || !cam || !reward)
+    return (int)cudaErrorInvalidValue;
+  return launch_reward(states, n_states, state_stride, N, goal_img, Hh, Ww, goal_coor, M, cam[0], cam[1], cam[2],
+                       cam[3], off_x, off_y, normalize, reward, argmin, (cudaStream_t)stream);
+}
+
+int pile_reward_backward(const float* states, long long n_states, long long state_stride, int N,
+                         const float* goal_img, int Hh, int Ww, const float* goal_coor, int M, const float* cam,
+                         float off_x, float off_y, int normalize, const float* g_reward, const int* argmin,
+                         float* g_states, long long g_stride, int accumulate, void* stream) {
+  if (n_states < 0 || N <= 0 || M <= 0 || !states || !goal_img || !goal_coor || !cam || !g_reward || !argmin ||
+      !g_states)
+    return (int)cudaErrorInvalidValue;
+  return launch_reward_bwd(states, n_states, state_stride, N, goal_img, Hh, Ww, goal_coor, M, cam[0], cam[1],
+                           cam[2], cam[3], off_x, off_y, normalize, g_reward, argmin, g_states, g_stride,
+                           accumulate, (cudaStream_t)stream);
+}
+
+int pile_mppi_num_chunks(int S) { return mppi_num_chunks(S); }
+
+int pile_mppi_partials(const float* reward, const float* acts, int S, int T, float reward_weight, float* partials,
+                       void* stream) {
+  if (S <= 0 || T <= 0 || !reward || !acts || !partials) return (int)cudaErrorInvalidValue;
+  return launch_mppi_partials(reward, acts, S, T, reward_weight, partials, (cudaStream_t)stream);
+}
+
+int pile_mppi_combine(const float* partials, int P, int T, float* out, void* stream) {
+  if (P <= 0 || T <= 0 || !partials || !out) return (int)cudaErrorInvalidValue;
+  return launch_mppi_combine(partials, P, T, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// Internal launch interface between the translation units of libpilegnn (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace pile {
+
+// per-step relation structure of all samples
+struct Csr {
+  int* rowptr;   // [B, N+1]
+  int* col;      // [B, KMAX*N] sender
+  int* row;      // [B, KMAX*N] receiver
+  int* trowptr;  // [B, N+1]    sender-major transpose (nullable)
+  int* trecv;    // [B, KMAX*N]
+  int* tedge;    // [B, KMAX*N]
+};
+
+// ReLU sign bits kept for the dgrad-only backward: one byte per (row, 8-column block)
+struct Masks {
+  uint8_t* pe0;        // [B*N, 8]
+  uint8_t* pe1;
+  uint8_t* eff[PSTEP]; // [B*N, 8]
+  uint8_t* q;
+  uint8_t* re0;        // [B*KMAX*N, 8]
+  uint8_t* re1;
+  uint8_t* re2;
+  uint8_t* edge[PSTEP];
+};
+
+// scratch of one forward step (reused across steps)
+struct StepScratch {
+  float* s_delta;  // [B, N, 3]
+  float* Ce;       // [B*KMAX*N, H]
+  float* Cp;       // [B*N, H]
+  float* eff;      // [B*N, H]
+  float* Pr[2];    // [B*N, H] ping-pong
+  float* Ps[2];
+};
+
+int launch_gen_s_delta(const float* s_cur, long long s_stride, const float* action, int act_stride,
+                       const PushCam& cam, int B, int N, float* s_delta, cudaStream_t st);
+size_t nbr_smem_bytes(int N);
+// s_delta either given (s_delta_in) or computed from `action` and written to s_delta_out
+int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_delta_in, const float* action,
+                      int act_stride, const PushCam& cam, float* s_delta_out, const int* particle_nums, int B,
+                      int N, float thr, const Csr& csr, cudaStream_t st);
+
+// forward of the propagation network on a prepared CSR; s_cur / s_out are [B, N, 3] with a per-sample
+// stride in floats (so slices of [B, T, N, 3] work in place)
+int launch_forward(const float* wpack, const float* attr, const float* dens, const float* s_cur,
+                   long long s_cur_stride, const float* s_delta, const Csr& csr, const StepScratch& ws,
+                   const Masks* masks, float* s_out, long long s_out_stride, int B, int N, cudaStream_t st);
+
+int launch_reward(const float* states, long long n_states, long long state_stride, int N, const float* goal_img,
+                  int Hh, int Ww, const float* goal_coor, int M, float fx, float fy, float cx, float cy,
+                  float off_x, float off_y, int normalize, float* reward, int* argmin_out, cudaStream_t st);
+int launch_reward_bwd(const float* states, long long n_states, long long state_stride, int N, const float* goal_img,
+                      int Hh, int Ww, const float* goal_coor, int M, float fx, float fy, float cx, float cy,
+                      float off_x, float off_y, int normalize, const float* g_reward, const int* argmin_in,
+                      float* g_states, long long g_stride, int accumulate, cudaStream_t st);
+int mppi_num_chunks(int S);
+int launch_mppi_partials(const float* reward, const float* acts, int S, int T, float weight, float* part,
+                         cudaStream_t st);
+int launch_mppi_combine(const float* part, int P, int T, float* out, cudaStream_t st);
+
+size_t bwd_scratch_bytes(int B, int N);
+// backward of one model step: g_pred [B,N,3] (strided) -> g_s_cur [B,N,3] dense (overwritten, includes the
+// residual), g_s_delta [B,N,3] dense (overwritten)
+int launch_step_backward(const float* wpack, const Csr& csr, const Masks& mk, const float* g_pred,
+                         long long g_stride, float* g_s_cur, float* g_s_delta, void* scratch, int B, int N,
+                         cudaStream_t st);
+int launch_gen_s_delta_bwd(const float* s_cur, long long s_stride, const float* action, int act_stride,
+                           const PushCam& cam, int B, int N, const float* g_sd, float* g_s_cur, long long g_stride,
+                           float* g_action, int g_act_stride, cudaStream_t st);
+int launch_transpose_relations(const Csr& csr, int B, int N, cudaStream_t st);
+int launch_add_strided(float* dst, long long d_stride, const float* src, long long s_stride, int B, int per,
+                       cudaStream_t st);
+
+}  // namespace pile

@@ -1,0 +1,440 @@
+// K1/K2: pusher influence (s_delta) and the radius ^ top-10 neighbour search.
+//
+// Replaces the dense O(N^2) tensors of reference model/gnn_dyn.py:221-251 (repeat -> dis -> topk ->
+// scatter -> nonzero -> one-hot Rr/Rs) by one CTA per sample that keeps the pushed positions in
+// shared memory and emits a compact int32 CSR (+COO receiver ids, + optional sender-major transpose
+// for the deterministic backward scatter).  The relation SET is bit-exact w.r.t. the reference:
+// distances use separately rounded fp32 mul/add in the reference's x,y,z order on
+// p = fl(s_cur + s_delta); ties at the 10th place resolve to the lower sender index.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pile {
+
+struct PushFrame {
+  float sx, sy, sz, ex, ey, ez, ux, uy, uz, len;
+};
+
+__device__ __forceinline__ void cam_point(const PushCam& c, float wx, float wy, float wz, float& x, float& y,
+                                          float& z) {
+  x = __fdiv_rn(c.m[0] * wx + c.m[1] * wy + c.m[2] * wz + c.m[3], c.global_scale);
+  y = __fdiv_rn(c.m[4] * wx + c.m[5] * wy + c.m[6] * wz + c.m[7], c.global_scale);
+  z = __fdiv_rn(c.m[8] * wx + c.m[9] * wy + c.m[10] * wz + c.m[11], c.global_scale);
+}
+
+// planners.py:218-240: action (sx,sy,ex,ey) -> start/end in the camera frame, unit push direction
+__device__ __forceinline__ PushFrame make_push_frame(const PushCam& c, const float* __restrict__ act) {
+  PushFrame f;
+  cam_point(c, act[0], 0.f, -act[1], f.sx, f.sy, f.sz);
+  cam_point(c, act[2], 0.f, -act[3], f.ex, f.ey, f.ez);
+  const float dx = __fsub_rn(f.ex, f.sx), dy = __fsub_rn(f.ey, f.sy), dz = __fsub_rn(f.ez, f.sz);
+  f.len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  f.ux = __fdiv_rn(dx, f.len);
+  f.uy = __fdiv_rn(dy, f.len);
+  f.uz = __fdiv_rn(dz, f.len);
+  return f;
+}
+
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+
+// planners.py:241-254 for one particle
+__device__ __forceinline__ void push_delta(const PushCam& c, const PushFrame& f, float x, float y, float z,
+                                           float& ox, float& oy, float& oz) {
+  const float rx = __fsub_rn(x, f.sx), ry = __fsub_rn(y, f.sy), rz = __fsub_rn(z, f.sz);
+  const float across = dot3_rn(rx, ry, rz, -f.uy, f.ux, 0.f);
+  const float along = dot3_rn(rx, ry, rz, f.ux, f.uy, f.uz);
+  const float hard = (along < f.len && along > 0.f) ? 1.f : 0.f;
+  const float excess = fmaxf(fmaxf(__fsub_rn(-c.pusher_w, across), 0.f), fmaxf(__fsub_rn(across, c.pusher_w), 0.f));
+  const float soft = expf(__fdiv_rn(-excess, c.decay));
+  const float to_end = dot3_rn(__fsub_rn(f.ex, x), __fsub_rn(f.ey, y), __fsub_rn(f.ez, z), f.ux, f.uy, f.uz);
+  ox = __fmul_rn(__fmul_rn(__fmul_rn(to_end, f.ux), hard), soft);
+  oy = __fmul_rn(__fmul_rn(__fmul_rn(to_end, f.uy), hard), soft);
+  oz = __fmul_rn(__fmul_rn(__fmul_rn(to_end, f.uz), hard), soft);
+}
+
+__global__ void k_gen_s_delta(const float* __restrict__ s_cur, long long s_stride,
+                              const float* __restrict__ action, int act_stride,
+                              PushCam cam, int N, float* __restrict__ s_delta) {
+  const int b = blockIdx.x;
+  const PushFrame f = make_push_frame(cam, action + (size_t)b * act_stride);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float* p = s_cur + (long long)b * s_stride + i * 3;
+    float ox, oy, oz;
+    push_delta(cam, f, p[0], p[1], p[2], ox, oy, oz);
+    float* o = s_delta + ((size_t)b * N + i) * 3;
+    o[0] = ox; o[1] = oy; o[2] = oz;
+  }
+}
+
+// dis[i][j] exactly as torch evaluates sum((p_j - p_i)^2, -1)   (gnn_dyn.py:224-230)
+__device__ __forceinline__ float sqdist_rn(float xi, float yi, float zi, float xj, float yj, float zj) {
+  const float dx = __fsub_rn(xj, xi), dy = __fsub_rn(yj, yi), dz = __fsub_rn(zj, zi);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+#define PILE_CE(a, b)                                   \
+  {                                                     \
+    const int lo__ = min(id[a], id[b]);                 \
+    const int hi__ = max(id[a], id[b]);                 \
+    id[a] = lo__;                                       \
+    id[b] = hi__;                                       \
+  }
+
+// 29-comparator sorting network for 10 keys (verified with the 0-1 principle in tests/test_host_logic.py)
+__device__ __forceinline__ void sort10(int (&id)[KMAX]) {
+  PILE_CE(0, 8) PILE_CE(1, 9) PILE_CE(2, 7) PILE_CE(3, 5) PILE_CE(4, 6)
+  PILE_CE(0, 2) PILE_CE(1, 4) PILE_CE(5, 8) PILE_CE(7, 9)
+  PILE_CE(0, 3) PILE_CE(2, 4) PILE_CE(5, 7) PILE_CE(6, 9)
+  PILE_CE(0, 1) PILE_CE(3, 6) PILE_CE(8, 9)
+  PILE_CE(1, 5) PILE_CE(2, 3) PILE_CE(4, 8) PILE_CE(6, 7)
+  PILE_CE(1, 2) PILE_CE(3, 5) PILE_CE(4, 6) PILE_CE(7, 8)
+  PILE_CE(2, 3) PILE_CE(4, 5) PILE_CE(6, 7)
+  PILE_CE(3, 4) PILE_CE(5, 6)
+}
+
+constexpr int NBR_THREADS = 256;
+
+// exclusive scan of one int per thread over the CTA; returns the exclusive prefix, total via *total
+__device__ __forceinline__ int block_exscan(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < (NBR_THREADS / 32) ? warp_sums[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < NBR_THREADS / 32) warp_sums[lane] = winc - w;
+    if (lane == 31) *total = winc;
+  }
+  __syncthreads();
+  return warp_sums[warp] + inc - v;
+}
+
+// One CTA per sample.  Optional fused s_delta (action != nullptr).
+// dynamic smem: px,py,pz[N] | cutd[N] | cuti[N] | deg[N] | roff[N+1] | sel[N*KMAX]
+__global__ void __launch_bounds__(NBR_THREADS)
+k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* __restrict__ s_delta_in,
+             const float* __restrict__ action, int act_stride, PushCam cam, float* __restrict__ s_delta_out,
+             const int* __restrict__ particle_nums, int N, float thr,
+             int* __restrict__ rowptr, int* __restrict__ col, int* __restrict__ row,
+             int* __restrict__ trowptr, int* __restrict__ trecv, int* __restrict__ tedge) {
+  extern __shared__ float smem[];
+  float* px = smem;
+  float* py = px + N;
+  float* pz = py + N;
+  float* cutd = pz + N;
+  int* cuti = reinterpret_cast<int*>(cutd + N);
+  int* deg = cuti + N;
+  int* roff = deg + N;           // N+1
+  int* sel = roff + (N + 1);     // N*KMAX
+  __shared__ int warp_sums[NBR_THREADS / 32];
+  __shared__ int total_s;
+
+  const int b = blockIdx.x;
+  const int nvalid = particle_nums ? min(particle_nums[b], N) : N;
+  const size_t base = (size_t)b * N;
+
+  PushFrame f;
+  if (action) f = make_push_frame(cam, action + (size_t)b * act_stride);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float* p = s_cur + (long long)b * s_stride + i * 3;
+    const float x = p[0], y = p[1], z = p[2];
+    float dx, dy, dz;
+    if (action) {
+      push_delta(cam, f, x, y, z, dx, dy, dz);
+      float* o = s_delta_out + (base + i) * 3;
+      o[0] = dx; o[1] = dy; o[2] = dz;
+    } else {
+      const float* d = s_delta_in + (base + i) * 3;
+      dx = d[0]; dy = d[1]; dz = d[2];
+    }
+    px[i] = __fadd_rn(x, dx);
+    py[i] = __fadd_rn(y, dy);
+    pz[i] = __fadd_rn(z, dz);
+  }
+  __syncthreads();
+
+  // pass 1: per receiver, the (up to) 10 nearest in-radius senders, then sort them by index
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    float bd[KMAX];
+    int id[KMAX];
+#pragma unroll
+    for (int s = 0; s < KMAX; ++s) { bd[s] = __int_as_float(0x7f800000); id[s] = 0x7fffffff; }
+    const float xi = px[i], yi = py[i], zi = pz[i];
+    for (int j = 0; j < N; ++j) {
+      const float d = sqdist_rn(xi, yi, zi, px[j], py[j], pz[j]);
+      if (d < thr && d < bd[KMAX - 1]) {
+        // insert keeping (d, index) ascending; equal d keeps the earlier (lower) index first
+#pragma unroll
+        for (int s = KMAX - 1; s > 0; --s) {
+          const bool shift = d < bd[s - 1];
+          const bool here = !shift && d < bd[s];
+          const float nd = shift ? bd[s - 1] : (here ? d : bd[s]);
+          const int ni = shift ? id[s - 1] : (here ? j : id[s]);
+          bd[s] = nd; id[s] = ni;
+        }
+        if (d < bd[0]) { bd[0] = d; id[0] = j; }
+      }
+    }
+    cutd[i] = bd[KMAX - 1];          // +inf when fewer than 10 in radius
+    cuti[i] = id[KMAX - 1];
+    int n = 0;
+    if (i < nvalid) {
+#pragma unroll
+      for (int s = 0; s < KMAX; ++s) {
+        if (id[s] >= nvalid) id[s] = 0x7fffffff;    // padded particles are dropped AFTER top-k (gnn_dyn.py:238-241)
+        n += id[s] != 0x7fffffff;
+      }
+      sort10(id);
+    }
+#pragma unroll
+    for (int s = 0; s < KMAX; ++s) sel[i * KMAX + s] = (i < nvalid) ? id[s] : 0x7fffffff;
+    deg[i] = n;
+  }
+  __syncthreads();
+
+  // CSR offsets
+  const int per = (N + NBR_THREADS - 1) / NBR_THREADS;
+  {
+    const int lo = min(threadIdx.x * per, N), hi = min(lo + per, N);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += deg[i];
+    int run = block_exscan(s, warp_sums, &total_s);
+    for (int i = lo; i < hi; ++i) { roff[i] = run; run += deg[i]; }
+    if (threadIdx.x == 0) roff[N] = total_s;
+  }
+  __syncthreads();
+  int* rp = rowptr + (size_t)b * (N + 1);
+  for (int i = threadIdx.x; i <= N; i += blockDim.x) rp[i] = roff[i];
+  const size_t ebase = (size_t)b * KMAX * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int o = roff[i], n = deg[i];
+    for (int s = 0; s < n; ++s) {
+      col[ebase + o + s] = sel[i * KMAX + s];
+      row[ebase + o + s] = i;
+    }
+  }
+
+  if (trowptr == nullptr) return;
+  // sender-major transpose: for sender j the receivers i (ascending) with j in nbr(i), and the edge id
+  __syncthreads();
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    int n = 0;
+    if (j < nvalid) {
+      const float xj = px[j], yj = py[j], zj = pz[j];
+      for (int i = 0; i < nvalid; ++i) {
+        const float d = sqdist_rn(px[i], py[i], pz[i], xj, yj, zj);
+        const float cd = cutd[i];
+        n += (d < thr) && (d < cd || (d == cd && j <= cuti[i]));
+      }
+    }
+    deg[j] = n;     // reuse as in-degree
+  }
+  __syncthreads();
+  {
+    const int lo = min(threadIdx.x * per, N), hi = min(lo + per, N);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += deg[i];
+    int run = block_exscan(s, warp_sums, &total_s);
+    int* trp = trowptr + (size_t)b * (N + 1);
+    for (int i = lo; i < hi; ++i) { const int d = deg[i]; trp[i] = run; deg[i] = run; run += d; }
+    if (threadIdx.x == 0) trp[N] = total_s;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nvalid; j += blockDim.x) {
+    const float xj = px[j], yj = py[j], zj = pz[j];
+    int o = deg[j];
+    for (int i = 0; i < nvalid; ++i) {
+      const float d = sqdist_rn(px[i], py[i], pz[i], xj, yj, zj);
+      const float cd = cutd[i];
+      if ((d < thr) && (d < cd || (d == cd && j <= cuti[i]))) {
+        int pos = 0;
+#pragma unroll
+        for (int s = 0; s < KMAX; ++s) pos += sel[i * KMAX + s] < j;
+        trecv[ebase + o] = i;
+        tedge[ebase + o] = roff[i] + pos;
+        ++o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of the pusher model: g_s_delta [B,N,3] -> g_s_cur (+=) and g_action [B,4].
+// The hard along-push mask and the push length inside it carry no gradient (planners.py:248).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NBR_THREADS)
+k_gen_s_delta_bwd(const float* __restrict__ s_cur, long long s_stride, const float* __restrict__ action,
+                  int act_stride, PushCam cam, int N, const float* __restrict__ g_sd, float* __restrict__ g_s_cur,
+                  long long g_stride, float* __restrict__ g_action, int g_act_stride) {
+  __shared__ float red[9][NBR_THREADS / 32];
+  const int b = blockIdx.x;
+  const PushFrame f = make_push_frame(cam, action + (size_t)b * act_stride);
+  float gu[3] = {0.f, 0.f, 0.f}, ge[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float* p = s_cur + (long long)b * s_stride + i * 3;
+    const float x = p[0], y = p[1], z = p[2];
+    const float* g = g_sd + ((size_t)b * N + i) * 3;
+    const float g0 = g[0], g1 = g[1], g2 = g[2];
+    const float rx = x - f.sx, ry = y - f.sy, rz = z - f.sz;
+    const float vx = -f.uy, vy = f.ux;
+    const float across = rx * vx + ry * vy;
+    const float along = rx * f.ux + ry * f.uy + rz * f.uz;
+    const float hard = (along < f.len && along > 0.f) ? 1.f : 0.f;
+    const float excess = fmaxf(fmaxf(-cam.pusher_w - across, 0.f), fmaxf(across - cam.pusher_w, 0.f));
+    const float soft = expf(-excess / cam.decay);
+    const float ex = f.ex - x, ey = f.ey - y, ez = f.ez - z;
+    const float to_end = ex * f.ux + ey * f.uy + ez * f.uz;
+    const float c = hard * soft;
+    const float gdotu = g0 * f.ux + g1 * f.uy + g2 * f.uz;
+    const float g_te = c * gdotu;
+    const float g_soft = to_end * gdotu * hard;
+    const float g_excess = -g_soft * soft / cam.decay;
+    const float g_across = g_excess * (across > cam.pusher_w ? 1.f : (across < -cam.pusher_w ? -1.f : 0.f));
+    // out = to_end * c * u
+    gu[0] += to_end * c * g0 + g_te * ex;
+    gu[1] += to_end * c * g1 + g_te * ey;
+    gu[2] += to_end * c * g2 + g_te * ez;
+    // v = (-u.y, u.x, 0): across = rel . v
+    gu[1] -= g_across * rx;
+    gu[0] += g_across * ry;
+    ge[0] += g_te * f.ux; ge[1] += g_te * f.uy; ge[2] += g_te * f.uz;
+    const float grx = g_across * vx, gry = g_across * vy;
+    gs[0] -= grx; gs[1] -= gry;
+    float* o = g_s_cur + (long long)b * g_stride + i * 3;
+    o[0] += grx - g_te * f.ux;
+    o[1] += gry - g_te * f.uy;
+    o[2] += -g_te * f.uz;
+  }
+  float v[9] = {gu[0], gu[1], gu[2], ge[0], ge[1], ge[2], gs[0], gs[1], gs[2]};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) red[k][warp] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t[9];
+    for (int k = 0; k < 9; ++k) {
+      t[k] = 0.f;
+      for (int w = 0; w < NBR_THREADS / 32; ++w) t[k] += red[k][w];
+    }
+    // u = p / |p|
+    const float udg = f.ux * t[0] + f.uy * t[1] + f.uz * t[2];
+    const float gp[3] = {(t[0] - f.ux * udg) / f.len, (t[1] - f.uy * udg) / f.len, (t[2] - f.uz * udg) / f.len};
+    const float gE[3] = {t[3] + gp[0], t[4] + gp[1], t[5] + gp[2]};
+    const float gS[3] = {t[6] - gp[0], t[7] - gp[1], t[8] - gp[2]};
+    // start = (M[:,0] a0 - M[:,2] a1 + M[:,3]) / gs ; end likewise with a2, a3
+    const float inv = 1.f / cam.global_scale;
+    float* ga = g_action + (size_t)b * g_act_stride;
+    ga[0] = (gS[0] * cam.m[0] + gS[1] * cam.m[4] + gS[2] * cam.m[8]) * inv;
+    ga[1] = -(gS[0] * cam.m[2] + gS[1] * cam.m[6] + gS[2] * cam.m[10]) * inv;
+    ga[2] = (gE[0] * cam.m[0] + gE[1] * cam.m[4] + gE[2] * cam.m[8]) * inv;
+    ga[3] = -(gE[0] * cam.m[2] + gE[1] * cam.m[6] + gE[2] * cam.m[10]) * inv;
+  }
+}
+
+int launch_gen_s_delta_bwd(const float* s_cur, long long s_stride, const float* action, int act_stride,
+                           const PushCam& cam, int B, int N, const float* g_sd, float* g_s_cur, long long g_stride,
+                           float* g_action, int g_act_stride, cudaStream_t st) {
+  k_gen_s_delta_bwd<<<B, NBR_THREADS, 0, st>>>(s_cur, s_stride, action, act_stride, cam, N, g_sd, g_s_cur, g_stride,
+                                               g_action, g_act_stride);
+  PILE_CHECK_LAUNCH();
+  return 0;
+}
+
+// sender-major transpose of caller-provided relation lists (dense Rr/Rs shim path): one CTA per sample,
+// thread per sender, edges visited in ascending id so the result is deterministic
+__global__ void k_transpose_relations(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                      const int* __restrict__ row, int N, int* __restrict__ trowptr,
+                                      int* __restrict__ trecv, int* __restrict__ tedge) {
+  extern __shared__ int cnt[];    // [N+1]
+  const int b = blockIdx.x;
+  const int ne = rowptr[(size_t)b * (N + 1) + N];
+  const size_t ebase = (size_t)b * KMAX * N;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    int n = 0;
+    for (int e = 0; e < ne; ++e) n += col[ebase + e] == j;
+    cnt[j] = n;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int j = 0; j < N; ++j) { const int n = cnt[j]; cnt[j] = run; run += n; }
+    cnt[N] = run;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j <= N; j += blockDim.x) trowptr[(size_t)b * (N + 1) + j] = cnt[j];
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    int o = cnt[j];
+    for (int e = 0; e < ne; ++e)
+      if (col[ebase + e] == j) { trecv[ebase + o] = row[ebase + e]; tedge[ebase + o] = e; ++o; }
+  }
+}
+
+int launch_transpose_relations(const Csr& csr, int B, int N, cudaStream_t st) {
+  k_transpose_relations<<<B, 256, (N + 1) * sizeof(int), st>>>(csr.rowptr, csr.col, csr.row, N, csr.trowptr,
+                                                               csr.trecv, csr.tedge);
+  PILE_CHECK_LAUNCH();
+  return 0;
+}
+
+// dst[b, i, :] += src[b, i, :] with per-sample strides
+__global__ void k_add_strided(float* __restrict__ dst, long long d_stride, const float* __restrict__ src,
+                              long long s_stride, int per, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long b = i / per, k = i % per;
+  dst[b * d_stride + k] += src[b * s_stride + k];
+}
+
+int launch_add_strided(float* dst, long long d_stride, const float* src, long long s_stride, int B, int per,
+                       cudaStream_t st) {
+  const long long total = (long long)B * per;
+  k_add_strided<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dst, d_stride, src, s_stride, per, total);
+  PILE_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_gen_s_delta(const float* s_cur, long long s_stride, const float* action, int act_stride,
+                       const PushCam& cam, int B, int N, float* s_delta, cudaStream_t st) {
+  k_gen_s_delta<<<B, 128, 0, st>>>(s_cur, s_stride, action, act_stride, cam, N, s_delta);
+  PILE_CHECK_LAUNCH();
+  return 0;
+}
+
+size_t nbr_smem_bytes(int N) { return sizeof(float) * (size_t)(3 * N + N) + sizeof(int) * (size_t)(N + N + N + 1 + N * KMAX); }
+
+int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_delta_in, const float* action,
+                      int act_stride, const PushCam& cam, float* s_delta_out, const int* particle_nums, int B,
+                      int N, float thr, const Csr& csr, cudaStream_t st) {
+  const size_t smem = nbr_smem_bytes(N);
+  if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_nbr_search, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  k_nbr_search<<<B, NBR_THREADS, smem, st>>>(s_cur, s_stride, s_delta_in, action, act_stride, cam, s_delta_out,
+                                             particle_nums, N, thr, csr.rowptr, csr.col, csr.row, csr.trowptr,
+                                             csr.trecv, csr.tedge);
+  PILE_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace pile

@@ -1,0 +1,341 @@
+"""Thin torch-facing wrappers over the libpilegnn C ABI (include/pile_gnn.h).
+
+torch is used for device memory and streams only; every compute call goes to the CUDA
+library and raises if it is missing or fails -- there is no CPU or eager fallback.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+KMAX = 10
+
+# must list the slots of enum WSlot (csrc/common.cuh) in order; checked against the library at pack time
+WSLOTS = ["W_PE0T", "B_PE0", "W_PE1T", "B_PE1", "W_RE0T", "B_RE0", "W_RE1T", "B_RE1", "W_RE2T", "B_RE2",
+          "W_ET", "W_RT", "W_ST", "WD_RP", "B_RP", "W_PT", "W_AT", "WD_PP", "B_PP", "W_V0T", "B_V0", "W_V1T", "B_V1",
+          "W_PE0", "W_PE1", "W_RE0", "W_RE1", "W_RE2", "W_E", "W_R", "W_S", "W_P", "W_A", "W_V0", "W_V1"]
+
+CKPT_KEYS = [  # reference checkpoint layout, SURVEY.md §8b
+    "model.particle_encoder.model.0", "model.particle_encoder.model.2",
+    "model.relation_encoder.model.0", "model.relation_encoder.model.2", "model.relation_encoder.model.4",
+    "model.particle_propagator.linear", "model.relation_propagator.linear",
+    "model.particle_predictor.linear_0", "model.particle_predictor.linear_1"]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t, device=None):
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    if device is not None and t.device != device:
+        t = t.to(device)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise _lib.PileLibraryError("%s must live on a CUDA device: the pile-GNN path has no CPU implementation" % name)
+
+
+def _pad_rows(m, rows):
+    out = m.new_zeros(rows, m.shape[1])
+    out[:m.shape[0]] = m
+    return out
+
+
+def _pad_cols(m, cols):
+    out = m.new_zeros(m.shape[0], cols)
+    out[:, :m.shape[1]] = m
+    return out
+
+
+def pack_weights(state, device):
+    """18 checkpoint tensors -> the packed float buffer the kernels read (layout: csrc/common.cuh)."""
+    lib = _lib.load()
+    H = lib.pile_nf_effect()
+    g = {k: _f32(v.detach(), device) for k, v in state.items()}
+
+    def w(name):
+        return g[name + ".weight"], g[name + ".bias"]
+    pe0, bpe0 = w(CKPT_KEYS[0]); pe1, bpe1 = w(CKPT_KEYS[1])
+    re0, bre0 = w(CKPT_KEYS[2]); re1, bre1 = w(CKPT_KEYS[3]); re2, bre2 = w(CKPT_KEYS[4])
+    pp, bpp = w(CKPT_KEYS[5]); rp, brp = w(CKPT_KEYS[6])
+    v0, bv0 = w(CKPT_KEYS[7]); v1, bv1 = w(CKPT_KEYS[8])
+    if pe1.shape != (H, H) or rp.shape != (H, 3 * H + 1) or pp.shape != (H, 2 * H + 1):
+        raise _lib.PileLibraryError("libpilegnn is compiled for nf_effect=%d, checkpoint has %d" % (H, pe1.shape[0]))
+    blocks = {
+        "W_PE0T": _pad_rows(pe0.t(), 8), "B_PE0": bpe0, "W_PE1T": pe1.t(), "B_PE1": bpe1,
+        "W_RE0T": _pad_rows(re0.t(), 8), "B_RE0": bre0, "W_RE1T": re1.t(), "B_RE1": bre1, "W_RE2T": re2.t(), "B_RE2": bre2,
+        "W_ET": rp[:, 0:H].t(), "W_RT": rp[:, H:2 * H].t(), "W_ST": rp[:, 2 * H:3 * H].t(), "WD_RP": rp[:, 3 * H], "B_RP": brp,
+        "W_PT": pp[:, 0:H].t(), "W_AT": pp[:, H:2 * H].t(), "WD_PP": pp[:, 2 * H], "B_PP": bpp,
+        "W_V0T": v0.t(), "B_V0": bv0, "W_V1T": _pad_cols(v1.t(), 4), "B_V1": torch.cat([bv1, bv1.new_zeros(1)]),
+        "W_PE0": _pad_cols(pe0, 8), "W_PE1": pe1, "W_RE0": _pad_cols(re0, 8), "W_RE1": re1, "W_RE2": re2,
+        "W_E": rp[:, 0:H], "W_R": rp[:, H:2 * H], "W_S": rp[:, 2 * H:3 * H], "W_P": pp[:, 0:H], "W_A": pp[:, H:2 * H],
+        "W_V0": v0, "W_V1": _pad_rows(v1, 4),
+    }
+    if lib.pile_wpack_num_slots() != len(WSLOTS):
+        raise _lib.PileLibraryError("weight-slot table out of sync with libpilegnn")
+    out = torch.zeros(lib.pile_wpack_total(), dtype=torch.float32, device=device)
+    for i, name in enumerate(WSLOTS):
+        blk = blocks[name].contiguous().reshape(-1)
+        off, size = lib.pile_wpack_slot_offset(i), lib.pile_wpack_slot_size(i)
+        if blk.numel() != size:
+            raise _lib.PileLibraryError("slot %s: %d floats, library expects %d" % (name, blk.numel(), size))
+        out[off:off + size] = blk
+    return out
+
+
+def cam_matrix12(cam_extrinsic):
+    """Rows 0..2 of the world->camera(OpenCV) matrix the reference rebuilds per call (planners.py:197-203)."""
+    flip = np.diag([1.0, -1.0, -1.0, 1.0])
+    m = np.linalg.inv(np.matmul(np.linalg.inv(np.asarray(cam_extrinsic, dtype=np.float64)), flip))
+    return [float(np.float32(v)) for v in m[:3].reshape(-1)]
+
+
+@dataclass
+class Relations:
+    """Compact relation lists of a batch: the Rr/Rs-equivalent (SURVEY.md §8b 'Forward')."""
+    rowptr: torch.Tensor   # [B, N+1] int32, offsets local to the sample
+    col: torch.Tensor      # [B, 10N] int32 sender of relation e
+    row: torch.Tensor      # [B, 10N] int32 receiver of relation e
+
+    @property
+    def n_rel(self):
+        return self.rowptr[:, -1]
+
+    def edge_sets(self):
+        """list over samples of int arrays [E_b, 2] = (receiver, sender), in storage order."""
+        rp, col, row = self.rowptr.cpu().numpy(), self.col.cpu().numpy(), self.row.cpu().numpy()
+        return [np.stack([row[b, :rp[b, -1]], col[b, :rp[b, -1]]], axis=1) for b in range(rp.shape[0])]
+
+    def to_dense(self, dtype=torch.float32):
+        """One-hot Rr, Rs [B, n_rel, N] laid out like the reference (gnn_dyn.py:242-251)."""
+        B, N = self.rowptr.shape[0], self.rowptr.shape[1] - 1
+        n_rel = int(self.n_rel.max())
+        Rr = torch.zeros(B, n_rel, N, dtype=dtype, device=self.col.device)
+        Rs = torch.zeros_like(Rr)
+        slot = torch.arange(n_rel, device=self.col.device)[None].expand(B, n_rel)
+        live = slot < self.n_rel[:, None]
+        b_idx = torch.arange(B, device=self.col.device)[:, None].expand(B, n_rel)
+        Rr[b_idx[live], slot[live], self.row[:, :n_rel][live].long()] = 1
+        Rs[b_idx[live], slot[live], self.col[:, :n_rel][live].long()] = 1
+        return Rr, Rs
+
+    @staticmethod
+    def from_dense(Rr, Rs):
+        """One-hot [B, rel, N] (any relation order, zero rows = padding) -> receiver-grouped lists."""
+        B, n_rel, N = Rr.shape
+        dev = Rr.device
+        live = Rr.sum(2) > 0
+        recv = Rr.argmax(2)
+        send = Rs.argmax(2)
+        key = torch.where(live, recv * N + send, torch.full_like(recv, N * N))
+        order = key.argsort(dim=1, stable=True)
+        recv, send, live = recv.gather(1, order), send.gather(1, order), live.gather(1, order)
+        if n_rel > KMAX * N:
+            raise ValueError("more than %d relations per sample" % (KMAX * N))
+        col = torch.zeros(B, KMAX * N, dtype=torch.int32, device=dev)
+        row = torch.zeros(B, KMAX * N, dtype=torch.int32, device=dev)
+        col[:, :n_rel] = torch.where(live, send, torch.zeros_like(send)).int()
+        row[:, :n_rel] = torch.where(live, recv, torch.zeros_like(recv)).int()
+        counts = torch.zeros(B, N + 1, dtype=torch.int64, device=dev)
+        counts.scatter_add_(1, torch.where(live, recv + 1, torch.zeros_like(recv)), live.long())
+        counts[:, 0] = 0
+        return Relations(counts.cumsum(1).int().contiguous(), col, row)
+
+
+class Workspace:
+    """Per-(B,N) device scratch reused across calls (the library never allocates)."""
+
+    def __init__(self):
+        self._scratch = {}
+        self._bwd = {}
+
+    def scratch(self, B, N, device):
+        key = (B, N, str(device))
+        if key not in self._scratch:
+            n = _lib.load().pile_step_scratch_bytes(B, N)
+            if n < 0:
+                raise _lib.PileLibraryError("unsupported sizes B=%d N=%d" % (B, N))
+            self._scratch[key] = torch.empty(n, dtype=torch.uint8, device=device)
+        return self._scratch[key]
+
+    def bwd(self, B, N, device):
+        key = (B, N, str(device))
+        if key not in self._bwd:
+            n = _lib.load().pile_bwd_scratch_bytes(B, N)
+            self._bwd[key] = torch.empty(n, dtype=torch.uint8, device=device)
+        return self._bwd[key]
+
+
+def new_tape(B, N, T, device):
+    n = _lib.load().pile_tape_step_bytes(B, N)
+    return torch.empty(n * T, dtype=torch.uint8, device=device)
+
+
+def gen_s_delta_raw(s_cur, action, cam12, global_scale):
+    _require_cuda(s_cur, "s_cur")
+    B, N, _ = s_cur.shape
+    out = torch.empty_like(s_cur)
+    _lib.check(_lib.load().pile_gen_s_delta(_lib.ptr(s_cur), _lib.ptr(action), action.stride(0), _lib.host_floats(cam12),
+                                            float(global_scale), B, N, _lib.ptr(out), _stream()), "pile_gen_s_delta")
+    return out
+
+
+def gen_s_delta_backward_raw(s_cur, action, cam12, global_scale, g_sd):
+    B, N, _ = s_cur.shape
+    g_s = torch.zeros_like(s_cur)
+    g_a = torch.empty(B, 4, dtype=torch.float32, device=s_cur.device)
+    _lib.check(_lib.load().pile_gen_s_delta_backward(
+        _lib.ptr(s_cur), _lib.ptr(action), action.stride(0), _lib.host_floats(cam12), float(global_scale), B, N,
+        _lib.ptr(g_sd), _lib.ptr(g_s), _lib.ptr(g_a), 4, _stream()), "pile_gen_s_delta_backward")
+    return g_s, g_a
+
+
+class _GenSDelta(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s_cur, action, cam12, global_scale):
+        s_cur, action = _f32(s_cur), _f32(action)
+        ctx.save_for_backward(s_cur, action)
+        ctx.cam12, ctx.gs = cam12, global_scale
+        return gen_s_delta_raw(s_cur, action, cam12, global_scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        s_cur, action = ctx.saved_tensors
+        g_s, g_a = gen_s_delta_backward_raw(s_cur, action, ctx.cam12, ctx.gs, _f32(g))
+        return g_s, g_a, None, None
+
+
+def gen_s_delta(s_cur, action, cam12, global_scale):
+    """Differentiable pusher model (planners.py:211-257)."""
+    return _GenSDelta.apply(s_cur, action, cam12, global_scale)
+
+
+def build_relations(s_cur, s_delta, adj_thresh, particle_nums=None):
+    """model/gnn_dyn.py:221-251 -> Relations (bit-exact relation set, torch.nonzero order)."""
+    s_cur, s_delta = _f32(s_cur.detach()), _f32(s_delta.detach())
+    _require_cuda(s_cur, "s_cur")
+    B, N, _ = s_cur.shape
+    dev = s_cur.device
+    rowptr = torch.empty(B, N + 1, dtype=torch.int32, device=dev)
+    col = torch.zeros(B, KMAX * N, dtype=torch.int32, device=dev)
+    row = torch.zeros(B, KMAX * N, dtype=torch.int32, device=dev)
+    pn = None if particle_nums is None else torch.as_tensor(particle_nums).to(device=dev, dtype=torch.int32).contiguous()
+    _lib.check(_lib.load().pile_build_relations(_lib.ptr(s_cur), _lib.ptr(s_delta), _lib.ptr(pn), B, N, float(adj_thresh),
+                                                _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(row), None, None, None,
+                                                _stream()), "pile_build_relations")
+    return Relations(rowptr, col, row)
+
+
+def relations_from_buffer(buf, is_tape, B, N):
+    """View the relation lists a step left in its scratch / tape buffer (no copy)."""
+    lib = _lib.load()
+    ps = [C.c_void_p() for _ in range(3)]
+    _lib.check(lib.pile_relations_view(_lib.ptr(buf), int(is_tape), B, N, *[C.byref(p) for p in ps]), "pile_relations_view")
+    base = buf.data_ptr()
+    out = []
+    for p, n in zip(ps, [B * (N + 1), B * KMAX * N, B * KMAX * N]):
+        off = p.value - base
+        out.append(buf[off:off + 4 * n].view(torch.int32))
+    return Relations(out[0].view(B, N + 1), out[1].view(B, KMAX * N), out[2].view(B, KMAX * N))
+
+
+def predict_step_raw(wpack, attr, dens, s_cur, s_delta, adj_thresh, particle_nums, scratch, tape):
+    B, N, _ = s_cur.shape
+    out = torch.empty_like(s_cur)
+    _lib.check(_lib.load().pile_predict_step(_lib.ptr(wpack), _lib.ptr(attr), _lib.ptr(dens), _lib.ptr(particle_nums),
+                                             _lib.ptr(s_cur), _lib.ptr(s_delta), float(adj_thresh), B, N,
+                                             _lib.ptr(scratch), _lib.ptr(tape), _lib.ptr(out), _stream()),
+               "pile_predict_step")
+    return out
+
+
+def forward_relations_raw(wpack, attr, dens, s_cur, s_delta, rel, scratch, tape):
+    B, N, _ = s_cur.shape
+    out = torch.empty_like(s_cur)
+    _lib.check(_lib.load().pile_forward_relations(
+        _lib.ptr(wpack), _lib.ptr(attr), _lib.ptr(dens), _lib.ptr(s_cur), _lib.ptr(s_delta), _lib.ptr(rel.rowptr),
+        _lib.ptr(rel.col), _lib.ptr(rel.row), B, N, _lib.ptr(scratch), _lib.ptr(tape), _lib.ptr(out), _stream()),
+        "pile_forward_relations")
+    return out
+
+
+def step_backward_raw(wpack, dens, tape, B, N, g_pred, bwd_scratch):
+    g_s = torch.empty(B, N, 3, dtype=torch.float32, device=g_pred.device)
+    g_sd = torch.empty_like(g_s)
+    _lib.check(_lib.load().pile_step_backward(_lib.ptr(wpack), _lib.ptr(dens), _lib.ptr(tape), B, N, _lib.ptr(g_pred),
+                                              _lib.ptr(g_s), _lib.ptr(g_sd), _lib.ptr(bwd_scratch), _stream()),
+               "pile_step_backward")
+    return g_s, g_sd
+
+
+def rollout_forward_raw(wpack, attr, dens, s0, actions, cam12, global_scale, adj_thresh, scratch, tape, out=None):
+    B, N, _ = s0.shape
+    T = actions.shape[1]
+    if out is None:
+        out = torch.empty(B, T, N, 3, dtype=torch.float32, device=s0.device)
+    _lib.check(_lib.load().pile_rollout_forward(
+        _lib.ptr(wpack), _lib.ptr(attr), _lib.ptr(dens), _lib.ptr(s0), _lib.ptr(actions), _lib.host_floats(cam12),
+        float(global_scale), float(adj_thresh), B, N, T, _lib.ptr(scratch), _lib.ptr(tape), _lib.ptr(out), _stream()),
+        "pile_rollout_forward")
+    return out
+
+
+def rollout_backward_raw(wpack, dens, s0, actions, cam12, global_scale, tape, states, g_states, bwd_scratch):
+    B, T, N, _ = states.shape
+    g_act = torch.empty(B, T, 4, dtype=torch.float32, device=states.device)
+    _lib.check(_lib.load().pile_rollout_backward(
+        _lib.ptr(wpack), _lib.ptr(dens), _lib.ptr(s0), _lib.ptr(actions), _lib.host_floats(cam12), float(global_scale),
+        B, N, T, _lib.ptr(tape), _lib.ptr(states), _lib.ptr(g_states), _lib.ptr(bwd_scratch), _lib.ptr(g_act),
+        _stream()), "pile_rollout_backward")
+    return g_act
+
+
+def reward_raw(states, n_states, state_stride, N, goal_img, goal_coor, cam_params, offset, normalize, want_argmin=False):
+    M = goal_coor.shape[0]
+    Hh, Ww = goal_img.shape
+    out = torch.empty(n_states, dtype=torch.float32, device=goal_img.device)
+    arg = torch.empty(n_states, M, dtype=torch.int32, device=goal_img.device) if want_argmin else None
+    _lib.check(_lib.load().pile_reward(_lib.ptr(states), n_states, state_stride, N, _lib.ptr(goal_img), Hh, Ww,
+                                       _lib.ptr(goal_coor), M, _lib.host_floats(cam_params), float(offset[0]),
+                                       float(offset[1]), int(bool(normalize)), _lib.ptr(out), _lib.ptr(arg), _stream()),
+               "pile_reward")
+    return out, arg
+
+
+def reward_backward_raw(states, n_states, state_stride, N, goal_img, goal_coor, cam_params, offset, normalize,
+                        g_reward, argmin, g_states, g_stride, accumulate):
+    M = goal_coor.shape[0]
+    Hh, Ww = goal_img.shape
+    _lib.check(_lib.load().pile_reward_backward(
+        _lib.ptr(states), n_states, state_stride, N, _lib.ptr(goal_img), Hh, Ww, _lib.ptr(goal_coor), M,
+        _lib.host_floats(cam_params), float(offset[0]), float(offset[1]), int(bool(normalize)), _lib.ptr(g_reward),
+        _lib.ptr(argmin), _lib.ptr(g_states), g_stride, int(bool(accumulate)), _stream()), "pile_reward_backward")
+
+
+def mppi_partials(reward, acts, reward_weight):
+    """reward [S], acts [S,T,4] -> one record [2+4T] = (max z, sum exp, sum exp*act) for this device."""
+    lib = _lib.load()
+    S, T = acts.shape[0], acts.shape[1]
+    P = lib.pile_mppi_num_chunks(S)
+    part = torch.empty(P, 2 + 4 * T, dtype=torch.float32, device=acts.device)
+    _lib.check(lib.pile_mppi_partials(_lib.ptr(reward), _lib.ptr(acts), S, T, float(reward_weight), _lib.ptr(part),
+                                      _stream()), "pile_mppi_partials")
+    return mppi_combine(part, T)
+
+
+def mppi_combine(parts, T):
+    """parts [P, 2+4T] -> merged record [2+4T] (log-sum-exp rescale)."""
+    parts = parts.contiguous()
+    out = torch.empty(2 + 4 * T, dtype=torch.float32, device=parts.device)
+    _lib.check(_lib.load().pile_mppi_combine(_lib.ptr(parts), parts.shape[0], T, _lib.ptr(out), _stream()),
+               "pile_mppi_combine")
+    return out

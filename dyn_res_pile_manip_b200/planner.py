@@ -1,0 +1,431 @@
+"""Drop-in replacement of the reference planner's particle path (planners.py:64-871).
+
+`PlannerGD(config, env)` keeps the reference entry points -- `gen_s_delta`,
+`ptcl_model_rollout`, `ptcl_evaluate_traj`, `sample_action_sequences`, `optimize_action`,
+`trajectory_optimization_ptcl_multi_traj` -- with the same argument meaning, asserts and
+returned dict, and adds `trajectory_optimization_mppi` (the MPPI composition the reference
+ships in pieces but never wires up).  All tensor work runs in
+libpilegnn; torch provides memory, streams, autograd glue and the process group.
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .propnet import PropNetDiffDenModel
+from .rewards import GoalCache, config_reward_ptcl
+from .synthetic import fps_np
+
+DEBUG = False
+
+
+def particle_num_to_iter_time(particle_num):
+    """The authors' fitted ms-per-iteration model that caps the iteration count (planners.py:25-28)."""
+    t = (2969.3971 - 69.923244 * particle_num + 1.8509846 * particle_num ** 2) / 200.
+    return max(int(t), 1)
+
+
+class _RolloutFn(torch.autograd.Function):
+    """T-step rollout; differentiable w.r.t. the action sequences only (planners.py:674)."""
+
+    @staticmethod
+    def forward(ctx, act_seqs, planner, model_dy, s0, dens, attr):
+        dev = s0.device
+        acts = ops._f32(act_seqs.detach(), dev)
+        Bt, T, _ = acts.shape
+        N = s0.shape[1]
+        need_grad = act_seqs.requires_grad
+        net = model_dy.model
+        wpack = net.packed_weights(dev)
+        scratch = net.workspace.scratch(Bt, N, dev)
+        tape = ops.new_tape(Bt, N, T, dev) if need_grad else None
+        states = ops.rollout_forward_raw(wpack, attr, dens, s0, acts, planner.cam12, planner.global_scale,
+                                         model_dy.adj_thresh, scratch, tape)
+        ctx.saved = (wpack, dens, s0, acts, tape, states, planner, net)
+        return states
+
+    @staticmethod
+    def backward(ctx, g_states):
+        wpack, dens, s0, acts, tape, states, planner, net = ctx.saved
+        if tape is None:
+            raise RuntimeError("rollout was recorded without a tape (actions did not require grad)")
+        Bt, T, N, _ = states.shape
+        g = ops._f32(g_states).clone()          # consumed by the backward sweep
+        g_act = ops.rollout_backward_raw(wpack, dens, s0, acts, planner.cam12, planner.global_scale, tape, states, g,
+                                         net.workspace.bwd(Bt, N, states.device))
+        return g_act, None, None, None, None, None
+
+
+class Planner(object):
+    """reference planners.py:30-62 (attributes read from the environment)."""
+
+    def __init__(self, config, env):
+        self.config = config
+        self.action_dim = 4
+        self.global_scale = config['dataset']['global_scale']
+        self.img_ch = 1
+        self.n_his = config['train']['n_history']
+        self.env = env
+        self.cam_params = self.env.get_cam_params()
+        self.is_real = self.env.is_real
+        if not self.is_real:
+            self.cam_extrinsic = self.env.get_cam_extrinsics()
+        self.screenHeight = self.env.screenHeight
+        self.screenWidth = self.env.screenWidth
+
+    def trajectory_optimization(self, state_cur, obs_goal, model_dy, act_seq, n_sample, n_look_ahead, n_update_iter,
+                                action_lower_lim, action_upper_lim, use_gpu):
+        pass
+
+
+class PlannerGD(Planner):
+
+    def __init__(self, config, env):
+        super(PlannerGD, self).__init__(config, env)
+        if self.is_real:
+            raise NotImplementedError("real-robot pusher model (gen_s_delta_irl) is a SURVEY.md §8f 'next' row")
+        self.cam12 = ops.cam_matrix12(self.cam_extrinsic)
+        self.goals = GoalCache()
+        self.dist_group = None      # torch.distributed process group for sample-sharded planning
+
+    # ---- workspace box (planners.py:150-155, 756-760) ---------------------------------------------
+    def action_box(self, cvx_l=0):
+        r = self.env.cvx_region
+        x_diff, y_diff = r[cvx_l, 1] - r[cvx_l, 0], r[cvx_l, 3] - r[cvx_l, 2]
+        lo = np.array([r[cvx_l, 0], r[cvx_l, 2], r[cvx_l, 0] + x_diff * 0.15, r[cvx_l, 2] + y_diff * 0.15])
+        hi = np.array([r[cvx_l, 1], r[cvx_l, 3], r[cvx_l, 1] - x_diff * 0.15, r[cvx_l, 3] - y_diff * 0.15])
+        return lo, hi
+
+    # ---- MPPI pieces (host numpy like the reference, planners.py:69-190) --------------------------
+    def sample_action_sequences(self, init_act_seq, init_act_label_seq, n_sample, action_lower_lim, action_upper_lim,
+                                noise_type="normal"):
+        beta = self.config['mpc']['mppi']['beta_filter']
+        nd = init_act_seq.ndim
+        assert nd in (2, 3)
+        act_seqs = np.stack([init_act_seq] * n_sample)
+        resid = np.zeros((n_sample,) + init_act_seq.shape[1:])
+        for i in range(self.n_his - 1, init_act_seq.shape[0]):
+            if noise_type == "normal":
+                sigma = self.config['mpc']['sigma'] * self.global_scale / 12.0
+                noise = np.random.normal(0, sigma, resid.shape)
+            elif noise_type == "uniform":
+                sigma = 2.0 * self.global_scale / 12.0
+                noise = np.random.uniform(-sigma, sigma, resid.shape)
+            elif noise_type == "total_rand":
+                noise = np.zeros(resid.shape)
+            else:
+                raise ValueError("unknown noise type: %s" % (noise_type))
+            resid = beta * noise + resid * (1. - beta)
+            act_seqs[:, i] += resid
+            if nd == 2:
+                lo, hi = self.action_box(int(init_act_label_seq[i]))
+                act_seqs[:, i] = np.clip(act_seqs[:, i], lo, hi)
+            else:
+                lo, hi = self.action_box(0)       # only trajectory 0 is clipped (planners.py:161-167)
+                act_seqs[:, i, 0] = np.clip(act_seqs[:, i, 0], lo, hi)
+            if noise_type == 'total_rand':
+                lo, hi = self.action_box(0)
+                act_seqs[:, i, 0] = np.random.uniform(lo, hi, (n_sample, self.action_dim))
+        return act_seqs
+
+    def optimize_action(self, act_seqs, reward_seqs):
+        """softmax(reward_weight * reward)-weighted mean of the sampled sequences (planners.py:549-561)."""
+        w = self.config['mpc']['mppi']['reward_weight']
+        assert len(act_seqs.shape) == 4
+        n_sample, n_look_ahead, cvx_num, action_dim = act_seqs.shape
+        dev = torch.device('cuda')
+        out = np.zeros((n_look_ahead, cvx_num, action_dim))
+        for i in range(cvx_num):
+            a = torch.as_tensor(np.ascontiguousarray(act_seqs[:, :, i, :]), dtype=torch.float32, device=dev)
+            r = torch.as_tensor(np.ascontiguousarray(reward_seqs[:, i]), dtype=torch.float32, device=dev)
+            rec = ops.mppi_partials(r, a, w)
+            out[:, i, :] = (rec[2:] / rec[1]).reshape(n_look_ahead, action_dim).cpu().numpy()
+        return out
+
+    # ---- pusher model (planners.py:192-257) --------------------------------------------------------
+    def world2cam(self, world_pts):
+        assert type(world_pts) == torch.Tensor
+        m = torch.tensor(self.cam12, device=world_pts.device, dtype=world_pts.dtype).view(3, 4)
+        return (world_pts @ m[:, :3].T + m[:, 3]) / self.global_scale
+
+    def gen_s_delta(self, s_cur: torch.Tensor, action: torch.Tensor):
+        assert type(s_cur) == torch.Tensor
+        assert s_cur.shape[1:] == (self.particle_num, 3)
+        assert s_cur.shape[0] == action.shape[0]
+        assert type(action) == torch.Tensor
+        return ops.gen_s_delta(s_cur, action, self.cam12, self.global_scale)
+
+    # ---- rollout (planners.py:302-370) ---------------------------------------------------------------
+    def ptcl_model_rollout(self, s_cur_tensor, s_param_tensor, a_cur_tensor, model_dy, act_seqs, enable_grad=True):
+        n_sample_times_n_batch, T, action_dim = act_seqs.size()
+        n_batch = s_cur_tensor.shape[0]
+        n_sample = n_sample_times_n_batch // n_batch
+        assert type(s_cur_tensor) == torch.Tensor
+        assert type(a_cur_tensor) == torch.Tensor
+        assert s_cur_tensor.shape[1] == self.particle_num
+        assert s_cur_tensor.shape[2] == 3
+        assert a_cur_tensor.shape[1] == self.particle_num
+        assert type(act_seqs) == torch.Tensor
+        if type(model_dy) != PropNetDiffDenModel:
+            raise NotImplementedError
+        ops._require_cuda(s_cur_tensor, "s_cur_tensor")
+        dev = s_cur_tensor.device
+        # flat row = sample * n_batch + b (state tiled n_sample times, planners.py:336-339)
+        s0 = ops._f32(s_cur_tensor.detach()).repeat(n_sample, 1, 1)
+        dens = ops._f32(s_param_tensor.detach(), dev).repeat(n_sample)
+        attr = ops._f32(a_cur_tensor.detach(), dev).repeat(n_sample, 1)
+        start = torch.cuda.Event(enable_timing=True)
+        end = torch.cuda.Event(enable_timing=True)
+        start.record()
+        states = _RolloutFn.apply(act_seqs, self, model_dy, s0, dens, attr)
+        end.record()
+        self._rollout_events = (start, end)
+        return {'model_rollout': {'state_pred': states}, 'rollout_time': _LazyMs(start, end)}
+
+    # ---- reward (planners.py:372-452) -------------------------------------------------------------------
+    def ptcl_evaluate_traj(self, obs_seqs, obs_goal, obs_goal_coor_tensor, debug=False, funnel_dist=None,
+                           distractor_df_fn=None, act_seqs_tensor=None, normalize_rew=True):
+        assert type(obs_seqs) == torch.Tensor
+        assert len(obs_seqs.shape) == 5
+        assert obs_seqs.shape[3] == self.particle_num
+        assert obs_seqs.shape[4] == 3
+        assert type(obs_goal) == torch.Tensor
+        assert len(obs_goal.shape) == 2
+        assert obs_goal.shape[0] == self.screenHeight
+        assert obs_goal.shape[1] == self.screenWidth
+        if distractor_df_fn is not None:
+            raise NotImplementedError("distractor reward is inactive in the reference MPC loop (env/flex_env.py:1048-1065)")
+        n_sample, n_look_ahead, cvx_num, _, _ = obs_seqs.shape
+        obs_future = obs_seqs.reshape(n_sample * n_look_ahead * cvx_num, self.particle_num, 3)
+        next_r = config_reward_ptcl(obs_future, obs_goal, cam_params=self.cam_params, goal_coor=obs_goal_coor_tensor,
+                                    normalize=normalize_rew, offset=(0, 0), cache=self.goals)
+        next_r = next_r.reshape(n_sample, n_look_ahead, cvx_num)
+        reward_seqs = next_r[:, -1]
+        assert reward_seqs.shape == (n_sample, cvx_num)
+        return reward_seqs, next_r
+
+    # ---- gradient-descent planner (planners.py:563-871) ---------------------------------------------
+    def trajectory_optimization_ptcl_multi_traj(self, state_cur_np, state_param, attr_cur_np, obs_goal, model_dy, act_seq,
+                                                act_label_seq, n_sample, n_look_ahead, n_update_iter, action_lower_lim,
+                                                action_upper_lim, use_gpu=True, rollout_best_action_sequence=True,
+                                                reward_params=None, funnel_dist=None, distractor_df_fn=None, gd_loop=1,
+                                                time_lim=float('inf')):
+        time_lim = time_lim / 1000.0
+        assert type(state_cur_np) == np.ndarray
+        assert len(state_cur_np.shape) == 3
+        assert state_cur_np.shape[0] == state_param.shape[0]
+        assert state_cur_np.shape[2] == 3
+        assert type(obs_goal) == np.ndarray
+        assert len(obs_goal.shape) == 2
+        assert type(act_seq) == np.ndarray
+        assert len(act_seq.shape) == 3
+        assert act_seq.shape[0] == act_label_seq.shape[0]
+        assert len(act_label_seq.shape) == 1
+        assert type(state_param) == np.ndarray
+        if not use_gpu:
+            raise _lib.PileLibraryError("use_gpu=False: this planner has no CPU path")
+
+        self.particle_num = state_cur_np.shape[1]
+        n_batch = state_cur_np.shape[0]
+        device = torch.device('cuda')
+        state_cur_tensor = torch.tensor(state_cur_np, device=device, dtype=torch.float)
+        attr_cur_tensor = torch.tensor(attr_cur_np, device=device, dtype=torch.float)
+        obs_goal_tensor = torch.tensor(obs_goal, device=device, dtype=torch.float)
+        obs_goal_coor_tensor = self.goal_coordinates(obs_goal, device)
+        state_param_tensor = torch.from_numpy(state_param).to(device=device, dtype=torch.float)
+
+        n_act = act_seq.shape[0]
+        traj_num = int(act_seq.shape[1])
+        assert n_act == n_look_ahead
+        assert traj_num == n_sample
+
+        n_iter = min(n_update_iter, int(time_lim * 1000.0 / particle_num_to_iter_time(self.particle_num))) \
+            if time_lim != float('inf') else n_update_iter
+        rew_mean = np.zeros((1, n_update_iter * gd_loop), dtype=np.float32)
+        rew_std = np.zeros((1, n_update_iter * gd_loop), dtype=np.float32)
+        rew_mean_d = torch.zeros(max(n_iter, 1), device=device)
+        rew_std_d = torch.zeros(max(n_iter, 1), device=device)
+
+        act_seqs = np.repeat(act_seq.transpose(1, 0, 2)[:, :, np.newaxis, :], n_batch, axis=0)
+        act_seqs_tensor = torch.tensor(act_seqs, device=device, dtype=torch.float, requires_grad=True)
+        reward_seqs_tensor = torch.ones((traj_num * n_batch, 1), device=device, dtype=torch.float)
+        start = time.time()
+        optimizer = torch.optim.Adam([act_seqs_tensor], lr=self.config['mpc']['gd']['lr'], betas=(0.9, 0.999))
+        max_reward = -float('inf') * torch.ones(n_batch, device=device, dtype=torch.float)
+        max_reward_traj_idx = torch.zeros(n_batch, device=device, dtype=torch.long)
+        best_actions_of_samples = torch.zeros((n_batch, n_act, self.action_dim), device=device, dtype=torch.float)
+        lo, hi = self.action_box(0)
+        lo_t = torch.tensor(lo, device=device, dtype=torch.float)
+        hi_t = torch.tensor(hi, device=device, dtype=torch.float)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        rollout_ms, optim_ms, timed = [], [], []
+        batch_ids = torch.arange(n_batch, device=device)
+
+        i = -1
+        for i in range(n_iter):
+            mdl_inp = act_seqs_tensor.permute(0, 2, 1, 3).reshape(-1, n_act, self.action_dim)
+            e0, e1, e2, e3 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            e0.record()
+            try:
+                out = self.ptcl_model_rollout(state_cur_tensor, state_param_tensor, attr_cur_tensor, model_dy, mdl_inp,
+                                              enable_grad=True)
+            except _lib.PileLibraryError:
+                print('OOM error')
+                break
+            e1.record()
+            pred = out['model_rollout']['state_pred']
+            obs_seqs_tensor = pred.reshape(n_sample * n_batch, 1, n_act, self.particle_num, 3).permute(0, 2, 1, 3, 4)
+            reward_seqs_tensor, _ = self.ptcl_evaluate_traj(obs_seqs_tensor, obs_goal_tensor, obs_goal_coor_tensor,
+                                                            distractor_df_fn=distractor_df_fn,
+                                                            act_seqs_tensor=act_seqs_tensor)
+            reward_seqs_tensor = reward_seqs_tensor.reshape(n_sample, n_batch)
+            with torch.no_grad():
+                # per state variant: keep the best trajectory seen so far (planners.py:721-727), on device
+                cur_max, idx_best = torch.max(reward_seqs_tensor, dim=0)
+                better = cur_max > max_reward
+                max_reward = torch.where(better, cur_max, max_reward)
+                max_reward_traj_idx = torch.where(better, idx_best, max_reward_traj_idx)
+                picked = act_seqs_tensor.detach()[idx_best * n_batch + batch_ids, :, 0]
+                best_actions_of_samples = torch.where(better[:, None, None], picked, best_actions_of_samples)
+                rew_mean_d[i] = reward_seqs_tensor[:, 0].mean()
+                rew_std_d[i] = reward_seqs_tensor[:, 0].std()
+            e2.record()
+            loss = torch.sum(-reward_seqs_tensor)
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+            e3.record()
+            with torch.no_grad():     # clamp to the workspace box (planners.py:756-764)
+                act_seqs_tensor.data[:, :, 0, :] = torch.minimum(torch.maximum(act_seqs_tensor.data[:, :, 0, :], lo_t), hi_t)
+            timed.append((e0, e1, e2, e3))
+
+        torch.cuda.synchronize()
+        rollout_time = float(sum(a.elapsed_time(b) for a, b, _, _ in timed))
+        optim_time = float(sum(c.elapsed_time(d) for _, _, c, d in timed))
+        done = i + 1 if n_iter > 0 else 0
+        rew_mean[0, :done] = rew_mean_d[:done].cpu().numpy()
+        rew_std[0, :done] = rew_std_d[:done].cpu().numpy()
+
+        reward_seqs = reward_seqs_tensor.data.cpu().numpy()
+        act_seqs = act_seqs_tensor.data.cpu().numpy()
+        # vote over state variants for the winning trajectory, then the best variant of it (planners.py:771-781)
+        max_reward_traj_count = torch.bincount(max_reward_traj_idx)
+        idx_best_act = torch.argmax(max_reward_traj_count).item()
+        mr, mi = max_reward.cpu().numpy(), max_reward_traj_idx.cpu().numpy()
+        idx_best_sample, reward_from_best_sample = -1, -float('inf')
+        for j in range(n_batch):
+            if idx_best_act == mi[j] and mr[j] > reward_from_best_sample:
+                idx_best_sample, reward_from_best_sample = j, mr[j]
+        act_seq_best = best_actions_of_samples.detach().cpu().numpy()[idx_best_sample][:, None, :]
+
+        obs_seq_best = None
+        reward_best = None
+        next_r = None
+        reward_best_idx = 0
+        act_seq_out = act_seq_best.transpose(1, 0, 2)
+        if rollout_best_action_sequence:
+            assert act_seq_out.shape == (1, n_act, self.action_dim)
+            act_seq_tensor = torch.from_numpy(act_seq_out).float().to(device)
+            out = self.ptcl_model_rollout(state_cur_tensor[0:1], state_param_tensor[0:1], attr_cur_tensor[0:1],
+                                          model_dy, act_seq_tensor, enable_grad=True)
+            obs_seq = out['model_rollout']['state_pred'].permute(1, 0, 2, 3).unsqueeze(0)
+            reward_seq_best, next_seq_r = self.ptcl_evaluate_traj(obs_seq.contiguous(), obs_goal_tensor,
+                                                                  obs_goal_coor_tensor)
+            reward_best_idx = next_seq_r[:, 0].argmax()
+            next_r = next_seq_r[reward_best_idx]
+            reward_best = reward_seq_best[reward_best_idx]
+            obs_seq_best = out['model_rollout']['state_pred'][reward_best_idx].detach().cpu().numpy()
+        action_seq_future = act_seq_out[int(reward_best_idx)]
+        total_time = time.time() - start
+        return {'action_sequence': action_seq_future,
+                'action_full': act_seqs[:, 0, 0, :],
+                'reward_full': reward_seqs[:, 0],
+                'observation_sequence': obs_seq_best,
+                'observation_distractor_sequence': None,
+                'reward': None if reward_best is None else reward_best.detach().cpu().numpy(),
+                'next_r': None if next_r is None else next_r.detach().cpu().numpy(),
+                'rew_mean': rew_mean,
+                'rew_std': rew_std,
+                'times': {'total_time': total_time, 'rollout_time': rollout_time, 'optim_time': optim_time},
+                'iter_num': i}
+
+    # ---- helpers -----------------------------------------------------------------------------------------
+    def goal_coordinates(self, obs_goal, device):
+        """FPS-thinned (col,row) pixels of the goal region (planners.py:620-624)."""
+        g = np.asarray(obs_goal)
+        rc = np.argwhere(g < 0.5)
+        coords = rc[:, ::-1].astype(np.float32)
+        picked, _ = fps_np(coords, min(self.particle_num * 5, coords.shape[0]), 0)
+        return torch.tensor(picked, device=device, dtype=torch.float)
+
+    # ---- MPPI planner: sample -> rollout -> score -> softmax-weighted mean, sample-sharded ----------
+    def trajectory_optimization_mppi(self, state_cur_np, state_param, attr_cur_np, obs_goal, model_dy, act_seq,
+                                     n_sample, n_update_iter=1, seed=None):
+        """act_seq [T,4] mean sequence -> dict(action_sequence [T,4], reward [n_sample local], ...).
+
+        Composition of the reference's unwired MPPI pieces (planners.py:69-190, 549-561): every iteration
+        draws n_sample filtered-noise perturbations of the mean sequence, rolls each out from state variant
+        0, scores the last state, and replaces the mean by softmax(reward_weight*reward)-weighted samples.
+        With a process group set (`self.dist_group`), each rank draws the SAME n_sample perturbations,
+        evaluates its contiguous slice, and one all-gather of the (max, Z, A[T,4]) record per iteration
+        merges the ranks -- the result is identical for any world size.
+        """
+        import torch.distributed as dist
+        device = torch.device('cuda')
+        self.particle_num = state_cur_np.shape[1]
+        T = act_seq.shape[0]
+        w = self.config['mpc']['mppi']['reward_weight']
+        world, rank = 1, 0
+        if self.dist_group is not None or (dist.is_available() and dist.is_initialized()):
+            world, rank = dist.get_world_size(self.dist_group), dist.get_rank(self.dist_group)
+        assert n_sample % world == 0
+        per = n_sample // world
+        s0 = torch.tensor(state_cur_np[0:1], device=device, dtype=torch.float)
+        dens = torch.tensor(np.asarray(state_param)[0:1], device=device, dtype=torch.float)
+        attr = torch.tensor(attr_cur_np[0:1], device=device, dtype=torch.float)
+        goal_t = torch.tensor(obs_goal, device=device, dtype=torch.float)
+        coor = self.goal_coordinates(obs_goal, device)
+        mean = np.asarray(act_seq, dtype=np.float64).reshape(T, 1, 4)
+        if seed is not None:
+            np.random.seed(seed)
+        rewards = None
+        for _ in range(n_update_iter):
+            sampled = self.sample_action_sequences(mean, np.zeros(T), n_sample, None, None)   # [n_sample,T,1,4]
+            mine = torch.tensor(sampled[rank * per:(rank + 1) * per, :, 0, :], device=device, dtype=torch.float)
+            with torch.no_grad():
+                out = self.ptcl_model_rollout(s0, dens, attr, model_dy, mine)
+                last = out['model_rollout']['state_pred'][:, -1]
+                rewards = config_reward_ptcl(last, goal_t, self.cam_params, coor, cache=self.goals)
+                rec = ops.mppi_partials(rewards, mine, w)
+                if world > 1:
+                    allrec = torch.empty(world, rec.numel(), device=device)
+                    dist.all_gather_into_tensor(allrec, rec, group=self.dist_group)
+                    rec = ops.mppi_combine(allrec, T)
+            mean = (rec[2:] / rec[1]).reshape(T, 1, 4).double().cpu().numpy()
+        return {'action_sequence': mean[:, 0, :], 'reward': rewards.cpu().numpy(), 'record': rec.cpu().numpy()}
+
+
+class _LazyMs(float):
+    """rollout_time in ms, resolved from CUDA events on first use (no host sync inside the hot loop)."""
+
+    def __new__(cls, start, end):
+        obj = float.__new__(cls, 0.0)
+        obj._ev = (start, end)
+        return obj
+
+    def _value(self):
+        s, e = self._ev
+        e.synchronize()
+        return s.elapsed_time(e)
+
+    def __float__(self):
+        return self._value()
+
+    def __add__(self, other):
+        return self._value() + float(other)
+
+    __radd__ = __add__
+
+    def __repr__(self):
+        return repr(self._value())

@@ -1,0 +1,134 @@
+"""Drop-in replacement of the reference dynamics model (model/gnn_dyn.py).
+
+Same constructor, same `state_dict` keys (so reference checkpoints load with
+`load_state_dict(torch.load(...), strict=False)`, visualize_mpc.py:37-40), same
+`predict_one_step(a_cur, s_cur, s_delta, particle_dens, particle_nums=None)` and
+`model.forward(a_cur, s_cur, s_delta, Rr, Rs, particle_dens)` signatures -- but every
+tensor op runs in libpilegnn's sm_100a kernels.  `Rr`/`Rs` may be the reference's dense
+one-hot matrices or (preferred) one `ops.Relations` object passed as `Rr` with `Rs=None`.
+
+Differentiable w.r.t. `s_cur` and `s_delta` (the only gradients the planner needs,
+planners.py:674); the parameters are inference-only on this path.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+
+class _Stack(nn.Module):
+    """Linear layers registered under the names the reference checkpoint uses."""
+
+    def __init__(self, seq_name, dims):
+        super().__init__()
+        if seq_name is None:
+            return
+        layers = []
+        for i, (fan_in, fan_out) in enumerate(dims):
+            layers.append(nn.Linear(fan_in, fan_out))
+            layers.append(nn.ReLU())
+        setattr(self, seq_name, nn.Sequential(*layers))
+
+
+class _Named(nn.Module):
+    def __init__(self, **linears):
+        super().__init__()
+        for name, (fan_in, fan_out) in linears.items():
+            setattr(self, name, nn.Linear(fan_in, fan_out))
+
+
+class _StepFn(torch.autograd.Function):
+    """One model step; relation lists either searched (rel=None) or supplied."""
+
+    @staticmethod
+    def forward(ctx, s_cur, s_delta, attr, dens, owner, rel, particle_nums):
+        need_grad = s_cur.requires_grad or s_delta.requires_grad
+        s_cur_c, s_delta_c = ops._f32(s_cur.detach()), ops._f32(s_delta.detach())
+        ops._require_cuda(s_cur_c, "s_cur")
+        dev = s_cur_c.device
+        B, N, _ = s_cur_c.shape
+        attr_c, dens_c = ops._f32(attr.detach(), dev), ops._f32(dens.detach(), dev)
+        wpack = owner.packed_weights(dev)
+        scratch = owner.workspace.scratch(B, N, dev)
+        tape = ops.new_tape(B, N, 1, dev) if need_grad else None
+        if rel is None:
+            pn = None
+            if particle_nums is not None:
+                pn = torch.as_tensor(particle_nums).to(device=dev, dtype=torch.int32).contiguous()
+            out = ops.predict_step_raw(wpack, attr_c, dens_c, s_cur_c, s_delta_c, owner.adj_thresh, pn, scratch, tape)
+            owner.last_relations_buffer = (tape if need_grad else scratch, need_grad, B, N)
+        else:
+            out = ops.forward_relations_raw(wpack, attr_c, dens_c, s_cur_c, s_delta_c, rel, scratch, tape)
+        ctx.owner, ctx.tape, ctx.dims, ctx.wpack, ctx.dens = owner, tape, (B, N), wpack, dens_c
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, N = ctx.dims
+        g = ops._f32(g)
+        g_s, g_sd = ops.step_backward_raw(ctx.wpack, ctx.dens, ctx.tape, B, N, g,
+                                          ctx.owner.workspace.bwd(B, N, g.device))
+        return g_s, g_sd, None, None, None, None, None
+
+
+class PropModuleDiffDen(nn.Module):
+    """Propagation network (reference model/gnn_dyn.py:113-198), weights only + CUDA forward."""
+
+    def __init__(self, config, use_gpu=False):
+        super().__init__()
+        self.config = config
+        nf = config['train']['particle']['nf_effect']
+        self.nf_effect = nf
+        self.add_delta = config['train']['particle']['add_delta']
+        self.use_gpu = use_gpu
+        # construction order = reference order, so torch.manual_seed(s) gives identical initial weights
+        self.particle_encoder = _Stack("model", [(5, nf), (nf, nf)])
+        self.relation_encoder = _Stack("model", [(6, nf), (nf, nf), (nf, nf)])
+        self.particle_propagator = _Named(linear=(2 * nf + 1, nf))
+        self.relation_propagator = _Named(linear=(3 * nf + 1, nf))
+        self.particle_predictor = _Named(linear_0=(nf, nf), linear_1=(nf, 3))
+        self.workspace = ops.Workspace()
+        self.adj_thresh = config['train']['particle']['adj_thresh']
+        self.last_relations_buffer = None
+        self._packed = {}
+
+    # ---- weights -> packed device buffer, re-packed only when a parameter changed --------------
+    def packed_weights(self, device):
+        params = list(self.named_parameters())
+        stamp = tuple((p.data_ptr(), p._version) for _, p in params)
+        hit = self._packed.get(str(device))
+        if hit is None or hit[0] != stamp:
+            state = {"model." + k: p for k, p in params}
+            self._packed[str(device)] = (stamp, ops.pack_weights(state, device))
+        return self._packed[str(device)][1]
+
+    def forward(self, a_cur, s_cur, s_delta, Rr, Rs, particle_dens, verbose=False):
+        rel = Rr if isinstance(Rr, ops.Relations) else ops.Relations.from_dense(Rr, Rs)
+        return _StepFn.apply(s_cur, s_delta, a_cur, particle_dens, self, rel, None)
+
+
+class PropNetDiffDenModel(nn.Module):
+    """reference model/gnn_dyn.py:200-254."""
+
+    def __init__(self, config, use_gpu=False):
+        super().__init__()
+        self.config = config
+        self.adj_thresh = config['train']['particle']['adj_thresh']
+        self.model = PropModuleDiffDen(config, use_gpu)
+        if self.model.nf_effect != 64 and _lib.os.path.isfile(_lib.LIB_PATH):
+            if _lib.load().pile_nf_effect() != self.model.nf_effect:
+                raise _lib.PileLibraryError("libpilegnn is compiled for nf_effect=%d" % _lib.load().pile_nf_effect())
+
+    def predict_one_step(self, a_cur, s_cur, s_delta, particle_dens, particle_nums=None):
+        assert type(a_cur) == torch.Tensor
+        assert type(s_cur) == torch.Tensor
+        assert type(s_delta) == torch.Tensor
+        assert a_cur.shape == s_cur.shape[:2]
+        assert s_cur.shape == s_delta.shape
+        self.model.adj_thresh = self.adj_thresh
+        return _StepFn.apply(s_cur, s_delta, a_cur, particle_dens, self.model, None, particle_nums)
+
+    def relations_of_last_step(self):
+        """Relation lists built by the most recent predict_one_step (for parity checks)."""
+        buf, is_tape, B, N = self.model.last_relations_buffer
+        return ops.relations_from_buffer(buf, is_tape, B, N)

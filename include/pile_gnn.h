@@ -1,0 +1,115 @@
+/* libpilegnn -- C ABI of the B200-native particle-GNN rollout path.
+ *
+ * The reference (WangYixuan12/dyn-res-pile-manip) has no FFI layer: its boundary for this path is the
+ * Python class API.  These entry points are what a maintainer binds underneath that API
+ * (ctypes stub in INTEGRATION.md); each one names the reference code it replaces.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless stated; float32 / int32, row-major, contiguous;
+ * `stream` is a cudaStream_t passed as void*; nothing allocates, nothing synchronises, no global state
+ * except one-time kernel attribute setup.  Return value: 0 = ok, otherwise a cudaError_t value
+ * (cudaErrorInvalidValue for rejected arguments).  All launches are CUDA-graph capturable.
+ */
+#ifndef PILE_GNN_H
+#define PILE_GNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PILE_ABI_VERSION 1
+
+int pile_abi_version(void);
+int pile_nf_effect(void);        /* hidden width compiled in (config train.particle.nf_effect = 64) */
+int pile_max_relations(void);    /* 10, model/gnn_dyn.py:231 */
+const char* pile_error_string(int code);
+
+/* ---- packed weights ---------------------------------------------------------------------------
+ * The host packs the 18 checkpoint tensors into one float buffer; slots are listed in
+ * csrc/common.cuh (enum WSlot): transposed [in][out] blocks for the forward, [out][in] for the dgrad. */
+int pile_wpack_num_slots(void);
+long long pile_wpack_slot_offset(int slot);   /* in floats */
+long long pile_wpack_slot_size(int slot);
+long long pile_wpack_total(void);
+
+/* ---- pusher model: replaces PlannerGD.world2cam + gen_s_delta (planners.py:192-257) -------------
+ * action[b] = (sx, sy, ex, ey) at action + b*act_stride; cam_m12 = rows 0..2 of the 4x4 world->camera
+ * matrix (HOST pointer, 12 floats). */
+int pile_gen_s_delta(const float* s_cur, const float* action, int act_stride, const float* cam_m12,
+                     float global_scale, int B, int N, float* s_delta, void* stream);
+
+/* ---- relation construction: replaces model/gnn_dyn.py:221-251 ------------------------------------
+ * rowptr [B, N+1] (offsets local to the sample), col/row [B, 10*N] sender / receiver index; relations of
+ * a sample are sorted by (receiver, sender) = torch.nonzero() order.  trowptr/trecv/tedge (nullable) are
+ * the sender-major transpose used by the backward.  particle_nums (nullable) [B] = padding mask. */
+int pile_build_relations(const float* s_cur, const float* s_delta, const int* particle_nums, int B, int N,
+                         float adj_thresh, int* rowptr, int* col, int* row, int* trowptr, int* trecv,
+                         int* tedge, void* stream);
+
+/* ---- one model step: replaces PropNetDiffDenModel.predict_one_step (model/gnn_dyn.py:209-254) ----
+ * scratch: pile_step_scratch_bytes(B,N) bytes; tape (nullable): pile_tape_step_bytes(B,N) bytes that
+ * receive the relation lists + ReLU sign bits needed by pile_step_backward. */
+long long pile_step_scratch_bytes(int B, int N);
+long long pile_tape_step_bytes(int B, int N);
+int pile_predict_step(const float* wpack, const float* attr, const float* dens, const int* particle_nums,
+                      const float* s_cur, const float* s_delta, float adj_thresh, int B, int N, void* scratch,
+                      void* tape, float* s_pred, void* stream);
+/* forward on caller-provided relation lists -- the "Rr/Rs-equivalent" entry of PropModuleDiffDen.forward
+ * (model/gnn_dyn.py:147): relations of a sample must be grouped by receiver (CSR). */
+int pile_forward_relations(const float* wpack, const float* attr, const float* dens, const float* s_cur,
+                           const float* s_delta, const int* rowptr, const int* col, const int* row, int B, int N,
+                           void* scratch, void* tape, float* s_pred, void* stream);
+/* backward of one recorded step (dgrad only): g_pred [B,N,3] -> g_s_cur, g_s_delta [B,N,3] (overwritten) */
+int pile_step_backward(const float* wpack, const float* dens, const void* tape, int B, int N, const float* g_pred,
+                       float* g_s_cur, float* g_s_delta, void* bwd_scratch, void* stream);
+/* backward of pile_gen_s_delta: g_s_cur += d/ds_cur, g_action[b] (at g_action + b*g_act_stride) = d/daction */
+int pile_gen_s_delta_backward(const float* s_cur, const float* action, int act_stride, const float* cam_m12,
+                              float global_scale, int B, int N, const float* g_s_delta, float* g_s_cur,
+                              float* g_action, int g_act_stride, void* stream);
+/* read the relation lists of a step back out of scratch (tape == NULL run) or tape */
+int pile_relations_view(void* scratch_or_tape, int is_tape, int B, int N, int** rowptr, int** col, int** row);
+
+/* ---- horizon rollout: replaces PlannerGD.ptcl_model_rollout (planners.py:302-370) ---------------
+ * attr [B,N], dens [B], s0 [B,N,3], actions [B,T,4] -> states [B,T,N,3]; B is the already tiled
+ * sample*state-variant batch (flat index = sample*n_batch + b).  tape (nullable): T * tape_step_bytes. */
+int pile_rollout_forward(const float* wpack, const float* attr, const float* dens, const float* s0,
+                         const float* actions, const float* cam_m12, float global_scale, float adj_thresh,
+                         int B, int N, int T, void* scratch, void* tape, float* states, void* stream);
+
+/* backward of the rollout w.r.t. the actions (dgrad only; relation sets and the hard along-push mask
+ * carry no gradient, as in autograd: planners.py:742-745).  g_states [B,T,N,3] = dL/dstates (consumed,
+ * overwritten), g_actions [B,T,4] out.  bwd_scratch: pile_bwd_scratch_bytes(B,N). */
+long long pile_bwd_scratch_bytes(int B, int N);
+int pile_rollout_backward(const float* wpack, const float* dens, const float* s0, const float* actions,
+                          const float* cam_m12, float global_scale, int B, int N, int T, const void* tape,
+                          const float* states, float* g_states, void* bwd_scratch, float* g_actions,
+                          void* stream);
+
+/* ---- reward: replaces config_reward_ptcl via ptcl_evaluate_traj (env/flex_rewards.py:156-214) ----
+ * states: n_states blocks of [N,3], state_stride floats apart; goal_img [Hh,Ww] is the SHAPED image
+ * (goal - DT - min, computed once per goal on the host with cv2); goal_coor [M,2] = (col,row).
+ * argmin (nullable) [n_states, M] int32 receives the nearest-particle index for the backward. */
+int pile_reward(const float* states, long long n_states, long long state_stride, int N, const float* goal_img,
+                int Hh, int Ww, const float* goal_coor, int M, const float* cam_params4 /*HOST fx,fy,cx,cy*/,
+                float off_x, float off_y, int normalize, float* reward, int* argmin, void* stream);
+int pile_reward_backward(const float* states, long long n_states, long long state_stride, int N,
+                         const float* goal_img, int Hh, int Ww, const float* goal_coor, int M,
+                         const float* cam_params4, float off_x, float off_y, int normalize,
+                         const float* g_reward, const int* argmin, float* g_states, long long g_stride,
+                         int accumulate, void* stream);
+
+/* ---- MPPI weighting: replaces PlannerGD.optimize_action (planners.py:549-561) -------------------
+ * partials: [pile_mppi_num_chunks(S)][2 + 4T] = (max z, sum exp(z-max), sum exp(z-max)*act) with
+ * z = reward_weight*reward; combine merges P such records (chunks and/or ranks) into one record
+ * out[2+4T]; the optimised action sequence is out[2:] / out[1]. */
+int pile_mppi_num_chunks(int S);
+int pile_mppi_partials(const float* reward, const float* acts, int S, int T, float reward_weight,
+                       float* partials, void* stream);
+int pile_mppi_combine(const float* partials, int P, int T, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PILE_GNN_H */

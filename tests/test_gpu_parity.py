@@ -1,0 +1,189 @@
+"""Parity of the CUDA path (through the drop-in API -> C ABI) against the golden vectors produced by the
+reference and against the CPU oracle.  Relation sets: bit-exact.  Positions: ||d|| / ||s|| <= 1e-4 after one
+step (BASELINE.json north_star); everything float is far inside that here because the whole path is fp32."""
+import numpy as np
+import pytest
+import torch
+
+import dyn_res_pile_manip_b200 as P
+from dyn_res_pile_manip_b200 import ops, synthetic
+from oracle import pile_oracle as O
+
+pytestmark = pytest.mark.gpu
+POS_TOL = 1e-4       # north_star: positions within 1e-4 relative after one step
+DEV = "cuda"
+
+
+def relerr(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def coo_from_relations(rel):
+    rows = []
+    for b, e in enumerate(rel.edge_sets()):
+        rows.append(np.concatenate([np.full((e.shape[0], 1), b), e], axis=1))
+    return np.concatenate(rows).astype(np.int16)
+
+
+@pytest.fixture(scope="module")
+def model(golden_weights):
+    m = P.PropNetDiffDenModel(synthetic.default_config(), True)
+    m.load_state_dict(golden_weights)
+    return m.to(DEV)
+
+
+@pytest.fixture(scope="module")
+def planner():
+    return P.PlannerGD(synthetic.default_config(), synthetic.FakeEnv())
+
+
+def cuda(x):
+    return torch.as_tensor(x).to(DEV)
+
+
+def test_s_delta_matches_reference(golden, planner):
+    planner.particle_num = 100
+    sd = planner.gen_s_delta(cuda(golden["A/s_cur"]), cuda(golden["A/act"]))
+    np.testing.assert_allclose(sd.cpu().numpy(), golden["A/s_delta"], rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("case", ["A", "B", "C"])
+def test_relation_sets_bit_exact_vs_reference(golden, case):
+    nums = golden.get(case + "/nums")
+    rel = ops.build_relations(cuda(golden[case + "/s_cur"]), cuda(golden[case + "/s_delta"]), 0.08, nums)
+    assert np.array_equal(coo_from_relations(rel), golden[case + "/rel"])
+
+
+@pytest.mark.parametrize("N,B", [(1, 2), (9, 3), (10, 3), (11, 3), (50, 8), (100, 16), (300, 8), (777, 2)])
+def test_relation_sets_bit_exact_vs_oracle(N, B):
+    rng = np.random.RandomState(N)
+    s, _ = synthetic.make_pile_batch(B, N, seed=N) if N >= 10 else (rng.uniform(-.1, .1, (B, N, 3)).astype(np.float32), 0)
+    sd = (rng.normal(0, 0.02, size=s.shape) * (rng.uniform(size=s.shape[:2] + (1,)) < 0.3)).astype(np.float32)
+    adj = O.adjacency(torch.from_numpy(s), torch.from_numpy(sd), 0.08)
+    rel = ops.build_relations(cuda(s), cuda(sd), 0.08)
+    assert np.array_equal(coo_from_relations(rel), adj.nonzero().to(torch.int16).numpy())
+    deg = (rel.rowptr[:, 1:] - rel.rowptr[:, :-1]).cpu()
+    assert deg.min() >= 1 and deg.max() <= min(10, N)
+
+
+def test_relations_duplicate_points_lowest_index_wins():
+    # 14 coincident particles: every distance ties at 0 -> the 10 lowest sender indices must be kept
+    s = np.zeros((1, 14, 3), dtype=np.float32)
+    rel = ops.build_relations(cuda(s), cuda(np.zeros_like(s)), 0.08)
+    e = rel.edge_sets()[0]
+    for i in range(14):
+        assert list(e[e[:, 0] == i, 1]) == list(range(10))
+
+
+@pytest.mark.parametrize("case", ["A", "B", "C"])
+def test_one_step_positions_vs_reference(golden, model, case):
+    g = {k.split("/")[1]: v for k, v in golden.items() if k.startswith(case + "/")}
+    B, N, _ = g["s_cur"].shape
+    a = cuda(g["a_cur"]) if "a_cur" in g else torch.zeros(B, N, device=DEV)
+    out = model.predict_one_step(a, cuda(g["s_cur"]), cuda(g["s_delta"]), cuda(g["dens"]), g.get("nums"))
+    assert relerr(out, g["s_pred"]) < POS_TOL
+    valid = slice(None)
+    np.testing.assert_allclose(out.cpu().numpy()[valid], g["s_pred"][valid], rtol=0, atol=5e-6)
+    assert np.array_equal(coo_from_relations(model.relations_of_last_step()), g["rel"])
+
+
+def test_forward_accepts_dense_one_hot_relations(golden, model, golden_weights):
+    s, sd, dn = (torch.from_numpy(golden["A/" + k]) for k in ("s_cur", "s_delta", "dens"))
+    adj = O.adjacency(s, sd, 0.08)
+    Rr, Rs = O.one_hot_relations(adj)
+    perm = torch.randperm(Rr.shape[1])
+    out = model.model.forward(torch.zeros(4, 100, device=DEV), s.to(DEV), sd.to(DEV), Rr[:, perm].to(DEV),
+                              Rs[:, perm].to(DEV), dn.to(DEV))
+    np.testing.assert_allclose(out.cpu().numpy(), golden["A/s_pred"], rtol=0, atol=5e-6)
+    rel = ops.build_relations(s.to(DEV), sd.to(DEV), 0.08)
+    out2 = model.model.forward(torch.zeros(4, 100, device=DEV), s.to(DEV), sd.to(DEV), rel, None, dn.to(DEV))
+    assert torch.equal(out, out2)
+
+
+def test_rollout_reward_gradient_vs_reference(golden, model, planner):
+    n_batch, n_sample, N, T = 2, 3, 60, 4
+    planner.particle_num = N
+    acts = cuda(golden["D/acts"]).requires_grad_(True)
+    out = planner.ptcl_model_rollout(cuda(golden["D/s0"]), cuda(golden["D/dens"]), torch.zeros(n_batch, N, device=DEV),
+                                     model, acts)
+    pred = out["model_rollout"]["state_pred"]
+    assert float(out["rollout_time"]) > 0
+    drift = [relerr(pred[:, t], golden["D/state_pred"][:, t]) for t in range(T)]
+    assert drift[0] < POS_TOL and max(drift) < 1e-4, drift
+    goal = cuda(synthetic.make_goal(str(golden["D/goal_kind"])))
+    obs = pred.reshape(n_sample * n_batch, 1, T, N, 3).permute(0, 2, 1, 3, 4)
+    reward, next_r = planner.ptcl_evaluate_traj(obs, goal, cuda(golden["D/goal_coor"]))
+    np.testing.assert_allclose(reward.detach().cpu().numpy(), golden["D/reward"], rtol=2e-5)
+    np.testing.assert_allclose(next_r.detach().cpu().numpy(), golden["D/next_r"], rtol=2e-5)
+    torch.sum(-reward).backward()
+    g, ref = acts.grad.cpu().numpy(), golden["D/act_grad"]
+    np.testing.assert_allclose(g, ref, rtol=5e-3, atol=5e-4 * np.abs(ref).max())
+
+
+def test_rollout_relation_sets_every_step(golden, model, planner):
+    """Drive the CUDA relation search with the reference's own per-step states: sets must be identical."""
+    N, T = 60, 4
+    planner.particle_num = N
+    s = torch.from_numpy(golden["D/s0"]).repeat(3, 1, 1)
+    for t in range(T):
+        sd = planner.gen_s_delta(s.to(DEV), cuda(golden["D/acts"][:, t]))
+        rel = ops.build_relations(s.to(DEV), sd, 0.08)
+        assert np.array_equal(coo_from_relations(rel), golden["D/rel%d" % t]), t
+        s = torch.from_numpy(golden["D/state_pred"][:, t])
+
+
+def test_step_gradients_vs_oracle_autograd(golden, model, golden_weights):
+    s = torch.tensor(golden["A/s_cur"], requires_grad=True)
+    sd = torch.tensor(golden["A/s_delta"], requires_grad=True)
+    rng = np.random.RandomState(0)
+    a = torch.tensor(rng.uniform(0, 1, (4, 100)).astype(np.float32))
+    dn = torch.from_numpy(golden["A/dens"])
+    wgt = torch.tensor(rng.normal(size=(4, 100, 3)).astype(np.float32))
+    (O.predict_one_step(golden_weights, 0.08, a, s, sd, dn) * wgt).sum().backward()
+    s2 = s.detach().to(DEV).requires_grad_(True)
+    sd2 = sd.detach().to(DEV).requires_grad_(True)
+    (model.predict_one_step(a.to(DEV), s2, sd2, dn.to(DEV)) * wgt.to(DEV)).sum().backward()
+    assert relerr(s2.grad, s.grad) < 1e-4 and relerr(sd2.grad, sd.grad) < 1e-4
+
+
+def test_s_delta_gradients_vs_oracle_autograd(golden, planner):
+    env = synthetic.FakeEnv()
+    s = torch.tensor(golden["A/s_cur"], requires_grad=True)
+    act = torch.tensor(golden["A/act"], requires_grad=True)
+    wgt = torch.tensor(np.random.RandomState(1).normal(size=(4, 100, 3)).astype(np.float32))
+    (O.gen_s_delta(env.get_cam_extrinsics(), synthetic.GLOBAL_SCALE, s, act) * wgt).sum().backward()
+    planner.particle_num = 100
+    s2 = s.detach().to(DEV).requires_grad_(True)
+    a2 = act.detach().to(DEV).requires_grad_(True)
+    (planner.gen_s_delta(s2, a2) * wgt.to(DEV)).sum().backward()
+    assert relerr(s2.grad, s.grad) < 1e-4 and relerr(a2.grad, act.grad) < 1e-4
+
+
+def test_reward_vs_oracle_including_out_of_view_particles():
+    rng = np.random.RandomState(3)
+    goal = synthetic.make_goal("tee")
+    env = synthetic.FakeEnv()
+    coords = np.argwhere(goal < 0.5)[:, ::-1].astype(np.float32)
+    coor, _ = synthetic.fps_np(coords, 200, 0)
+    st = np.concatenate([rng.uniform(-0.4, 0.4, (6, 80, 2)), rng.uniform(0.6, 0.8, (6, 80, 1))], 2).astype(np.float32)
+    s_cpu = torch.tensor(st, requires_grad=True)
+    r_ref = O.reward_ptcl(s_cpu, torch.from_numpy(goal), env.get_cam_params(), torch.from_numpy(coor))
+    wgt = torch.tensor(rng.normal(size=6).astype(np.float32))
+    (r_ref * wgt).sum().backward()
+    s_gpu = torch.tensor(st, device=DEV, requires_grad=True)
+    r = P.config_reward_ptcl(s_gpu, cuda(goal), env.get_cam_params(), cuda(coor))
+    np.testing.assert_allclose(r.detach().cpu().numpy(), r_ref.detach().numpy(), rtol=2e-5)
+    (r * wgt.to(DEV)).sum().backward()
+    assert relerr(s_gpu.grad, s_cpu.grad) < 1e-4
+
+
+def test_mppi_weighting_vs_reference(golden, planner):
+    out = planner.optimize_action(golden["E/sampled"], golden["E/reward"])
+    np.testing.assert_allclose(out, golden["E/optimized"], rtol=2e-5, atol=1e-6)
+    # many chunks + extreme reward spread (log-sum-exp path)
+    rng = np.random.RandomState(2)
+    acts = rng.uniform(-4, 4, (1000, 7, 1, 4))
+    rew = rng.uniform(-900, -1, (1000, 1))
+    np.testing.assert_allclose(planner.optimize_action(acts, rew), O.mppi_optimize_action(acts, rew, 0.1),
+                               rtol=1e-4, atol=1e-5)

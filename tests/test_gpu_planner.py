@@ -1,0 +1,120 @@
+"""End-to-end planner behaviour on the GPU and size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+import dyn_res_pile_manip_b200 as P
+from dyn_res_pile_manip_b200 import ops, synthetic
+from oracle import pile_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def setup():
+    cfg, env = synthetic.default_config(), synthetic.FakeEnv()
+    torch.manual_seed(0)
+    model = P.PropNetDiffDenModel(cfg, True).to(DEV)
+    return cfg, env, model, P.PlannerGD(cfg, env)
+
+
+def test_gd_planner_matches_oracle_adam_loop(setup):
+    """Three Adam iterations of trajectory_optimization_ptcl_multi_traj == the same loop written with the
+    oracle + torch autograd on the CPU (reference planners.py:682-764)."""
+    cfg, env, model, planner = setup
+    n_batch, n_sample, N, T, iters = 2, 3, 50, 2, 3
+    st, dn = synthetic.make_pile_batch(n_batch, N, seed=5)
+    act0 = synthetic.random_actions(n_sample, T, seed=5).transpose(1, 0, 2).copy()     # [T, traj, 4]
+    goal = synthetic.make_goal("bar")
+    res = planner.trajectory_optimization_ptcl_multi_traj(
+        st, dn, np.zeros((n_batch, N), np.float32), goal, model, act0.astype(np.float64), np.zeros(T), n_sample, T, iters,
+        None, None, use_gpu=True, rollout_best_action_sequence=True)
+    assert res["iter_num"] == iters - 1
+    # oracle loop
+    W = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    acts = torch.tensor(np.repeat(act0.transpose(1, 0, 2)[:, :, None, :], n_batch, axis=0), dtype=torch.float,
+                        requires_grad=True)
+    opt = torch.optim.Adam([acts], lr=0.05, betas=(0.9, 0.999))
+    coords = np.argwhere(goal < 0.5)[:, ::-1].astype(np.float32)
+    coor, _ = synthetic.fps_np(coords, min(5 * N, len(coords)), 0)
+    lo, hi = O.action_box(env.cvx_region)
+    means = []
+    for _ in range(iters):
+        pred = O.rollout(W, 0.08, env.get_cam_extrinsics(), synthetic.GLOBAL_SCALE, torch.tensor(st), torch.tensor(dn),
+                         torch.zeros(n_batch, N), acts[:, :, 0, :])
+        obs = pred.reshape(n_sample * n_batch, 1, T, N, 3).permute(0, 2, 1, 3, 4)
+        reward, _ = O.evaluate_traj(obs, torch.from_numpy(goal), env.get_cam_params(), torch.from_numpy(coor))
+        means.append(float(reward.reshape(n_sample, n_batch)[:, 0].mean()))
+        opt.zero_grad()
+        torch.sum(-reward).backward()
+        opt.step()
+        with torch.no_grad():
+            acts.data[:, :, 0, :] = torch.minimum(torch.maximum(acts.data[:, :, 0, :], torch.tensor(lo).float()),
+                                                  torch.tensor(hi).float())
+    np.testing.assert_allclose(res["rew_mean"][0, :iters], means, rtol=1e-4)
+    np.testing.assert_allclose(res["action_full"], acts.detach().numpy()[:, 0, 0, :], rtol=0, atol=2e-3)
+    assert res["observation_sequence"].shape == (T, N, 3)
+    assert res["action_sequence"].shape == (T, 4)
+    assert set(res) >= {"action_sequence", "action_full", "reward_full", "observation_sequence", "reward", "next_r",
+                        "rew_mean", "rew_std", "times", "iter_num"}
+
+
+def test_gd_planner_improves_reward(setup):
+    cfg, env, model, planner = setup
+    st, dn = synthetic.make_pile_batch(3, 80, seed=6)
+    act0 = synthetic.random_actions(8, 1, seed=6).transpose(1, 0, 2).astype(np.float64)
+    res = planner.trajectory_optimization_ptcl_multi_traj(
+        st, dn, np.zeros((3, 80), np.float32), synthetic.make_goal("disc"), model, act0, np.zeros(1), 8, 1, 25, None, None)
+    rm = res["rew_mean"][0, :25]
+    assert rm[-1] > rm[0]
+    lo, hi = planner.action_box(0)
+    assert (res["action_full"] >= lo - 1e-6).all() and (res["action_full"] <= hi + 1e-6).all()
+
+
+def test_mppi_planner_is_deterministic_and_in_bounds(setup):
+    cfg, env, model, planner = setup
+    st, dn = synthetic.make_pile_batch(1, 100, seed=7)
+    args = (st, dn, np.zeros((1, 100), np.float32), synthetic.make_goal("bar"), model,
+            synthetic.random_actions(1, 5, seed=7)[0])
+    a = planner.trajectory_optimization_mppi(*args, n_sample=64, n_update_iter=2, seed=3)
+    b = planner.trajectory_optimization_mppi(*args, n_sample=64, n_update_iter=2, seed=3)
+    assert np.array_equal(a["action_sequence"], b["action_sequence"])
+    assert a["action_sequence"].shape == (5, 4) and np.isfinite(a["action_sequence"]).all()
+
+
+@pytest.mark.parametrize("N,B,T", [(300, 256, 3), (100, 256, 10)])
+def test_full_size_properties(setup, N, B, T):
+    """BASELINE.json sizes (per-GPU slices): properties that need no CPU reference."""
+    cfg, env, model, planner = setup
+    planner.particle_num = N
+    st, dn = synthetic.make_pile_batch(1, N, seed=8)
+    acts = torch.tensor(synthetic.random_actions(B, T, seed=8), device=DEV)
+    z = torch.zeros(1, N, device=DEV)
+    with torch.no_grad():
+        p1 = planner.ptcl_model_rollout(torch.tensor(st).to(DEV), torch.tensor(dn).to(DEV), z, model, acts)
+        p1 = p1["model_rollout"]["state_pred"].clone()
+        p2 = planner.ptcl_model_rollout(torch.tensor(st).to(DEV), torch.tensor(dn).to(DEV), z, model, acts)
+        p2 = p2["model_rollout"]["state_pred"]
+    assert torch.isfinite(p1).all()
+    assert torch.equal(p1, p2)                                    # deterministic (no float atomics)
+    # samples are independent: a sub-batch gives the same rows bit for bit
+    with torch.no_grad():
+        sub = planner.ptcl_model_rollout(torch.tensor(st).to(DEV), torch.tensor(dn).to(DEV), z, model, acts[17:29])
+    assert torch.equal(sub["model_rollout"]["state_pred"], p1[17:29])
+    # relation structure on the last state: self edge, degree bound, sorted senders, symmetric distances
+    s_last = p1[:, -1].contiguous()
+    rel = ops.build_relations(s_last, torch.zeros_like(s_last), 0.08)
+    deg = rel.rowptr[:, 1:] - rel.rowptr[:, :-1]
+    assert int(deg.min()) >= 1 and int(deg.max()) <= 10
+    e = rel.edge_sets()[5]
+    assert (np.diff(e[:, 0]) >= 0).all()
+    for i in range(0, N, 37):
+        snd = e[e[:, 0] == i, 1]
+        assert i in snd and (np.diff(snd) > 0).all()
+    # one sample against the oracle at full N (the oracle handles a single sample in well under a second)
+    W = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref = O.rollout(W, 0.08, env.get_cam_extrinsics(), synthetic.GLOBAL_SCALE, torch.tensor(st), torch.tensor(dn),
+                    torch.zeros(1, N), acts[3:4, :2].cpu())
+    err = float((p1[3, :2].cpu() - ref[0]).norm() / ref[0].norm())
+    assert err < 1e-4, err

@@ -1,0 +1,135 @@
+"""CPU-side checks: the C ABI library loads and exports what include/pile_gnn.h declares, the drop-in
+classes keep the reference's checkpoint layout, and the host-side helpers agree with the oracle."""
+import itertools
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import dyn_res_pile_manip_b200 as P
+from dyn_res_pile_manip_b200 import _lib, ops, synthetic
+from oracle import pile_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.isfile(_lib.LIB_PATH):
+        _lib.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "pile_gnn.h")).read()
+    declared = set(re.findall(r"\b(pile_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pile_abi_version() == 1
+    assert lib.pile_nf_effect() == 64 and lib.pile_max_relations() == 10
+
+
+def test_argument_validation_without_gpu(lib):
+    assert lib.pile_step_scratch_bytes(0, 10) == -1
+    assert lib.pile_step_scratch_bytes(4, 100) > 4 * 1000 * 64 * 4
+    assert lib.pile_tape_step_bytes(4, 100) > 0
+    assert lib.pile_predict_step(None, None, None, None, None, None, 0.08, 4, 100, None, None, None, None) != 0
+    assert lib.pile_mppi_num_chunks(1000) == 8
+
+
+def test_weight_pack_layout(lib, golden_weights):
+    pack = ops.pack_weights(golden_weights, torch.device("cpu"))
+    assert pack.numel() == lib.pile_wpack_total()
+    H = 64
+    off = {n: lib.pile_wpack_slot_offset(i) for i, n in enumerate(ops.WSLOTS)}
+    rp = golden_weights["model.relation_propagator.linear.weight"]
+    assert torch.equal(pack[off["W_RT"]:off["W_RT"] + H * H].view(H, H), rp[:, H:2 * H].t())
+    assert torch.equal(pack[off["WD_RP"]:off["WD_RP"] + H], rp[:, 3 * H])
+    assert torch.equal(pack[off["W_S"]:off["W_S"] + H * H].view(H, H), rp[:, 2 * H:3 * H])
+    pe0 = golden_weights["model.particle_encoder.model.0.weight"]
+    assert torch.equal(pack[off["W_PE0T"]:off["W_PE0T"] + 8 * H].view(8, H)[:5], pe0.t())
+    assert pack[off["W_PE0T"]:off["W_PE0T"] + 8 * H].view(8, H)[5:].abs().sum() == 0
+
+
+def test_checkpoint_layout_and_init_match_reference(golden_weights):
+    torch.manual_seed(0)
+    m = P.PropNetDiffDenModel(synthetic.default_config(), False)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(golden_weights.keys())
+    for k in sd:
+        assert torch.equal(sd[k], golden_weights[k]), k
+    m2 = P.PropNetDiffDenModel(synthetic.default_config())
+    missing = m2.load_state_dict(golden_weights, strict=False)
+    assert not missing.missing_keys and not missing.unexpected_keys
+
+
+def test_no_cpu_fallback():
+    m = P.PropNetDiffDenModel(synthetic.default_config())
+    s = torch.zeros(1, 5, 3)
+    with pytest.raises(_lib.PileLibraryError):
+        m.predict_one_step(torch.zeros(1, 5), s, s, torch.ones(1))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "dyn_res_pile_manip_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
+
+
+def test_sort10_network_is_a_sorting_network():
+    src = open(os.path.join(ROOT, "dyn_res_pile_manip_b200", "csrc", "nbr.cu")).read()
+    body = src[src.index("void sort10"):src.index("constexpr int NBR_THREADS")]
+    net = [(int(a), int(b)) for a, b in re.findall(r"PILE_CE\((\d+), (\d+)\)", body)]
+    assert len(net) == 29
+    for bits in itertools.product([0, 1], repeat=10):
+        a = list(bits)
+        for i, j in net:
+            if a[i] > a[j]:
+                a[i], a[j] = a[j], a[i]
+        assert a == sorted(a)
+
+
+def test_dense_relation_shim_roundtrip():
+    s, _ = synthetic.make_pile_batch(3, 40, seed=4)
+    adj = O.adjacency(torch.from_numpy(s), torch.zeros(3, 40, 3), 0.08)
+    Rr, Rs = O.one_hot_relations(adj)
+    rel = ops.Relations.from_dense(Rr, Rs)
+    for b, (r, c) in enumerate(O.edge_lists(adj)):
+        got = rel.edge_sets()[b]
+        assert np.array_equal(got[:, 0], r) and np.array_equal(got[:, 1], c)
+    Rr2, Rs2 = rel.to_dense()
+    assert torch.equal(Rr2, Rr) and torch.equal(Rs2, Rs)
+    # shuffled relation order + padding rows still give receiver-grouped lists
+    perm = torch.randperm(Rr.shape[1])
+    rel2 = ops.Relations.from_dense(Rr[:, perm], Rs[:, perm])
+    assert torch.equal(rel2.rowptr, rel.rowptr) and torch.equal(rel2.col, rel.col)
+
+
+def test_planner_host_pieces_match_oracle(golden):
+    env, cfg = synthetic.FakeEnv(), synthetic.default_config()
+    planner = P.PlannerGD(cfg, env)
+    np.random.seed(12)
+    mine = planner.sample_action_sequences(golden["E/init"], np.zeros(5), 16, None, None)
+    np.testing.assert_allclose(mine, golden["E/sampled"], rtol=0, atol=1e-12)
+    assert planner.cam12 == ops.cam_matrix12(golden["cam_extrinsic"])
+    np.testing.assert_allclose(np.array(planner.cam12).reshape(3, 4),
+                               O.world_to_cam_matrix(golden["cam_extrinsic"]).numpy()[:3])
+    assert P.particle_num_to_iter_time(100) == 72 and P.particle_num_to_iter_time(300) == 742
+    planner.particle_num = 60
+    coor = planner.goal_coordinates(synthetic.make_goal("bar"), "cpu")
+    assert np.array_equal(coor.numpy(), golden["D/goal_coor"])
+
+
+def test_synthetic_pile_statistics():
+    s, d = synthetic.make_pile(100, seed=0)
+    assert s.shape == (100, 3) and 800 < d < 2500
+    adj = O.adjacency(torch.from_numpy(s)[None], torch.zeros(1, 100, 3), 0.08)
+    deg = adj[0].sum(1)
+    assert deg.max() <= 10 and deg.min() >= 1 and adj[0].diagonal().all()
