@@ -36,6 +36,7 @@ SIGNATURES = {
     "pile_forward_relations": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "pile_relations_view": (_I, [_P, _I, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "pile_rollout_forward": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P, _P]),
+    "pile_profile_step": (_I, [_P, _P, _P, _P, _P, _I, _P, _F, _F, _I, _I, _P, _P, _I, _P, _P]),
     "pile_bwd_scratch_bytes": (_LL, [_I, _I]),
     "pile_step_backward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "pile_rollout_backward": (_I, [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P, _P]),

@@ -234,6 +234,40 @@ BwdView carve_bwd_view(void* p, int B, int N) {
 }
 }  // namespace
 
+int pile_profile_step(const float* wpack, const float* attr, const float* dens, const float* s_cur,
+                      const float* action, int act_stride, const float* cam_m12, float global_scale,
+                      float adj_thresh, int B, int N, void* scratch, float* s_out, int reps, float* ms_out,
+                      void* stream) {
+  if (bad_dims(B, N) || reps <= 0 || !wpack || !attr || !dens || !s_cur || !action || !cam_m12 || !scratch ||
+      !s_out || !ms_out)
+    return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  ScratchView sv = carve_scratch(scratch, B, N);
+  const PushCam cam = make_cam(cam_m12, global_scale);
+  constexpr int NK = 3 + PSTEP;   // nbr, node_encode, edge_encode, propagate x3
+  cudaEvent_t ev[NK + 1];
+  for (auto& e : ev) cudaEventCreate(&e);
+  for (int k = 0; k < NK; ++k) ms_out[k] = 0.f;
+  int rc = 0;
+  for (int r = 0; r < reps && !rc; ++r) {
+    cudaEventRecord(ev[0], st);
+    rc = launch_nbr_search(s_cur, (long long)N * 3, nullptr, action, act_stride, cam, sv.ws.s_delta, nullptr, B, N,
+                           adj_thresh * adj_thresh, sv.csr, st);
+    if (rc) break;
+    rc = launch_forward(wpack, attr, dens, s_cur, (long long)N * 3, sv.ws.s_delta, sv.csr, sv.ws, nullptr, s_out,
+                        (long long)N * 3, B, N, st, ev + 1);
+    if (rc) break;
+    cudaEventSynchronize(ev[NK]);
+    for (int k = 0; k < NK; ++k) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
+      ms_out[k] += ms / reps;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
+}
+
 long long pile_bwd_scratch_bytes(int B, int N) {
   if (bad_dims(B, N)) return -1;
   return (long long)carve_bwd_view(nullptr, B, N).bytes;

@@ -368,7 +368,8 @@ static int set_smem(Kern k, size_t bytes) {
 
 int launch_forward(const float* wpack, const float* attr, const float* dens, const float* s_cur,
                    long long s_cur_stride, const float* s_delta, const Csr& csr, const StepScratch& ws,
-                   const Masks* mk, float* s_out, long long s_out_stride, int B, int N, cudaStream_t st) {
+                   const Masks* mk, float* s_out, long long s_out_stride, int B, int N, cudaStream_t st,
+                   cudaEvent_t* ev) {
   static bool configured = false;
   if (!configured) {
     int e;
@@ -385,16 +386,19 @@ int launch_forward(const float* wpack, const float* attr, const float* dens, con
   const int g_node = node_tiles < persistent ? node_tiles : persistent;
   const int g_edge = edge_tiles < persistent ? (int)edge_tiles : persistent;
 
+  if (ev) cudaEventRecord(ev[0], st);
   k_node_encode<<<g_node, NT, sizeof(NodeEncSmem), st>>>(wpack, attr, dens, s_delta, mk ? mk->pe0 : nullptr,
                                                          mk ? mk->pe1 : nullptr, ws.Cp, ws.eff, ws.Pr[0],
                                                          ws.Ps[0], B, N);
   PILE_CHECK_LAUNCH();
+  if (ev) cudaEventRecord(ev[1], st);
   k_edge_encode<<<g_edge, NT, sizeof(EdgeEncSmem), st>>>(wpack, attr, dens, s_cur, s_cur_stride, csr.rowptr,
                                                          csr.col, csr.row, mk ? mk->re0 : nullptr,
                                                          mk ? mk->re1 : nullptr, mk ? mk->re2 : nullptr, ws.Ce, B, N);
   PILE_CHECK_LAUNCH();
   for (int p = 0; p < PSTEP; ++p) {
     const int in = p & 1, out = in ^ 1;
+    if (ev) cudaEventRecord(ev[2 + p], st);
     if (p < PSTEP - 1) {
       k_propagate<false><<<g_node, NT, sizeof(PropSmem), st>>>(
           wpack, csr.rowptr, csr.col, ws.Ce, ws.Cp, ws.eff, ws.Pr[in], ws.Ps[in], ws.Pr[out], ws.Ps[out],
@@ -408,6 +412,7 @@ int launch_forward(const float* wpack, const float* attr, const float* dens, con
     }
     PILE_CHECK_LAUNCH();
   }
+  if (ev) cudaEventRecord(ev[2 + PSTEP], st);
   return 0;
 }
 

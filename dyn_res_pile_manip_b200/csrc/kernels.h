@@ -51,7 +51,8 @@ int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_del
 // stride in floats (so slices of [B, T, N, 3] work in place)
 int launch_forward(const float* wpack, const float* attr, const float* dens, const float* s_cur,
                    long long s_cur_stride, const float* s_delta, const Csr& csr, const StepScratch& ws,
-                   const Masks* masks, float* s_out, long long s_out_stride, int B, int N, cudaStream_t st);
+                   const Masks* masks, float* s_out, long long s_out_stride, int B, int N, cudaStream_t st,
+                   cudaEvent_t* ev = nullptr);   // ev: 6 events recorded before each kernel and after the last
 
 int launch_reward(const float* states, long long n_states, long long state_stride, int N, const float* goal_img,
                   int Hh, int Ww, const float* goal_coor, int M, float fx, float fy, float cx, float cy,

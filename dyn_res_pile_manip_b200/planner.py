@@ -88,6 +88,7 @@ class PlannerGD(Planner):
         self.cam12 = ops.cam_matrix12(self.cam_extrinsic)
         self.goals = GoalCache()
         self.dist_group = None      # torch.distributed process group for sample-sharded planning
+        self.device = torch.device('cuda')
 
     # ---- workspace box (planners.py:150-155, 756-760) ---------------------------------------------
     def action_box(self, cvx_l=0):
@@ -372,15 +373,14 @@ class PlannerGD(Planner):
         merges the ranks -- the result is identical for any world size.
         """
         import torch.distributed as dist
-        device = torch.device('cuda')
+        device = self.device
         self.particle_num = state_cur_np.shape[1]
         T = act_seq.shape[0]
         w = self.config['mpc']['mppi']['reward_weight']
         world, rank = 1, 0
         if self.dist_group is not None or (dist.is_available() and dist.is_initialized()):
             world, rank = dist.get_world_size(self.dist_group), dist.get_rank(self.dist_group)
-        assert n_sample % world == 0
-        per = n_sample // world
+        per = shard_size(n_sample, world)
         s0 = torch.tensor(state_cur_np[0:1], device=device, dtype=torch.float)
         dens = torch.tensor(np.asarray(state_param)[0:1], device=device, dtype=torch.float)
         attr = torch.tensor(attr_cur_np[0:1], device=device, dtype=torch.float)
@@ -392,18 +392,31 @@ class PlannerGD(Planner):
         rewards = None
         for _ in range(n_update_iter):
             sampled = self.sample_action_sequences(mean, np.zeros(T), n_sample, None, None)   # [n_sample,T,1,4]
-            mine = torch.tensor(sampled[rank * per:(rank + 1) * per, :, 0, :], device=device, dtype=torch.float)
+            lo_i, hi_i = shard_bounds(n_sample, rank, world)
+            mine = torch.tensor(sampled[lo_i:hi_i, :, 0, :], device=device, dtype=torch.float)
             with torch.no_grad():
                 out = self.ptcl_model_rollout(s0, dens, attr, model_dy, mine)
                 last = out['model_rollout']['state_pred'][:, -1]
                 rewards = config_reward_ptcl(last, goal_t, self.cam_params, coor, cache=self.goals)
                 rec = ops.mppi_partials(rewards, mine, w)
                 if world > 1:
-                    allrec = torch.empty(world, rec.numel(), device=device)
-                    dist.all_gather_into_tensor(allrec, rec, group=self.dist_group)
-                    rec = ops.mppi_combine(allrec, T)
+                    allrec = torch.empty(world * rec.numel(), device=device)
+                    dist.all_gather_into_tensor(allrec, rec.contiguous(), group=self.dist_group)
+                    rec = ops.mppi_combine(allrec.view(world, -1), T)
             mean = (rec[2:] / rec[1]).reshape(T, 1, 4).double().cpu().numpy()
         return {'action_sequence': mean[:, 0, :], 'reward': rewards.cpu().numpy(), 'record': rec.cpu().numpy()}
+
+
+def shard_size(n_sample, world):
+    if n_sample % world != 0:
+        raise ValueError("n_sample=%d is not divisible by the %d ranks" % (n_sample, world))
+    return n_sample // world
+
+
+def shard_bounds(n_sample, rank, world):
+    """Contiguous slice of the sample dimension owned by `rank` (SURVEY.md §8e partitioning)."""
+    per = shard_size(n_sample, world)
+    return rank * per, (rank + 1) * per
 
 
 class _LazyMs(float):

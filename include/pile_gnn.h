@@ -78,6 +78,14 @@ int pile_rollout_forward(const float* wpack, const float* attr, const float* den
                          const float* actions, const float* cam_m12, float global_scale, float adj_thresh,
                          int B, int N, int T, void* scratch, void* tape, float* states, void* stream);
 
+/* measurement hook for bench.py's roofline line: runs one rollout step `reps` times with CUDA events
+ * around each of its 6 kernels (relation search, node encode, relation encode, 3 x propagate) on `stream`,
+ * SYNCHRONISES, and writes the mean milliseconds per kernel to ms_out (HOST, 6 floats). */
+int pile_profile_step(const float* wpack, const float* attr, const float* dens, const float* s_cur,
+                      const float* action, int act_stride, const float* cam_m12, float global_scale,
+                      float adj_thresh, int B, int N, void* scratch, float* s_out, int reps, float* ms_out,
+                      void* stream);
+
 /* backward of the rollout w.r.t. the actions (dgrad only; relation sets and the hard along-push mask
  * carry no gradient, as in autograd: planners.py:742-745).  g_states [B,T,N,3] = dL/dstates (consumed,
  * overwritten), g_actions [B,T,4] out.  bwd_scratch: pile_bwd_scratch_bytes(B,N). */

@@ -275,6 +275,22 @@ def mppi_optimize_action(act_seqs, reward_seqs, reward_weight):
     return out
 
 
+def mppi_record(reward, acts, reward_weight):
+    """(max z, sum exp(z-max), sum exp(z-max)*act) of one shard; acts [n,T,4] -> float64 [2+4T]."""
+    z = reward_weight * np.asarray(reward, dtype=np.float64)
+    m = z.max()
+    w = np.exp(z - m)
+    return np.concatenate([[m, w.sum()], (w[:, None, None] * np.asarray(acts, dtype=np.float64)).sum(0).reshape(-1)])
+
+
+def mppi_merge(records):
+    """log-sum-exp merge of shard records; merged[2:]/merged[1] equals mppi_optimize_action on the union."""
+    records = np.asarray(records, dtype=np.float64)
+    m = records[:, 0].max()
+    sc = np.exp(records[:, 0] - m)
+    return np.concatenate([[m, (sc * records[:, 1]).sum()], (sc[:, None] * records[:, 2:]).sum(0)])
+
+
 # --------------------------------------------------------------------------------------
 # helpers shared by tests / bench baseline
 # --------------------------------------------------------------------------------------

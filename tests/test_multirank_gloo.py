@@ -1,0 +1,89 @@
+"""world_size-2 `gloo` test of the sample-sharded MPPI planner's host logic.
+
+The CUDA ops are replaced by oracle-backed test doubles (this is the one place that is legitimate: the
+product itself has no CPU path); what is exercised is the real planner code: identical noise on every
+rank, contiguous sample shards, one all_gather of the (2+4T) record per iteration, log-sum-exp merge --
+and the requirement that 1 rank and 2 ranks produce the same plan."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import dyn_res_pile_manip_b200 as P
+from dyn_res_pile_manip_b200 import ops, planner as planner_mod, synthetic
+from oracle import pile_oracle as O
+
+N, T, NS = 30, 3, 8
+
+
+def _install_doubles(pl, W, env):
+    def rollout(s0, dens, attr, model_dy, acts, enable_grad=True):
+        pred = O.rollout(W, 0.08, env.get_cam_extrinsics(), synthetic.GLOBAL_SCALE, s0, dens, attr, acts)
+        return {"model_rollout": {"state_pred": pred}, "rollout_time": 0.0}
+
+    def reward(state, goal, cam_params, goal_coor, normalize=True, offset=(0., 0.), cache=None):
+        return O.reward_ptcl(state, goal, cam_params, goal_coor, normalize, offset)
+
+    pl.ptcl_model_rollout = rollout
+    pl.device = torch.device("cpu")
+    planner_mod.config_reward_ptcl = reward
+    ops.mppi_partials = lambda r, a, w: torch.from_numpy(O.mppi_record(r.numpy(), a.numpy(), w)).float()
+    ops.mppi_combine = lambda parts, T_: torch.from_numpy(O.mppi_merge(parts.numpy())).float()
+
+
+def _plan(world, rank, port, out):
+    if world > 1:
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    cfg, env = synthetic.default_config(), synthetic.FakeEnv()
+    pl = P.PlannerGD(cfg, env)
+    W = O.weights_from_seed(0)
+    _install_doubles(pl, W, env)
+    st, dn = synthetic.make_pile_batch(1, N, seed=2)
+    res = pl.trajectory_optimization_mppi(st, dn, np.zeros((1, N), np.float32), synthetic.make_goal("disc"), None,
+                                          synthetic.random_actions(1, T, seed=2)[0], n_sample=NS, n_update_iter=2, seed=5)
+    if rank == 0:
+        np.save(out, res["action_sequence"])
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _worker(rank, world, port, out):
+    _plan(world, rank, port, out)
+
+
+def test_two_ranks_give_the_single_rank_plan(tmp_path):
+    one = str(tmp_path / "one.npy")
+    two = str(tmp_path / "two.npy")
+    mp.spawn(_worker, args=(1, 0, one), nprocs=1, join=True)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, two), nprocs=2, join=True)
+    a, b = np.load(one), np.load(two)
+    assert a.shape == (T, 4) and np.isfinite(a).all()
+    np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_shard_bounds_partition_the_samples():
+    for world in (1, 2, 4, 8):
+        spans = [planner_mod.shard_bounds(1024, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == 1024
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    try:
+        planner_mod.shard_size(10, 4)
+        assert False
+    except ValueError:
+        pass
+
+
+def test_record_merge_equals_softmax_on_union():
+    rng = np.random.RandomState(0)
+    acts, rew = rng.uniform(-4, 4, (64, 5, 1, 4)), rng.uniform(-400, -1, (64, 1))
+    recs = [O.mppi_record(rew[i:i + 16, 0], acts[i:i + 16, :, 0], 0.1) for i in range(0, 64, 16)]
+    m = O.mppi_merge(recs)
+    np.testing.assert_allclose((m[2:] / m[1]).reshape(5, 4), O.mppi_optimize_action(acts, rew, 0.1)[:, 0], rtol=1e-10)
