@@ -98,6 +98,13 @@ int pile_nf_effect(void) { return H; }
 int pile_max_relations(void) { return KMAX; }
 const char* pile_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
 
+int pile_set_tensor_cores(int enable) {
+  const int old = g_use_tensor_cores;
+  g_use_tensor_cores = enable ? 1 : 0;
+  return old;
+}
+int pile_get_tensor_cores(void) { return g_use_tensor_cores; }
+
 int pile_wpack_num_slots(void) { return W_NUM; }
 long long pile_wpack_slot_offset(int slot) { return (slot < 0 || slot > W_NUM) ? -1 : wslot_offset(slot); }
 long long pile_wpack_slot_size(int slot) { return (slot < 0 || slot >= W_NUM) ? -1 : wslot_size(slot); }

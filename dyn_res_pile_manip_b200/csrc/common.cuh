@@ -42,6 +42,9 @@ enum WSlot {
   W_PE0,              // [H][8]
   W_PE1, W_RE0 /*[H][8]*/, W_RE1, W_RE2, W_E, W_R, W_S, W_P, W_A, W_V0,
   W_V1,               // [4][H] (row 3 zero)
+  // tensor-core operands: [hi | lo] bf16 in the canonical K-major UMMA layout (tc.cuh), H*H floats each.
+  // TC_RE1, TC_RE2, TC_E must stay adjacent: k_edge_encode_tc fetches them with one bulk copy.
+  TC_RE1, TC_RE2, TC_E,
   W_NUM
 };
 

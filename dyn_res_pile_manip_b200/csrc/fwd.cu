@@ -361,6 +361,8 @@ k_propagate(const float* __restrict__ wpack, const int* __restrict__ rowptr, con
   }
 }
 
+int g_use_tensor_cores = 1;
+
 template <typename Kern>
 static int set_smem(Kern k, size_t bytes) {
   return (int)cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -392,10 +394,15 @@ int launch_forward(const float* wpack, const float* attr, const float* dens, con
                                                          ws.Ps[0], B, N);
   PILE_CHECK_LAUNCH();
   if (ev) cudaEventRecord(ev[1], st);
-  k_edge_encode<<<g_edge, NT, sizeof(EdgeEncSmem), st>>>(wpack, attr, dens, s_cur, s_cur_stride, csr.rowptr,
-                                                         csr.col, csr.row, mk ? mk->re0 : nullptr,
-                                                         mk ? mk->re1 : nullptr, mk ? mk->re2 : nullptr, ws.Ce, B, N);
-  PILE_CHECK_LAUNCH();
+  if (g_use_tensor_cores) {
+    const int e = launch_edge_encode_tc(wpack, attr, dens, s_cur, s_cur_stride, csr, mk, ws.Ce, B, N, st);
+    if (e) return e;
+  } else {
+    k_edge_encode<<<g_edge, NT, sizeof(EdgeEncSmem), st>>>(wpack, attr, dens, s_cur, s_cur_stride, csr.rowptr,
+                                                           csr.col, csr.row, mk ? mk->re0 : nullptr,
+                                                           mk ? mk->re1 : nullptr, mk ? mk->re2 : nullptr, ws.Ce, B, N);
+    PILE_CHECK_LAUNCH();
+  }
   for (int p = 0; p < PSTEP; ++p) {
     const int in = p & 1, out = in ^ 1;
     if (ev) cudaEventRecord(ev[2 + p], st);

@@ -54,6 +54,12 @@ int launch_forward(const float* wpack, const float* attr, const float* dens, con
                    const Masks* masks, float* s_out, long long s_out_stride, int B, int N, cudaStream_t st,
                    cudaEvent_t* ev = nullptr);   // ev: 6 events recorded before each kernel and after the last
 
+// process-wide switch: 1 = tcgen05 GEMM tiles for the relation encoder (default), 0 = FP32 CUDA-core tiles
+extern int g_use_tensor_cores;
+int launch_edge_encode_tc(const float* wpack, const float* attr, const float* dens, const float* s_cur,
+                          long long s_stride, const Csr& csr, const Masks* mk, float* Ce, int B, int N,
+                          cudaStream_t st);
+
 int launch_reward(const float* states, long long n_states, long long state_stride, int N, const float* goal_img,
                   int Hh, int Ww, const float* goal_coor, int M, float fx, float fy, float cx, float cy,
                   float off_x, float off_y, int normalize, float* reward, int* argmin_out, cudaStream_t st);

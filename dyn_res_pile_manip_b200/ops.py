@@ -16,13 +16,20 @@ KMAX = 10
 # must list the slots of enum WSlot (csrc/common.cuh) in order; checked against the library at pack time
 WSLOTS = ["W_PE0T", "B_PE0", "W_PE1T", "B_PE1", "W_RE0T", "B_RE0", "W_RE1T", "B_RE1", "W_RE2T", "B_RE2",
           "W_ET", "W_RT", "W_ST", "WD_RP", "B_RP", "W_PT", "W_AT", "WD_PP", "B_PP", "W_V0T", "B_V0", "W_V1T", "B_V1",
-          "W_PE0", "W_PE1", "W_RE0", "W_RE1", "W_RE2", "W_E", "W_R", "W_S", "W_P", "W_A", "W_V0", "W_V1"]
+          "W_PE0", "W_PE1", "W_RE0", "W_RE1", "W_RE2", "W_E", "W_R", "W_S", "W_P", "W_A", "W_V0", "W_V1",
+          "TC_RE1", "TC_RE2", "TC_E"]
 
 CKPT_KEYS = [  # reference checkpoint layout, SURVEY.md §8b
     "model.particle_encoder.model.0", "model.particle_encoder.model.2",
     "model.relation_encoder.model.0", "model.relation_encoder.model.2", "model.relation_encoder.model.4",
     "model.particle_propagator.linear", "model.relation_propagator.linear",
     "model.particle_predictor.linear_0", "model.particle_predictor.linear_1"]
+
+
+def set_tensor_cores(enable):
+    """Select the GEMM engine of the relation encoder: True = tcgen05 tiles (default), False = FP32 CUDA cores.
+    Returns the previous setting."""
+    return bool(_lib.load().pile_set_tensor_cores(int(bool(enable))))
 
 
 def _stream():
@@ -56,6 +63,18 @@ def _pad_cols(m, cols):
     return out
 
 
+def tc_operand(w):
+    """[out=64][in=64] fp32 weight -> bf16 (hi | lo) in the canonical K-major UMMA layout (csrc/tc.cuh):
+    element (n, k) at bf16 index (k//8)*512 + (n//8)*64 + (n%8)*8 + (k%8); returned as float32 words."""
+    n_out, n_in = w.shape
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+
+    def canon(x):
+        return x.view(n_out // 8, 8, n_in // 8, 8).permute(2, 0, 1, 3).contiguous().reshape(-1)
+    return torch.cat([canon(hi), canon(lo)]).view(torch.float32)
+
+
 def pack_weights(state, device):
     """18 checkpoint tensors -> the packed float buffer the kernels read (layout: csrc/common.cuh)."""
     lib = _lib.load()
@@ -79,6 +98,7 @@ def pack_weights(state, device):
         "W_PE0": _pad_cols(pe0, 8), "W_PE1": pe1, "W_RE0": _pad_cols(re0, 8), "W_RE1": re1, "W_RE2": re2,
         "W_E": rp[:, 0:H], "W_R": rp[:, H:2 * H], "W_S": rp[:, 2 * H:3 * H], "W_P": pp[:, 0:H], "W_A": pp[:, H:2 * H],
         "W_V0": v0, "W_V1": _pad_rows(v1, 4),
+        "TC_RE1": tc_operand(re1), "TC_RE2": tc_operand(re2), "TC_E": tc_operand(rp[:, 0:H].contiguous()),
     }
     if lib.pile_wpack_num_slots() != len(WSLOTS):
         raise _lib.PileLibraryError("weight-slot table out of sync with libpilegnn")

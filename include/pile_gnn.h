@@ -5,8 +5,9 @@
  * (ctypes stub in INTEGRATION.md); each one names the reference code it replaces.
  *
  * Conventions: every pointer is a DEVICE pointer unless stated; float32 / int32, row-major, contiguous;
- * `stream` is a cudaStream_t passed as void*; nothing allocates, nothing synchronises, no global state
- * except one-time kernel attribute setup.  Return value: 0 = ok, otherwise a cudaError_t value
+ * `stream` is a cudaStream_t passed as void*; nothing allocates, nothing synchronises (except the
+ * measurement hook), no global state except one-time kernel attribute setup and the pile_set_tensor_cores
+ * switch.  Return value: 0 = ok, otherwise a cudaError_t value
  * (cudaErrorInvalidValue for rejected arguments).  All launches are CUDA-graph capturable.
  */
 #ifndef PILE_GNN_H
@@ -25,6 +26,12 @@ int pile_abi_version(void);
 int pile_nf_effect(void);        /* hidden width compiled in (config train.particle.nf_effect = 64) */
 int pile_max_relations(void);    /* 10, model/gnn_dyn.py:231 */
 const char* pile_error_string(int code);
+
+/* GEMM engine of the relation encoder: 1 (default) = tcgen05/TMEM tensor-core tiles with bf16 hi/lo split
+ * operands (3 passes, fp32 accumulate), 0 = FP32 CUDA-core tiles (the bit-for-bit stable parity anchor).
+ * Process-wide; returns the previous setting. */
+int pile_set_tensor_cores(int enable);
+int pile_get_tensor_cores(void);
 
 /* ---- packed weights ---------------------------------------------------------------------------
  * The host packs the 18 checkpoint tensors into one float buffer; slots are listed in

@@ -14,6 +14,19 @@ POS_TOL = 1e-4       # north_star: positions within 1e-4 relative after one step
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True, params=["fp32", "tc"])
+def engine(request):
+    """Every parity test runs on both GEMM engines: FP32 CUDA-core tiles and tcgen05 (bf16 hi/lo split) tiles."""
+    old = ops.set_tensor_cores(request.param == "tc")
+    yield request.param
+    ops.set_tensor_cores(old)
+
+
+def atol_for(engine):
+    # fp32 engine: summation-order noise only; tensor-core engine: 3-pass split keeps ~2^-16 per product
+    return 5e-6 if engine == "fp32" else 4e-5
+
+
 def relerr(a, b):
     a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
     return float((a - b).norm() / b.norm())
@@ -77,31 +90,31 @@ def test_relations_duplicate_points_lowest_index_wins():
 
 
 @pytest.mark.parametrize("case", ["A", "B", "C"])
-def test_one_step_positions_vs_reference(golden, model, case):
+def test_one_step_positions_vs_reference(golden, model, case, engine):
     g = {k.split("/")[1]: v for k, v in golden.items() if k.startswith(case + "/")}
     B, N, _ = g["s_cur"].shape
     a = cuda(g["a_cur"]) if "a_cur" in g else torch.zeros(B, N, device=DEV)
     out = model.predict_one_step(a, cuda(g["s_cur"]), cuda(g["s_delta"]), cuda(g["dens"]), g.get("nums"))
     assert relerr(out, g["s_pred"]) < POS_TOL
     valid = slice(None)
-    np.testing.assert_allclose(out.cpu().numpy()[valid], g["s_pred"][valid], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(out.cpu().numpy()[valid], g["s_pred"][valid], rtol=0, atol=atol_for(engine))
     assert np.array_equal(coo_from_relations(model.relations_of_last_step()), g["rel"])
 
 
-def test_forward_accepts_dense_one_hot_relations(golden, model, golden_weights):
+def test_forward_accepts_dense_one_hot_relations(golden, model, golden_weights, engine):
     s, sd, dn = (torch.from_numpy(golden["A/" + k]) for k in ("s_cur", "s_delta", "dens"))
     adj = O.adjacency(s, sd, 0.08)
     Rr, Rs = O.one_hot_relations(adj)
     perm = torch.randperm(Rr.shape[1])
     out = model.model.forward(torch.zeros(4, 100, device=DEV), s.to(DEV), sd.to(DEV), Rr[:, perm].to(DEV),
                               Rs[:, perm].to(DEV), dn.to(DEV))
-    np.testing.assert_allclose(out.cpu().numpy(), golden["A/s_pred"], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(out.cpu().numpy(), golden["A/s_pred"], rtol=0, atol=atol_for(engine))
     rel = ops.build_relations(s.to(DEV), sd.to(DEV), 0.08)
     out2 = model.model.forward(torch.zeros(4, 100, device=DEV), s.to(DEV), sd.to(DEV), rel, None, dn.to(DEV))
     assert torch.equal(out, out2)
 
 
-def test_rollout_reward_gradient_vs_reference(golden, model, planner):
+def test_rollout_reward_gradient_vs_reference(golden, model, planner, engine):
     n_batch, n_sample, N, T = 2, 3, 60, 4
     planner.particle_num = N
     acts = cuda(golden["D/acts"]).requires_grad_(True)
@@ -114,11 +127,12 @@ def test_rollout_reward_gradient_vs_reference(golden, model, planner):
     goal = cuda(synthetic.make_goal(str(golden["D/goal_kind"])))
     obs = pred.reshape(n_sample * n_batch, 1, T, N, 3).permute(0, 2, 1, 3, 4)
     reward, next_r = planner.ptcl_evaluate_traj(obs, goal, cuda(golden["D/goal_coor"]))
-    np.testing.assert_allclose(reward.detach().cpu().numpy(), golden["D/reward"], rtol=2e-5)
-    np.testing.assert_allclose(next_r.detach().cpu().numpy(), golden["D/next_r"], rtol=2e-5)
+    rtol = 2e-5 if engine == "fp32" else 2e-4
+    np.testing.assert_allclose(reward.detach().cpu().numpy(), golden["D/reward"], rtol=rtol)
+    np.testing.assert_allclose(next_r.detach().cpu().numpy(), golden["D/next_r"], rtol=rtol)
     torch.sum(-reward).backward()
     g, ref = acts.grad.cpu().numpy(), golden["D/act_grad"]
-    np.testing.assert_allclose(g, ref, rtol=5e-3, atol=5e-4 * np.abs(ref).max())
+    np.testing.assert_allclose(g, ref, rtol=5e-3, atol=(5e-4 if engine == "fp32" else 3e-3) * np.abs(ref).max())
 
 
 def test_rollout_relation_sets_every_step(golden, model, planner):
@@ -144,7 +158,8 @@ def test_step_gradients_vs_oracle_autograd(golden, model, golden_weights):
     s2 = s.detach().to(DEV).requires_grad_(True)
     sd2 = sd.detach().to(DEV).requires_grad_(True)
     (model.predict_one_step(a.to(DEV), s2, sd2, dn.to(DEV)) * wgt.to(DEV)).sum().backward()
-    assert relerr(s2.grad, s.grad) < 1e-4 and relerr(sd2.grad, sd.grad) < 1e-4
+    tol = 1e-4 if ops._lib.load().pile_get_tensor_cores() == 0 else 2e-3
+    assert relerr(s2.grad, s.grad) < tol and relerr(sd2.grad, sd.grad) < tol
 
 
 def test_s_delta_gradients_vs_oracle_autograd(golden, planner):
