@@ -34,6 +34,8 @@ ScratchView carve_scratch(void* p, int B, int N) {
   ScratchView v;
   v.ws.s_delta = c.take<float>(R * 3);
   v.ws.Ce = c.take<float>(E * H);
+  v.ws.efeat = c.take<float>((E + TILE) * 8);
+  v.ws.agg = c.take<float>(R * H);
   v.ws.Cp = c.take<float>(R * H);
   v.ws.eff = c.take<float>(R * H);
   v.ws.Pr[0] = c.take<float>(R * H);
@@ -104,6 +106,8 @@ int pile_set_tensor_cores(int enable) {
   return old;
 }
 int pile_get_tensor_cores(void) { return g_use_tensor_cores; }
+
+int pile_debug_set_trace(long long* device_buf, int capacity) { return set_edge_trace(device_buf, capacity); }
 
 int pile_wpack_num_slots(void) { return W_NUM; }
 long long pile_wpack_slot_offset(int slot) { return (slot < 0 || slot > W_NUM) ? -1 : wslot_offset(slot); }

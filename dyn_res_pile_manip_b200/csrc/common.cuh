@@ -20,6 +20,7 @@ constexpr int LDA = H + 4;     // shared-memory activation row stride (conflict-
 constexpr int LDX = 12;        // shared-memory stride of the 8-wide input feature tile
 constexpr int NT = 256;        // threads per GEMM CTA: 8 warps x (4 rows/lane x 8 cols/warp)
 constexpr int NSM = 148;
+constexpr int TC_NODE_FLOATS = 29952;   // 117 KB of bf16 hi/lo weight images, layout in node_tc.cu
 
 // ---- packed weight buffer (floats). Forward blocks are transposed [K][H]; backward blocks keep the
 // checkpoint's [out][in] layout (that IS the [K=out][cols=in] operand of the dgrad GEMM).
@@ -42,9 +43,11 @@ enum WSlot {
   W_PE0,              // [H][8]
   W_PE1, W_RE0 /*[H][8]*/, W_RE1, W_RE2, W_E, W_R, W_S, W_P, W_A, W_V0,
   W_V1,               // [4][H] (row 3 zero)
-  // tensor-core operands: [hi | lo] bf16 in the canonical K-major UMMA layout (tc.cuh), H*H floats each.
-  // TC_RE1, TC_RE2, TC_E must stay adjacent: k_edge_encode_tc fetches them with one bulk copy.
-  TC_RE1, TC_RE2, TC_E,
+  // tensor-core operands of the relation encoder (edge_tc.cu): bf16 [hi | lo] images in the canonical
+  // K-major UMMA layout (tc.cuh) of W0aug [64 x 16], W1aug, W2aug, WEaug [64 x 80]; 64 KB, one bulk copy
+  TC_EDGE,
+  // tensor-core operands of the particle kernels (node_tc.cu): PE0aug, PE1aug, WPaug, [W_r;W_s], W_a, V0aug, V1aug
+  TC_NODE,
   W_NUM
 };
 
@@ -55,6 +58,8 @@ __host__ __device__ inline int wslot_size(int s) {
     case WD_PP: case B_PP: case B_V0: return H;
     case W_V1T: case W_V1: return 4 * H;
     case B_V1: return 4;
+    case TC_EDGE: return 4 * H * H;
+    case TC_NODE: return TC_NODE_FLOATS;
     default: return H * H;
   }
 }

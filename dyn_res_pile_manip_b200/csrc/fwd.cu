@@ -388,21 +388,31 @@ int launch_forward(const float* wpack, const float* attr, const float* dens, con
   const int g_node = node_tiles < persistent ? node_tiles : persistent;
   const int g_edge = edge_tiles < persistent ? (int)edge_tiles : persistent;
 
+  if (g_use_tensor_cores) {
+    // tcgen05 path: every dense contraction on the tensor cores, the gather/segmented sum as its own
+    // streaming kernel
+    int e;
+    if (ev) cudaEventRecord(ev[0], st);
+    if ((e = launch_node_encode_tc(wpack, attr, dens, s_delta, mk, ws, B, N, st))) return e;
+    if (ev) cudaEventRecord(ev[1], st);
+    if ((e = launch_edge_encode_tc(wpack, attr, dens, s_cur, s_cur_stride, csr, mk, ws.efeat, ws.Ce, B, N, st))) return e;
+    for (int p = 0; p < PSTEP; ++p) {
+      if (ev) cudaEventRecord(ev[2 + p], st);
+      if ((e = launch_propagate_tc(wpack, csr, ws, mk, p, s_cur, s_cur_stride, s_out, s_out_stride, B, N, st))) return e;
+    }
+    if (ev) cudaEventRecord(ev[2 + PSTEP], st);
+    return 0;
+  }
   if (ev) cudaEventRecord(ev[0], st);
   k_node_encode<<<g_node, NT, sizeof(NodeEncSmem), st>>>(wpack, attr, dens, s_delta, mk ? mk->pe0 : nullptr,
                                                          mk ? mk->pe1 : nullptr, ws.Cp, ws.eff, ws.Pr[0],
                                                          ws.Ps[0], B, N);
   PILE_CHECK_LAUNCH();
   if (ev) cudaEventRecord(ev[1], st);
-  if (g_use_tensor_cores) {
-    const int e = launch_edge_encode_tc(wpack, attr, dens, s_cur, s_cur_stride, csr, mk, ws.Ce, B, N, st);
-    if (e) return e;
-  } else {
-    k_edge_encode<<<g_edge, NT, sizeof(EdgeEncSmem), st>>>(wpack, attr, dens, s_cur, s_cur_stride, csr.rowptr,
-                                                           csr.col, csr.row, mk ? mk->re0 : nullptr,
-                                                           mk ? mk->re1 : nullptr, mk ? mk->re2 : nullptr, ws.Ce, B, N);
-    PILE_CHECK_LAUNCH();
-  }
+  k_edge_encode<<<g_edge, NT, sizeof(EdgeEncSmem), st>>>(wpack, attr, dens, s_cur, s_cur_stride, csr.rowptr,
+                                                         csr.col, csr.row, mk ? mk->re0 : nullptr,
+                                                         mk ? mk->re1 : nullptr, mk ? mk->re2 : nullptr, ws.Ce, B, N);
+  PILE_CHECK_LAUNCH();
   for (int p = 0; p < PSTEP; ++p) {
     const int in = p & 1, out = in ^ 1;
     if (ev) cudaEventRecord(ev[2 + p], st);

@@ -33,6 +33,8 @@ struct Masks {
 struct StepScratch {
   float* s_delta;  // [B, N, 3]
   float* Ce;       // [B*KMAX*N, H]
+  float* efeat;    // [B*KMAX*N + TILE, 8] relation input features (tensor-core path)
+  float* agg;      // [B*N, H] receiver-aggregated relation effects (tensor-core path)
   float* Cp;       // [B*N, H]
   float* eff;      // [B*N, H]
   float* Pr[2];    // [B*N, H] ping-pong
@@ -57,8 +59,16 @@ int launch_forward(const float* wpack, const float* attr, const float* dens, con
 // process-wide switch: 1 = tcgen05 GEMM tiles for the relation encoder (default), 0 = FP32 CUDA-core tiles
 extern int g_use_tensor_cores;
 int launch_edge_encode_tc(const float* wpack, const float* attr, const float* dens, const float* s_cur,
-                          long long s_stride, const Csr& csr, const Masks* mk, float* Ce, int B, int N,
+                          long long s_stride, const Csr& csr, const Masks* mk, float* efeat, float* Ce, int B, int N,
                           cudaStream_t st);
+
+int set_edge_trace(long long* buf, int cap);
+int launch_node_encode_tc(const float* wpack, const float* attr, const float* dens, const float* s_delta,
+                          const Masks* mk, const StepScratch& ws, int B, int N, cudaStream_t st);
+// propagation step p on the tensor-core path: k_edge_agg + k_node_update_tc (p == PSTEP-1: + predictor)
+int launch_propagate_tc(const float* wpack, const Csr& csr, const StepScratch& ws, const Masks* mk, int p,
+                        const float* s_cur, long long s_stride, float* s_out, long long o_stride, int B, int N,
+                        cudaStream_t st);
 
 int launch_reward(const float* states, long long n_states, long long state_stride, int N, const float* goal_img,
                   int Hh, int Ww, const float* goal_coor, int M, float fx, float fy, float cx, float cy,

@@ -1,0 +1,407 @@
+// K2/K4/K5 on the tensor cores: particle encoder and the per-propagation-step particle update.
+//
+// The FP32 k_propagate (fwd.cu) interleaves a memory-bound gather with FFMA GEMMs inside one CTA; here
+// the propagation step (reference model/gnn_dyn.py:182-193) is split into
+//   k_edge_agg          agg[i] = sum_{e=(i<-j)} ReLU(C_e[e] + P_r[i] + P_s[j])        pure HBM/L2 streaming
+//   k_node_update_tc    eff <- ReLU(W_a agg + C_p + eff);  (P_r, P_s) <- (W_r, W_s) eff  tcgen05 tiles
+//                       last step: s_pred = s_cur + V1 ReLU(V0 eff + c0) + c1            (gnn_dyn.py:196-198)
+// and the particle encoder (gnn_dyn.py:174-176) becomes k_node_encode_tc.  GEMMs use the bf16 hi/lo split
+// (three passes, fp32 accumulation in TMEM) and fold biases through the aux K chunk, see tc_tile.cuh.
+#include "kernels.h"
+#include "tc_tile.cuh"
+
+namespace pile {
+
+// ---- TC_NODE weight slot: [hi | lo] canonical images, in this order ---------------------------------
+constexpr uint32_t NB_PE0 = 2 * b_bytes(64, 16);    //   4 KB  PE0aug  [64 x 16]  cols: s_delta(3), attr, d, bias
+constexpr uint32_t NB_K80 = 2 * b_bytes(64, 80);    //  20 KB  PE1aug / WPaug / V0aug [64 x 80]
+constexpr uint32_t NB_WRS = 2 * b_bytes(128, 64);   //  32 KB  [W_r ; W_s]  [128 x 64]
+constexpr uint32_t NB_WA = 2 * b_bytes(64, 64);     //  16 KB  W_a  [64 x 64]
+constexpr uint32_t NB_V1 = 2 * b_bytes(16, 80);     //   5 KB  V1aug [16 x 80]
+constexpr uint32_t OFF_PE0 = 0, OFF_PE1 = OFF_PE0 + NB_PE0, OFF_WP = OFF_PE1 + NB_K80, OFF_WRS = OFF_WP + NB_K80,
+                   OFF_WA = OFF_WRS + NB_WRS, OFF_V0 = OFF_WA + NB_WA, OFF_V1 = OFF_V0 + NB_K80,
+                   TC_NODE_BYTES = OFF_V1 + NB_V1;
+static_assert(TC_NODE_BYTES == 4 * TC_NODE_FLOATS, "TC_NODE slot size (common.cuh) out of sync");
+
+constexpr uint32_t NODE_TMEM_PER_GROUP = 128;
+
+template <uint32_t WBYTES>
+struct NodeTcSmem {
+  alignas(128) uint8_t w[WBYTES];
+  GroupTile t[TC_GROUPS];
+  alignas(128) uint8_t zero[A_LBO];
+  uint64_t bar[TC_GROUPS];
+  uint64_t w_bar;
+  uint32_t tmem_base;
+};
+using NodeEncSmemTc = NodeTcSmem<OFF_WA>;                 // PE0, PE1, WP, WRS = 76 KB
+using NodeUpdSmemTc = NodeTcSmem<NB_WRS + NB_WA>;         // 48 KB (non-last: WRS, WA; last: WA, V0, V1 = 41 KB)
+static_assert(sizeof(NodeEncSmemTc) <= 227 * 1024, "shared memory budget");
+
+template <typename Smem>
+__device__ __forceinline__ GroupCtx tile_prologue(Smem& S, const float* wpack, uint32_t w_off, uint32_t w_bytes) {
+  const int g = threadIdx.x / GROUP_THREADS, t = threadIdx.x % GROUP_THREADS;
+  if (threadIdx.x < 32) tc::tmem_alloc(&S.tmem_base, TC_GROUPS * NODE_TMEM_PER_GROUP);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_GROUPS; ++i) tc::mbar_init(&S.bar[i], 1);
+    tc::mbar_init(&S.w_bar, 1);
+    tc::mbar_init_fence();
+  }
+  for (int i = threadIdx.x * 16; i < (int)A_LBO; i += TC_THREADS * 16) *reinterpret_cast<uint4*>(S.zero + i) = make_uint4(0, 0, 0, 0);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (threadIdx.x == 0) {
+    tc::mbar_expect_tx(&S.w_bar, w_bytes);
+    tc::bulk_g2s(S.w, reinterpret_cast<const uint8_t*>(wpack + wslot_offset(TC_NODE)) + w_off, w_bytes, &S.w_bar);
+  }
+  GroupCtx c;
+  c.g = g;
+  c.wig = t >> 5;
+  c.tmem_d = S.tmem_base + g * NODE_TMEM_PER_GROUP;
+  c.taddr = c.tmem_d + ((uint32_t)((c.wig & 3) * 32) << 16);
+  c.a_hi = tc::smem_u32(S.t[g].a[0]);
+  c.a_lo = tc::smem_u32(S.t[g].a[1]);
+  c.aux_hi = tc::smem_u32(S.t[g].aux[0]);
+  c.aux_lo = tc::smem_u32(S.t[g].aux[1]);
+  c.zero = tc::smem_u32(S.zero);
+  c.bar = &S.bar[g];
+  c.phase = 0;
+  return c;
+}
+
+template <typename Smem>
+__device__ __forceinline__ void tile_epilogue(Smem& S) {
+  tc::fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_dealloc(S.tmem_base, TC_GROUPS * NODE_TMEM_PER_GROUP);
+}
+
+__device__ __forceinline__ void st16(float* __restrict__ p, const float (&v)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) st4(p + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// particle encoder: p_enc (= effect_0), C_p, and (P_r, P_s) of propagation step 0
+// ------------------------------------------------------------------------------------------------
+template <bool RECORD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr, const float* __restrict__ dens,
+                 const float* __restrict__ s_delta, uint8_t* __restrict__ m_pe0, uint8_t* __restrict__ m_pe1,
+                 float* __restrict__ Cp, float* __restrict__ eff, float* __restrict__ Pr, float* __restrict__ Ps,
+                 int B, int N) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  NodeEncSmemTc& S = *reinterpret_cast<NodeEncSmemTc*>(smem_raw);
+  GroupCtx c = tile_prologue(S, wpack, OFF_PE0, OFF_WA);
+  const int g = c.g, wig = c.wig;
+  const int r = (wig & 3) * 32 + (threadIdx.x & 31), half = wig >> 2;
+  uint8_t* const a_hi = S.t[g].a[0];
+  uint8_t* const a_lo = S.t[g].a[1];
+  const uint32_t row_off = (r >> 3) * A_SBO + (r & 7) * 16;
+  const uint32_t w = tc::smem_u32(S.w);
+  const long long R = (long long)B * N;
+  const long long ntiles = (R + TILE - 1) / TILE;
+  tc::mbar_wait(&S.w_bar, 0);
+
+  for (long long tile = (long long)blockIdx.x * TC_GROUPS + g; tile < ntiles; tile += (long long)gridDim.x * TC_GROUPS) {
+    const long long row = tile * TILE + r;
+    const bool valid = row < R;
+    float d = 0.f;
+    if (valid) d = dens[row / N] / 5000.f;
+    if (half == 0) {
+      float f[8] = {0.f, 0.f, 0.f, 0.f, d, 1.f, 0.f, 0.f};
+      if (valid) { f[0] = s_delta[row * 3]; f[1] = s_delta[row * 3 + 1]; f[2] = s_delta[row * 3 + 2]; f[3] = attr[row]; }
+      store_chunk(a_hi, a_lo, row_off, f);
+    } else {
+      const float f[8] = {1.f, d, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      store_chunk(S.t[g].aux[0], S.t[g].aux[1], row_off, f);
+    }
+    // PE layer 0
+    run_gemm(c, [&](uint32_t el) { issue_gemm_k16<64>(el, c.tmem_d, c.a_hi, c.a_lo, c.zero, w + OFF_PE0, w + OFF_PE0 + NB_PE0 / 2); });
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float v[16];
+      tc::tmem_ld16(c.taddr + half * 32 + q * 16, v);
+      tc::tmem_ld_wait();
+      const uint32_t m = relu_to_tile<RECORD>(a_hi, a_lo, row_off + (half * 4 + q * 2) * A_LBO, v);
+      if (RECORD && valid) *reinterpret_cast<uint16_t*>(m_pe0 + row * 8 + half * 4 + q * 2) = (uint16_t)m;
+    }
+    // PE layer 1 -> particle_encode = effect_0
+    run_gemm(c, [&](uint32_t el) {
+      issue_gemm<64, 4, true>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w + OFF_PE1, w + OFF_PE1 + NB_K80 / 2);
+    });
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float v[16];
+      tc::tmem_ld16(c.taddr + half * 32 + q * 16, v);
+      tc::tmem_ld_wait();
+      const uint32_t m = relu_to_tile<RECORD>(a_hi, a_lo, row_off + (half * 4 + q * 2) * A_LBO, v);
+      if (valid) {
+        st16(eff + row * H + half * 32 + q * 16, v);
+        if (RECORD) *reinterpret_cast<uint16_t*>(m_pe1 + row * 8 + half * 4 + q * 2) = (uint16_t)m;
+      }
+    }
+    // C_p = W_p p_enc + w_d d + b
+    run_gemm(c, [&](uint32_t el) {
+      issue_gemm<64, 4, true>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w + OFF_WP, w + OFF_WP + NB_K80 / 2);
+    });
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float v[16];
+      tc::tmem_ld16(c.taddr + half * 32 + q * 16, v);
+      tc::tmem_ld_wait();
+      if (valid) st16(Cp + row * H + half * 32 + q * 16, v);
+    }
+    // (P_r, P_s) = (W_r, W_s) p_enc : one N = 128 product, column half 0 -> P_r, half 1 -> P_s
+    run_gemm(c, [&](uint32_t el) {
+      issue_gemm<128, 4, false>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w + OFF_WRS, w + OFF_WRS + NB_WRS / 2);
+    });
+    {
+      float* dst = (half == 0 ? Pr : Ps) + row * H;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[16];
+        tc::tmem_ld16(c.taddr + half * 64 + q * 16, v);
+        tc::tmem_ld_wait();
+        if (valid) st16(dst + q * 16, v);
+      }
+    }
+  }
+  tile_epilogue(S);
+}
+
+// ------------------------------------------------------------------------------------------------
+// receiver-segmented sum of the relation effects (memory-bound; no weights, high occupancy)
+// ------------------------------------------------------------------------------------------------
+template <bool RECORD>
+__global__ void __launch_bounds__(256)
+k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ Ce,
+           const float* __restrict__ Pr, const float* __restrict__ Ps, uint8_t* __restrict__ m_edge,
+           float* __restrict__ agg, int B, int N) {
+  const int l16 = threadIdx.x & 15;
+  const unsigned hmask = 0xffffu << (threadIdx.x & 16);
+  const long long R = (long long)B * N;
+  const long long nhw = (long long)gridDim.x * (blockDim.x >> 4);
+  for (long long node = (long long)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); node < R; node += nhw) {
+    const int b = (int)(node / N), i = (int)(node % N);
+    const int* rp = rowptr + (long long)b * (N + 1) + i;
+    const int e_lo = rp[0], cnt = rp[1] - e_lo;
+    const long long slot = (long long)b * KMAX * N + e_lo;
+    const float4 pr = ld4(Pr + node * H + 4 * l16);
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k0 = 0; k0 < cnt; k0 += 5) {
+      float4 ce[5], ps[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        if (k0 + k < cnt) {
+          const int s = col[slot + k0 + k];
+          ce[k] = ld4(Ce + (slot + k0 + k) * H + 4 * l16);
+          ps[k] = ld4(Ps + ((long long)b * N + s) * H + 4 * l16);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        if (k0 + k < cnt) {
+          float4 v = make_float4(ce[k].x + pr.x + ps[k].x, ce[k].y + pr.y + ps[k].y, ce[k].z + pr.z + ps[k].z,
+                                 ce[k].w + pr.w + ps[k].w);
+          if (RECORD) {
+            const unsigned m4 = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
+            const unsigned hi = __shfl_down_sync(hmask, m4, 1);
+            if ((l16 & 1) == 0) m_edge[(slot + k0 + k) * 8 + (l16 >> 1)] = (uint8_t)(m4 | (hi << 4));
+          }
+          sum.x += fmaxf(v.x, 0.f); sum.y += fmaxf(v.y, 0.f); sum.z += fmaxf(v.z, 0.f); sum.w += fmaxf(v.w, 0.f);
+        }
+      }
+    }
+    st4(agg + node * H + 4 * l16, sum);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// particle update of one propagation step (LAST: + predictor and residual state update)
+// ------------------------------------------------------------------------------------------------
+template <bool LAST, bool RECORD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg, const float* __restrict__ Cp,
+                 float* __restrict__ eff, float* __restrict__ PrOut, float* __restrict__ PsOut,
+                 uint8_t* __restrict__ m_eff, uint8_t* __restrict__ m_q, const float* __restrict__ s_cur,
+                 long long s_stride, float* __restrict__ s_out, long long o_stride, int B, int N) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  NodeUpdSmemTc& S = *reinterpret_cast<NodeUpdSmemTc*>(smem_raw);
+  // non-last: [WRS | WA]; last: [WA | V0 | V1]
+  GroupCtx c = tile_prologue(S, wpack, LAST ? OFF_WA : OFF_WRS, LAST ? (NB_WA + NB_K80 + NB_V1) : (NB_WRS + NB_WA));
+  const int g = c.g, wig = c.wig;
+  const int r = (wig & 3) * 32 + (threadIdx.x & 31), half = wig >> 2;
+  uint8_t* const a_hi = S.t[g].a[0];
+  uint8_t* const a_lo = S.t[g].a[1];
+  const uint32_t row_off = (r >> 3) * A_SBO + (r & 7) * 16;
+  const uint32_t w = tc::smem_u32(S.w);
+  const uint32_t w_a = LAST ? w : w + NB_WRS;
+  const uint32_t w_rs = w;                                  // non-last only
+  const uint32_t w_v0 = w + NB_WA, w_v1 = w + NB_WA + NB_K80;   // last only
+  const long long R = (long long)B * N;
+  const long long ntiles = (R + TILE - 1) / TILE;
+  if (LAST && half == 1) {       // constant aux chunk (1, 0, ...) for the predictor biases
+    const float f[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    store_chunk(S.t[g].aux[0], S.t[g].aux[1], row_off, f);
+  }
+  tc::mbar_wait(&S.w_bar, 0);
+
+  for (long long tile = (long long)blockIdx.x * TC_GROUPS + g; tile < ntiles; tile += (long long)gridDim.x * TC_GROUPS) {
+    const long long row = tile * TILE + r;
+    const bool valid = row < R;
+    // A = split(agg row)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float4 x[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        x[j] = valid ? ld4(agg + row * H + half * 32 + q * 16 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float o[8] = {x[2 * h].x, x[2 * h].y, x[2 * h].z, x[2 * h].w, x[2 * h + 1].x, x[2 * h + 1].y, x[2 * h + 1].z,
+                            x[2 * h + 1].w};
+        store_chunk(a_hi, a_lo, row_off + (half * 4 + q * 2 + h) * A_LBO, o);
+      }
+    }
+    run_gemm(c, [&](uint32_t el) {
+      issue_gemm<64, 4, false>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w_a, w_a + NB_WA / 2);
+    });
+    // eff <- ReLU(W_a agg + C_p + eff)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float4 a[4], e[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a[j] = valid ? ld4(Cp + row * H + half * 32 + q * 16 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        e[j] = valid ? ld4(eff + row * H + half * 32 + q * 16 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float v[16];
+      tc::tmem_ld16(c.taddr + half * 32 + q * 16, v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j * 4 + 0] += a[j].x + e[j].x; v[j * 4 + 1] += a[j].y + e[j].y;
+        v[j * 4 + 2] += a[j].z + e[j].z; v[j * 4 + 3] += a[j].w + e[j].w;
+      }
+      const uint32_t m = relu_to_tile<RECORD>(a_hi, a_lo, row_off + (half * 4 + q * 2) * A_LBO, v);
+      if (valid) {
+        if (!LAST) st16(eff + row * H + half * 32 + q * 16, v);
+        if (RECORD) *reinterpret_cast<uint16_t*>(m_eff + row * 8 + half * 4 + q * 2) = (uint16_t)m;
+      }
+    }
+    if (!LAST) {
+      run_gemm(c, [&](uint32_t el) {
+        issue_gemm<128, 4, false>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w_rs, w_rs + NB_WRS / 2);
+      });
+      float* dst = (half == 0 ? PrOut : PsOut) + row * H;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[16];
+        tc::tmem_ld16(c.taddr + half * 64 + q * 16, v);
+        tc::tmem_ld_wait();
+        if (valid) st16(dst + q * 16, v);
+      }
+    } else {
+      // predictor: q = ReLU(V0 eff + c0);  s_pred = s_cur + V1 q + c1
+      run_gemm(c, [&](uint32_t el) {
+        issue_gemm<64, 4, true>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w_v0, w_v0 + NB_K80 / 2);
+      });
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float v[16];
+        tc::tmem_ld16(c.taddr + half * 32 + q * 16, v);
+        tc::tmem_ld_wait();
+        const uint32_t m = relu_to_tile<RECORD>(a_hi, a_lo, row_off + (half * 4 + q * 2) * A_LBO, v);
+        if (RECORD && valid) *reinterpret_cast<uint16_t*>(m_q + row * 8 + half * 4 + q * 2) = (uint16_t)m;
+      }
+      run_gemm(c, [&](uint32_t el) {
+        issue_gemm<16, 4, true>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w_v1, w_v1 + NB_V1 / 2);
+      });
+      if (half == 0) {
+        float v[16];
+        tc::tmem_ld16(c.taddr, v);
+        tc::tmem_ld_wait();
+        if (valid) {
+          const int b = (int)(row / N), i = (int)(row % N);
+          const float* sc = s_cur + (long long)b * s_stride + i * 3;
+          float* so = s_out + (long long)b * o_stride + i * 3;
+          so[0] = v[0] + sc[0];
+          so[1] = v[1] + sc[1];
+          so[2] = v[2] + sc[2];
+        }
+      }
+    }
+  }
+  tile_epilogue(S);
+}
+
+template <typename Kern>
+static int set_smem_tc(Kern k, size_t bytes) {
+  return (int)cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static int tc_grid(long long ntiles) {
+  const long long want = (ntiles + TC_GROUPS - 1) / TC_GROUPS;
+  return (int)(want < 1 ? 1 : (want < NSM ? want : NSM));
+}
+
+int launch_node_encode_tc(const float* wpack, const float* attr, const float* dens, const float* s_delta,
+                          const Masks* mk, const StepScratch& ws, int B, int N, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    int e;
+    if ((e = set_smem_tc(k_node_encode_tc<false>, sizeof(NodeEncSmemTc)))) return e;
+    if ((e = set_smem_tc(k_node_encode_tc<true>, sizeof(NodeEncSmemTc)))) return e;
+    if ((e = set_smem_tc(k_node_update_tc<false, false>, sizeof(NodeUpdSmemTc)))) return e;
+    if ((e = set_smem_tc(k_node_update_tc<false, true>, sizeof(NodeUpdSmemTc)))) return e;
+    if ((e = set_smem_tc(k_node_update_tc<true, false>, sizeof(NodeUpdSmemTc)))) return e;
+    if ((e = set_smem_tc(k_node_update_tc<true, true>, sizeof(NodeUpdSmemTc)))) return e;
+    configured = true;
+  }
+  const long long ntiles = ((long long)B * N + TILE - 1) / TILE;
+  if (mk)
+    k_node_encode_tc<true><<<tc_grid(ntiles), TC_THREADS, sizeof(NodeEncSmemTc), st>>>(
+        wpack, attr, dens, s_delta, mk->pe0, mk->pe1, ws.Cp, ws.eff, ws.Pr[0], ws.Ps[0], B, N);
+  else
+    k_node_encode_tc<false><<<tc_grid(ntiles), TC_THREADS, sizeof(NodeEncSmemTc), st>>>(
+        wpack, attr, dens, s_delta, nullptr, nullptr, ws.Cp, ws.eff, ws.Pr[0], ws.Ps[0], B, N);
+  PILE_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_propagate_tc(const float* wpack, const Csr& csr, const StepScratch& ws, const Masks* mk, int p,
+                        const float* s_cur, long long s_stride, float* s_out, long long o_stride, int B, int N,
+                        cudaStream_t st) {
+  const int in = p & 1, out = in ^ 1;
+  const long long R = (long long)B * N;
+  const long long ntiles = (R + TILE - 1) / TILE;
+  const int agg_blocks = (int)((R + 15) / 16 < 8 * NSM ? (R + 15) / 16 : 8 * NSM);
+  if (mk)
+    k_edge_agg<true><<<agg_blocks, 256, 0, st>>>(csr.rowptr, csr.col, ws.Ce, ws.Pr[in], ws.Ps[in], mk->edge[p], ws.agg, B, N);
+  else
+    k_edge_agg<false><<<agg_blocks, 256, 0, st>>>(csr.rowptr, csr.col, ws.Ce, ws.Pr[in], ws.Ps[in], nullptr, ws.agg, B, N);
+  PILE_CHECK_LAUNCH();
+  const int grid = tc_grid(ntiles);
+  const size_t sm = sizeof(NodeUpdSmemTc);
+  if (p < PSTEP - 1) {
+    if (mk)
+      k_node_update_tc<false, true><<<grid, TC_THREADS, sm, st>>>(wpack, ws.agg, ws.Cp, ws.eff, ws.Pr[out], ws.Ps[out],
+                                                                  mk->eff[p], nullptr, s_cur, s_stride, s_out, o_stride, B, N);
+    else
+      k_node_update_tc<false, false><<<grid, TC_THREADS, sm, st>>>(wpack, ws.agg, ws.Cp, ws.eff, ws.Pr[out], ws.Ps[out],
+                                                                   nullptr, nullptr, s_cur, s_stride, s_out, o_stride, B, N);
+  } else {
+    if (mk)
+      k_node_update_tc<true, true><<<grid, TC_THREADS, sm, st>>>(wpack, ws.agg, ws.Cp, ws.eff, nullptr, nullptr, mk->eff[p],
+                                                                 mk->q, s_cur, s_stride, s_out, o_stride, B, N);
+    else
+      k_node_update_tc<true, false><<<grid, TC_THREADS, sm, st>>>(wpack, ws.agg, ws.Cp, ws.eff, nullptr, nullptr, nullptr,
+                                                                  nullptr, s_cur, s_stride, s_out, o_stride, B, N);
+  }
+  PILE_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace pile

@@ -1,0 +1,128 @@
+// Shared building blocks of the tcgen05 tile kernels (edge_tc.cu, node_tc.cu).
+//
+// Execution model: a persistent CTA (one per SM, 1024 threads) holds 4 independent GROUPS of 8 warps.
+// A group owns one 128-row tile at a time: an activation tile pair (bf16 hi / lo, canonical K-major
+// layout) in shared memory, a column range of TMEM for its accumulator and one mbarrier.  Its first warp
+// issues the MMAs (descriptor arithmetic warp-uniform, tcgen05.mma predicated on the elected lane), all 8
+// warps run the epilogues: thread (r, half) handles row r = TMEM lane and 32 of the accumulator columns
+// (warps w and w+4 of a group share a TMEM lane quarter).  While one group waits for the tensor pipe the
+// other groups run their epilogues.
+#pragma once
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace pile {
+
+constexpr int TC_GROUPS = 4;
+constexpr int GROUP_THREADS = 256;
+constexpr int TC_THREADS = TC_GROUPS * GROUP_THREADS;
+constexpr uint32_t A_SBO = 128, A_LBO = (TILE / 8) * 128;   // 2048: one 16-byte K chunk of a 128-row tile
+constexpr uint32_t A_BYTES = 8 * A_LBO;                     // 64 data columns: 16 KB per part
+constexpr uint32_t B_SBO = 128;
+__host__ __device__ constexpr uint32_t b_lbo(int n_rows) { return (uint32_t)(n_rows / 8) * 128; }
+// bytes of one part (hi or lo) of a canonical [n_rows x k] bf16 weight image
+__host__ __device__ constexpr uint32_t b_bytes(int n_rows, int k) { return (uint32_t)(k / 8) * b_lbo(n_rows); }
+
+struct GroupTile {          // per-group shared-memory operands
+  alignas(128) uint8_t a[2][A_BYTES];     // [hi, lo] activation tile, 8 K chunks
+  alignas(128) uint8_t aux[2][A_LBO];     // [hi, lo] K chunk (1, d, 0, ...): multiplies bias / density columns
+};
+
+__device__ __forceinline__ void group_barrier(int g) {
+  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(GROUP_THREADS) : "memory");
+}
+
+// D[128 x N] (=|+=) A * B^T with bf16 hi/lo split operands (three passes): KSTEPS data K-steps of the group's
+// A tile and, when AUX, one more K-step whose first chunk is the aux chunk and whose second chunk is the
+// shared all-zero chunk.  B: canonical image of [N x 16*(KSTEPS+AUX)], hi at b_hi, lo at b_lo.
+// To be executed by a CONVERGED warp; `elected` selects the issuing lane.
+template <int N, int KSTEPS, bool AUX>
+__device__ __forceinline__ void issue_gemm(uint32_t elected, uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo,
+                                           uint32_t aux_hi, uint32_t aux_lo, uint32_t zero, uint32_t b_hi,
+                                           uint32_t b_lo) {
+  constexpr uint32_t idesc = tc::make_idesc_bf16(TILE, N);
+  constexpr uint32_t BL = b_lbo(N);
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t a = pass == 1 ? a_lo : a_hi;
+    const uint32_t x = pass == 1 ? aux_lo : aux_hi;
+    const uint32_t b = pass == 2 ? b_lo : b_hi;
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k)
+      tc::mma_bf16_if(elected, tmem_d, tc::make_desc(a + k * 2 * A_LBO, A_LBO, A_SBO),
+                      tc::make_desc(b + k * 2 * BL, BL, B_SBO), idesc, (pass | k) != 0 ? 1u : 0u);
+    if (AUX)
+      tc::mma_bf16_if(elected, tmem_d, tc::make_desc(x, zero - x, A_SBO),
+                      tc::make_desc(b + KSTEPS * 2 * BL, BL, B_SBO), idesc, (KSTEPS | pass) != 0 ? 1u : 0u);
+  }
+}
+
+// input layer: a single K-step whose first chunk is chunk 0 of the A tile (features + constant 1) and whose
+// second chunk is the zero chunk; B = canonical [N x 16]
+template <int N>
+__device__ __forceinline__ void issue_gemm_k16(uint32_t elected, uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo,
+                                               uint32_t zero, uint32_t b_hi, uint32_t b_lo) {
+  constexpr uint32_t idesc = tc::make_idesc_bf16(TILE, N);
+  constexpr uint32_t BL = b_lbo(N);
+  tc::mma_bf16_if(elected, tmem_d, tc::make_desc(a_hi, zero - a_hi, A_SBO), tc::make_desc(b_hi, BL, B_SBO), idesc, 0u);
+  tc::mma_bf16_if(elected, tmem_d, tc::make_desc(a_lo, zero - a_lo, A_SBO), tc::make_desc(b_hi, BL, B_SBO), idesc, 1u);
+  tc::mma_bf16_if(elected, tmem_d, tc::make_desc(a_hi, zero - a_hi, A_SBO), tc::make_desc(b_lo, BL, B_SBO), idesc, 1u);
+}
+
+// 8 consecutive fp32 values of a row -> one 16-byte K chunk of a hi and a lo tile (off = row + chunk offset)
+__device__ __forceinline__ void store_chunk(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, const float (&v)[8]) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tc::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+  *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ReLU of 16 accumulator columns -> two K chunks of the A tile; returns the 16 sign bits
+template <bool RECORD>
+__device__ __forceinline__ uint32_t relu_to_tile(uint8_t* a_hi, uint8_t* a_lo, uint32_t off0, float (&v)[16]) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = v[h * 8 + j];
+      if (RECORD) m |= x > 0.f ? (1u << (h * 8 + j)) : 0u;
+      o[j] = fmaxf(x, 0.f);
+      v[h * 8 + j] = o[j];
+    }
+    store_chunk(a_hi, a_lo, off0 + h * A_LBO, o);
+  }
+  return m;
+}
+
+// everything a group needs to hand a layer to the tensor cores and wait for it
+struct GroupCtx {
+  int g, wig;
+  uint32_t tmem_d;          // accumulator base column of the group
+  uint32_t taddr;           // + lane-quarter offset of this warp
+  uint32_t a_hi, a_lo, aux_hi, aux_lo, zero;
+  uint64_t* bar;
+  uint32_t phase;
+};
+
+// call with the A tile (and aux chunk) written by this group's threads; `issue(elected)` enqueues the MMAs
+template <typename Issue>
+__device__ __forceinline__ void run_gemm(GroupCtx& c, Issue issue) {
+  tc::fence_async_smem();          // st.shared of the A tile -> visible to the tensor core
+  tc::fence_before_sync();         // this thread's tcgen05.ld of the previous accumulator are complete
+  group_barrier(c.g);
+  if (c.wig == 0) {
+    tc::fence_after_sync();
+    const uint32_t elected = tc::elect_one();
+    issue(elected);
+    if (elected) tc::mma_commit(c.bar);
+    __syncwarp();
+  }
+  tc::mbar_wait(c.bar, c.phase);
+  c.phase ^= 1;
+  tc::fence_after_sync();
+}
+
+}  // namespace pile

@@ -17,7 +17,7 @@ KMAX = 10
 WSLOTS = ["W_PE0T", "B_PE0", "W_PE1T", "B_PE1", "W_RE0T", "B_RE0", "W_RE1T", "B_RE1", "W_RE2T", "B_RE2",
           "W_ET", "W_RT", "W_ST", "WD_RP", "B_RP", "W_PT", "W_AT", "WD_PP", "B_PP", "W_V0T", "B_V0", "W_V1T", "B_V1",
           "W_PE0", "W_PE1", "W_RE0", "W_RE1", "W_RE2", "W_E", "W_R", "W_S", "W_P", "W_A", "W_V0", "W_V1",
-          "TC_RE1", "TC_RE2", "TC_E"]
+          "TC_EDGE", "TC_NODE"]
 
 CKPT_KEYS = [  # reference checkpoint layout, SURVEY.md §8b
     "model.particle_encoder.model.0", "model.particle_encoder.model.2",
@@ -64,8 +64,8 @@ def _pad_cols(m, cols):
 
 
 def tc_operand(w):
-    """[out=64][in=64] fp32 weight -> bf16 (hi | lo) in the canonical K-major UMMA layout (csrc/tc.cuh):
-    element (n, k) at bf16 index (k//8)*512 + (n//8)*64 + (n%8)*8 + (k%8); returned as float32 words."""
+    """[n_out][n_in] fp32 matrix -> bf16 (hi | lo) images in the canonical K-major UMMA layout (csrc/tc.cuh):
+    element (n, k) at bf16 index (k//8)*(8*n_out) + (n//8)*64 + (n%8)*8 + (k%8); returned as float32 words."""
     n_out, n_in = w.shape
     hi = w.to(torch.bfloat16)
     lo = (w - hi.float()).to(torch.bfloat16)
@@ -73,6 +73,15 @@ def tc_operand(w):
     def canon(x):
         return x.view(n_out // 8, 8, n_in // 8, 8).permute(2, 0, 1, 3).contiguous().reshape(-1)
     return torch.cat([canon(hi), canon(lo)]).view(torch.float32)
+
+
+def tc_augmented(w, k_total, extra_cols):
+    """[n_out][k] weight -> [n_out][k_total] with `extra_cols` (bias, density column, ...) appended at k, zeros after."""
+    out = w.new_zeros(w.shape[0], k_total)
+    out[:, :w.shape[1]] = w
+    for i, c in enumerate(extra_cols):
+        out[:, w.shape[1] + i] = c
+    return out
 
 
 def pack_weights(state, device):
@@ -98,7 +107,20 @@ def pack_weights(state, device):
         "W_PE0": _pad_cols(pe0, 8), "W_PE1": pe1, "W_RE0": _pad_cols(re0, 8), "W_RE1": re1, "W_RE2": re2,
         "W_E": rp[:, 0:H], "W_R": rp[:, H:2 * H], "W_S": rp[:, 2 * H:3 * H], "W_P": pp[:, 0:H], "W_A": pp[:, H:2 * H],
         "W_V0": v0, "W_V1": _pad_rows(v1, 4),
-        "TC_RE1": tc_operand(re1), "TC_RE2": tc_operand(re2), "TC_E": tc_operand(rp[:, 0:H].contiguous()),
+        # relation encoder on tcgen05: biases (and the density column of the last layer) ride in K chunk 8,
+        # which the kernel multiplies with the constant activation chunk (1, d, 0, ...)
+        "TC_EDGE": torch.cat([tc_operand(tc_augmented(re0, 16, [bre0])),
+                              tc_operand(tc_augmented(re1, 80, [bre1])),
+                              tc_operand(tc_augmented(re2, 80, [bre2])),
+                              tc_operand(tc_augmented(rp[:, 0:H], 80, [brp, rp[:, 3 * H]]))]),
+        # particle kernels on tcgen05 (layout: csrc/node_tc.cu)
+        "TC_NODE": torch.cat([tc_operand(tc_augmented(pe0, 16, [bpe0])),
+                              tc_operand(tc_augmented(pe1, 80, [bpe1])),
+                              tc_operand(tc_augmented(pp[:, 0:H], 80, [bpp, pp[:, 2 * H]])),
+                              tc_operand(torch.cat([rp[:, H:2 * H], rp[:, 2 * H:3 * H]], dim=0).contiguous()),
+                              tc_operand(pp[:, H:2 * H].contiguous()),
+                              tc_operand(tc_augmented(v0, 80, [bv0])),
+                              tc_operand(tc_augmented(_pad_rows(v1, 16), 80, [torch.cat([bv1, bv1.new_zeros(13)])]))]),
     }
     if lib.pile_wpack_num_slots() != len(WSLOTS):
         raise _lib.PileLibraryError("weight-slot table out of sync with libpilegnn")

@@ -39,7 +39,7 @@ def test_tc_step_matches_fp32_step(model, N, B):
     disp = (ref - args[1]).abs().max().item()
     err = (out - ref).abs().max().item()
     assert err <= 2e-4 * max(disp, 1e-3), (err, disp)          # error relative to the predicted displacement
-    assert float((out - ref).norm() / ref.norm()) < 2e-6        # relative to the positions (bar: 1e-4)
+    assert float((out - ref).norm() / ref.norm()) < 2e-5        # relative to the positions (bar: 1e-4)
 
 
 def test_tc_gradients_match_fp32_gradients(model):
