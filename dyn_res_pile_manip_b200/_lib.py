@@ -25,7 +25,7 @@ SIGNATURES = {
     "pile_error_string": (C.c_char_p, [_I]),
     "pile_set_tensor_cores": (_I, [_I]),
     "pile_get_tensor_cores": (_I, []),
-    "pile_debug_set_trace": (_I, [_P, _I]),
+    "pile_debug_set_trace": (_I, [_P, _I, _I]),
     "pile_wpack_num_slots": (_I, []),
     "pile_wpack_slot_offset": (_LL, [_I]),
     "pile_wpack_slot_size": (_LL, [_I]),

@@ -31,17 +31,21 @@ struct ScratchView {
 ScratchView carve_scratch(void* p, int B, int N) {
   Carver c(p);
   const size_t R = (size_t)B * N, E = (size_t)B * KMAX * N;
+  // the tensor-core path stores features tile-blocked (tc_tile.cuh): round rows up to whole 128-row tiles,
+  // relation tiles are per sample
+  const size_t Rp = (R + TILE - 1) / TILE * TILE;
+  const size_t Ep = (size_t)B * ((KMAX * N + TILE - 1) / TILE) * TILE;
   ScratchView v;
   v.ws.s_delta = c.take<float>(R * 3);
-  v.ws.Ce = c.take<float>(E * H);
+  v.ws.Ce = c.take<float>(Ep * H);
   v.ws.efeat = c.take<float>((E + TILE) * 8);
-  v.ws.agg = c.take<float>(R * H);
-  v.ws.Cp = c.take<float>(R * H);
-  v.ws.eff = c.take<float>(R * H);
-  v.ws.Pr[0] = c.take<float>(R * H);
-  v.ws.Pr[1] = c.take<float>(R * H);
-  v.ws.Ps[0] = c.take<float>(R * H);
-  v.ws.Ps[1] = c.take<float>(R * H);
+  v.ws.agg = c.take<float>(Rp * H);
+  v.ws.Cp = c.take<float>(Rp * H);
+  v.ws.eff = c.take<float>(Rp * H);
+  v.ws.Pr[0] = c.take<float>(Rp * H);
+  v.ws.Pr[1] = c.take<float>(Rp * H);
+  v.ws.Ps[0] = c.take<float>(Rp * H);
+  v.ws.Ps[1] = c.take<float>(Rp * H);
   v.csr.rowptr = c.take<int>((size_t)B * (N + 1));
   v.csr.col = c.take<int>(E);
   v.csr.row = c.take<int>(E);
@@ -107,7 +111,9 @@ int pile_set_tensor_cores(int enable) {
 }
 int pile_get_tensor_cores(void) { return g_use_tensor_cores; }
 
-int pile_debug_set_trace(long long* device_buf, int capacity) { return set_edge_trace(device_buf, capacity); }
+int pile_debug_set_trace(long long* device_buf, int capacity, int which) {
+  return which == 0 ? set_edge_trace(device_buf, capacity) : set_node_trace(device_buf, capacity);
+}
 
 int pile_wpack_num_slots(void) { return W_NUM; }
 long long pile_wpack_slot_offset(int slot) { return (slot < 0 || slot > W_NUM) ? -1 : wslot_offset(slot); }

@@ -122,14 +122,6 @@ __global__ void k_edge_features(const float* __restrict__ attr, const float* __r
   st4(efeat + slot * 8 + 4, make_float4(pr[2] - ps[2], dens[b] / 5000.f, 0.f, 0.f));
 }
 
-// optional cycle trace of one group (measurement hook, see pile_debug_set_trace): clock64 stamps
-__device__ long long* g_trace = nullptr;
-__device__ int g_trace_cap = 0;
-#define PILE_TRACE(slot_)                                                          \
-  do {                                                                             \
-    if (trace && tr_n < tr_cap) { trace[tr_n++] = ((long long)(slot_) << 56) | (clock64() & 0x00ffffffffffffffLL); } \
-  } while (0)
-
 template <bool RECORD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_edge_encode_tc(const float* __restrict__ wpack, const float* __restrict__ efeat, const int* __restrict__ rowptr,
@@ -185,9 +177,7 @@ k_edge_encode_tc(const float* __restrict__ wpack, const float* __restrict__ efea
     return p;
   };
 
-  long long* trace = (blockIdx.x == 0 && threadIdx.x == 32 * 9) ? g_trace : nullptr;   // group 1, warp 1, lane 0
-  const int tr_cap = g_trace_cap;
-  int tr_n = 0;
+  PILE_TRACE_DECL();
   long long tile = (long long)blockIdx.x * TC_GROUPS + g;
   Pre cur = fetch(tile);
   tc::mbar_wait(&S.w_bar, 0);
@@ -243,12 +233,12 @@ k_edge_encode_tc(const float* __restrict__ wpack, const float* __restrict__ efea
 #pragma unroll
           for (int q = 0; q < 2; ++q) tc::tmem_ld16(taddr + half * 32 + q * 16, v[q]);
           tc::tmem_ld_wait();
-          if (valid) {
+          if (valid) {      // C_e stays row-major: k_edge_agg streams it from HBM in whole 256-byte rows
             float* out = Ce + (slot0 + r) * H + half * 32;
 #pragma unroll
             for (int q = 0; q < 2; ++q)
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) st4(out + q * 16 + j, make_float4(v[q][j], v[q][j + 1], v[q][j + 2], v[q][j + 3]));
+              for (int h = 0; h < 2; ++h) st8(out + q * 16 + h * 8, &v[q][h * 8]);
           }
         }
       }
@@ -262,11 +252,7 @@ k_edge_encode_tc(const float* __restrict__ wpack, const float* __restrict__ efea
   if (threadIdx.x < 32) tc::tmem_dealloc(S.tmem_base, TMEM_COLS);
 }
 
-int set_edge_trace(long long* buf, int cap) {
-  cudaError_t e = cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf));
-  if (e != cudaSuccess) return (int)e;
-  return (int)cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap));
-}
+PILE_TRACE_SETTER(set_edge_trace)
 
 int launch_edge_encode_tc(const float* wpack, const float* attr, const float* dens, const float* s_cur,
                           long long s_stride, const Csr& csr, const Masks* mk, float* efeat, float* Ce, int B, int N,

@@ -63,6 +63,7 @@ int launch_edge_encode_tc(const float* wpack, const float* attr, const float* de
                           cudaStream_t st);
 
 int set_edge_trace(long long* buf, int cap);
+int set_node_trace(long long* buf, int cap);
 int launch_node_encode_tc(const float* wpack, const float* attr, const float* dens, const float* s_delta,
                           const Masks* mk, const StepScratch& ws, int B, int N, cudaStream_t st);
 // propagation step p on the tensor-core path: k_edge_agg + k_node_update_tc (p == PSTEP-1: + predictor)

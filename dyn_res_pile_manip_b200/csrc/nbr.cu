@@ -94,7 +94,7 @@ __device__ __forceinline__ void sort10(int (&id)[KMAX]) {
   PILE_CE(3, 4) PILE_CE(5, 6)
 }
 
-constexpr int NBR_THREADS = 256;
+constexpr int NBR_THREADS = 1024;   // upper bound; the search kernel runs round_up(N, 32) threads so one pass covers all receivers
 
 // exclusive scan of one int per thread over the CTA; returns the exclusive prefix, total via *total
 __device__ __forceinline__ int block_exscan(int v, int* warp_sums, int* total) {
@@ -108,14 +108,15 @@ __device__ __forceinline__ int block_exscan(int v, int* warp_sums, int* total) {
   if (lane == 31) warp_sums[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    int w = lane < (NBR_THREADS / 32) ? warp_sums[lane] : 0;
+    const int nwarps = (int)(blockDim.x >> 5);
+    int w = lane < nwarps ? warp_sums[lane] : 0;
     int winc = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, winc, o);
       if (lane >= o) winc += t;
     }
-    if (lane < NBR_THREADS / 32) warp_sums[lane] = winc - w;
+    if (lane < nwarps) warp_sums[lane] = winc - w;
     if (lane == 31) *total = winc;
   }
   __syncthreads();
@@ -206,7 +207,7 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
   __syncthreads();
 
   // CSR offsets
-  const int per = (N + NBR_THREADS - 1) / NBR_THREADS;
+  const int per = (N + (int)blockDim.x - 1) / (int)blockDim.x;
   {
     const int lo = min(threadIdx.x * per, N), hi = min(lo + per, N);
     int s = 0;
@@ -275,11 +276,12 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
 // backward of the pusher model: g_s_delta [B,N,3] -> g_s_cur (+=) and g_action [B,4].
 // The hard along-push mask and the push length inside it carry no gradient (planners.py:248).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NBR_THREADS)
+constexpr int SDB_THREADS = 256;
+__global__ void __launch_bounds__(SDB_THREADS)
 k_gen_s_delta_bwd(const float* __restrict__ s_cur, long long s_stride, const float* __restrict__ action,
                   int act_stride, PushCam cam, int N, const float* __restrict__ g_sd, float* __restrict__ g_s_cur,
                   long long g_stride, float* __restrict__ g_action, int g_act_stride) {
-  __shared__ float red[9][NBR_THREADS / 32];
+  __shared__ float red[9][SDB_THREADS / 32];
   const int b = blockIdx.x;
   const PushFrame f = make_push_frame(cam, action + (size_t)b * act_stride);
   float gu[3] = {0.f, 0.f, 0.f}, ge[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f};
@@ -331,7 +333,7 @@ k_gen_s_delta_bwd(const float* __restrict__ s_cur, long long s_stride, const flo
     float t[9];
     for (int k = 0; k < 9; ++k) {
       t[k] = 0.f;
-      for (int w = 0; w < NBR_THREADS / 32; ++w) t[k] += red[k][w];
+      for (int w = 0; w < SDB_THREADS / 32; ++w) t[k] += red[k][w];
     }
     // u = p / |p|
     const float udg = f.ux * t[0] + f.uy * t[1] + f.uz * t[2];
@@ -351,7 +353,7 @@ k_gen_s_delta_bwd(const float* __restrict__ s_cur, long long s_stride, const flo
 int launch_gen_s_delta_bwd(const float* s_cur, long long s_stride, const float* action, int act_stride,
                            const PushCam& cam, int B, int N, const float* g_sd, float* g_s_cur, long long g_stride,
                            float* g_action, int g_act_stride, cudaStream_t st) {
-  k_gen_s_delta_bwd<<<B, NBR_THREADS, 0, st>>>(s_cur, s_stride, action, act_stride, cam, N, g_sd, g_s_cur, g_stride,
+  k_gen_s_delta_bwd<<<B, SDB_THREADS, 0, st>>>(s_cur, s_stride, action, act_stride, cam, N, g_sd, g_s_cur, g_stride,
                                                g_action, g_act_stride);
   PILE_CHECK_LAUNCH();
   return 0;
@@ -430,7 +432,9 @@ int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_del
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  k_nbr_search<<<B, NBR_THREADS, smem, st>>>(s_cur, s_stride, s_delta_in, action, act_stride, cam, s_delta_out,
+  int threads = (N + 31) / 32 * 32;
+  threads = threads < 64 ? 64 : (threads > NBR_THREADS ? NBR_THREADS : threads);
+  k_nbr_search<<<B, threads, smem, st>>>(s_cur, s_stride, s_delta_in, action, act_stride, cam, s_delta_out,
                                              particle_nums, N, thr, csr.rowptr, csr.col, csr.row, csr.trowptr,
                                              csr.trecv, csr.tedge);
   PILE_CHECK_LAUNCH();

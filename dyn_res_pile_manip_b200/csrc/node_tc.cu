@@ -77,9 +77,10 @@ __device__ __forceinline__ void tile_epilogue(Smem& S) {
   if (threadIdx.x < 32) tc::tmem_dealloc(S.tmem_base, TC_GROUPS * NODE_TMEM_PER_GROUP);
 }
 
-__device__ __forceinline__ void st16(float* __restrict__ p, const float (&v)[16]) {
-#pragma unroll
-  for (int j = 0; j < 16; j += 4) st4(p + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+// 16 consecutive channels (chunks kc, kc+1) of tile row r -> tile-blocked array
+__device__ __forceinline__ void st16_tb(float* __restrict__ base, long long tile, int r, int kc, const float (&v)[16]) {
+  st8(base + tb_off(tile, r, kc), &v[0]);
+  st8(base + tb_off(tile, r, kc + 1), &v[8]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -138,7 +139,7 @@ k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr
       tc::tmem_ld_wait();
       const uint32_t m = relu_to_tile<RECORD>(a_hi, a_lo, row_off + (half * 4 + q * 2) * A_LBO, v);
       if (valid) {
-        st16(eff + row * H + half * 32 + q * 16, v);
+        st16_tb(eff, tile, r, half * 4 + q * 2, v);
         if (RECORD) *reinterpret_cast<uint16_t*>(m_pe1 + row * 8 + half * 4 + q * 2) = (uint16_t)m;
       }
     }
@@ -151,20 +152,20 @@ k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr
       float v[16];
       tc::tmem_ld16(c.taddr + half * 32 + q * 16, v);
       tc::tmem_ld_wait();
-      if (valid) st16(Cp + row * H + half * 32 + q * 16, v);
+      if (valid) st16_tb(Cp, tile, r, half * 4 + q * 2, v);
     }
     // (P_r, P_s) = (W_r, W_s) p_enc : one N = 128 product, column half 0 -> P_r, half 1 -> P_s
     run_gemm(c, [&](uint32_t el) {
       issue_gemm<128, 4, false>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w + OFF_WRS, w + OFF_WRS + NB_WRS / 2);
     });
     {
-      float* dst = (half == 0 ? Pr : Ps) + row * H;
+      float* dst = half == 0 ? Pr : Ps;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float v[16];
         tc::tmem_ld16(c.taddr + half * 64 + q * 16, v);
         tc::tmem_ld_wait();
-        if (valid) st16(dst + q * 16, v);
+        if (valid) st16_tb(dst, tile, r, q * 2, v);
       }
     }
   }
@@ -183,12 +184,13 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
   const unsigned hmask = 0xffffu << (threadIdx.x & 16);
   const long long R = (long long)B * N;
   const long long nhw = (long long)gridDim.x * (blockDim.x >> 4);
+  const int kc = l16 >> 1, sub = (l16 & 1) * 4;          // this lane's 4 channels inside chunk kc
   for (long long node = (long long)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); node < R; node += nhw) {
     const int b = (int)(node / N), i = (int)(node % N);
     const int* rp = rowptr + (long long)b * (N + 1) + i;
     const int e_lo = rp[0], cnt = rp[1] - e_lo;
     const long long slot = (long long)b * KMAX * N + e_lo;
-    const float4 pr = ld4(Pr + node * H + 4 * l16);
+    const float4 pr = ld4(Pr + tb_row(node, kc) + sub);
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k0 = 0; k0 < cnt; k0 += 5) {
       float4 ce[5], ps[5];
@@ -197,7 +199,7 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
         if (k0 + k < cnt) {
           const int s = col[slot + k0 + k];
           ce[k] = ld4(Ce + (slot + k0 + k) * H + 4 * l16);
-          ps[k] = ld4(Ps + ((long long)b * N + s) * H + 4 * l16);
+          ps[k] = ld4(Ps + tb_row((long long)b * N + s, kc) + sub);
         }
       }
 #pragma unroll
@@ -214,7 +216,7 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
         }
       }
     }
-    st4(agg + node * H + 4 * l16, sum);
+    st4(agg + tb_row(node, kc) + sub, sum);
   }
 }
 
@@ -242,6 +244,7 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
   const uint32_t w_v0 = w + NB_WA, w_v1 = w + NB_WA + NB_K80;   // last only
   const long long R = (long long)B * N;
   const long long ntiles = (R + TILE - 1) / TILE;
+  PILE_TRACE_DECL();
   if (LAST && half == 1) {       // constant aux chunk (1, 0, ...) for the predictor biases
     const float f[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     store_chunk(S.t[g].aux[0], S.t[g].aux[1], row_off, f);
@@ -251,57 +254,61 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
   for (long long tile = (long long)blockIdx.x * TC_GROUPS + g; tile < ntiles; tile += (long long)gridDim.x * TC_GROUPS) {
     const long long row = tile * TILE + r;
     const bool valid = row < R;
-    // A = split(agg row)
+    PILE_TRACE(1);
+    // A = split(agg row): four 32-byte loads in flight, then the hi/lo split
+    {
+      float o[4][8];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      float4 x[4];
+      for (int j = 0; j < 4; ++j) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        x[j] = valid ? ld4(agg + row * H + half * 32 + q * 16 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float o[8] = {x[2 * h].x, x[2 * h].y, x[2 * h].z, x[2 * h].w, x[2 * h + 1].x, x[2 * h + 1].y, x[2 * h + 1].z,
-                            x[2 * h + 1].w};
-        store_chunk(a_hi, a_lo, row_off + (half * 4 + q * 2 + h) * A_LBO, o);
+        for (int i = 0; i < 8; ++i) o[j][i] = 0.f;
+        if (valid) ld8(agg + tb_off(tile, r, half * 4 + j), o[j]);
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) store_chunk(a_hi, a_lo, row_off + (half * 4 + j) * A_LBO, o[j]);
     }
+    PILE_TRACE(2);
     run_gemm(c, [&](uint32_t el) {
       issue_gemm<64, 4, false>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w_a, w_a + NB_WA / 2);
     });
+    PILE_TRACE(5);
     // eff <- ReLU(W_a agg + C_p + eff)
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      float4 a[4], e[4];
+      float a[16], e[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        a[j] = valid ? ld4(Cp + row * H + half * 32 + q * 16 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        e[j] = valid ? ld4(eff + row * H + half * 32 + q * 16 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 16; ++j) { a[j] = 0.f; e[j] = 0.f; }
+      if (valid) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          ld8(Cp + tb_off(tile, r, half * 4 + q * 2 + h), a + h * 8);
+          ld8(eff + tb_off(tile, r, half * 4 + q * 2 + h), e + h * 8);
+        }
       }
       float v[16];
       tc::tmem_ld16(c.taddr + half * 32 + q * 16, v);
       tc::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[j * 4 + 0] += a[j].x + e[j].x; v[j * 4 + 1] += a[j].y + e[j].y;
-        v[j * 4 + 2] += a[j].z + e[j].z; v[j * 4 + 3] += a[j].w + e[j].w;
-      }
+      for (int j = 0; j < 16; ++j) v[j] += a[j] + e[j];
       const uint32_t m = relu_to_tile<RECORD>(a_hi, a_lo, row_off + (half * 4 + q * 2) * A_LBO, v);
       if (valid) {
-        if (!LAST) st16(eff + row * H + half * 32 + q * 16, v);
+        if (!LAST) st16_tb(eff, tile, r, half * 4 + q * 2, v);
         if (RECORD) *reinterpret_cast<uint16_t*>(m_eff + row * 8 + half * 4 + q * 2) = (uint16_t)m;
       }
     }
     if (!LAST) {
+      PILE_TRACE(2);
       run_gemm(c, [&](uint32_t el) {
         issue_gemm<128, 4, false>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w_rs, w_rs + NB_WRS / 2);
       });
-      float* dst = (half == 0 ? PrOut : PsOut) + row * H;
+      PILE_TRACE(5);
+      float* dst = half == 0 ? PrOut : PsOut;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float v[16];
         tc::tmem_ld16(c.taddr + half * 64 + q * 16, v);
         tc::tmem_ld_wait();
-        if (valid) st16(dst + q * 16, v);
+        if (valid) st16_tb(dst, tile, r, q * 2, v);
       }
     } else {
       // predictor: q = ReLU(V0 eff + c0);  s_pred = s_cur + V1 q + c1
@@ -333,9 +340,12 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
         }
       }
     }
+    PILE_TRACE(6);
   }
   tile_epilogue(S);
 }
+
+PILE_TRACE_SETTER(set_node_trace)
 
 template <typename Kern>
 static int set_smem_tc(Kern k, size_t bytes) {

@@ -13,6 +13,25 @@
 
 namespace pile {
 
+// optional cycle trace of one warp (measurement hook, pile_debug_set_trace): every translation unit that
+// includes this header gets its own copy and exposes a setter
+static __device__ long long* g_trace = nullptr;
+static __device__ int g_trace_cap = 0;
+#define PILE_TRACE_DECL()                                                                                  \
+  long long* trace = (blockIdx.x == 0 && threadIdx.x == 32 * 9) ? g_trace : nullptr; /* group 1, warp 1 */ \
+  const int tr_cap = g_trace_cap;                                                                          \
+  int tr_n = 0;
+#define PILE_TRACE(tag_)                                                                                     \
+  do {                                                                                                       \
+    if (trace && tr_n < tr_cap) trace[tr_n++] = ((long long)(tag_) << 56) | (clock64() & 0x00ffffffffffffffLL); \
+  } while (0)
+#define PILE_TRACE_SETTER(name_)                                              \
+  int name_(long long* buf, int cap) {                                        \
+    cudaError_t e = cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf));           \
+    if (e != cudaSuccess) return (int)e;                                      \
+    return (int)cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap));           \
+  }
+
 constexpr int TC_GROUPS = 4;
 constexpr int GROUP_THREADS = 256;
 constexpr int TC_THREADS = TC_GROUPS * GROUP_THREADS;
@@ -22,6 +41,26 @@ constexpr uint32_t B_SBO = 128;
 __host__ __device__ constexpr uint32_t b_lbo(int n_rows) { return (uint32_t)(n_rows / 8) * 128; }
 // bytes of one part (hi or lo) of a canonical [n_rows x k] bf16 weight image
 __host__ __device__ constexpr uint32_t b_bytes(int n_rows, int k) { return (uint32_t)(k / 8) * b_lbo(n_rows); }
+
+// Feature arrays stay row-major ([rows][64] fp32).  The tile kernels own one row per thread, so they move
+// 8 consecutive channels (one 32-byte sector) per instruction with sm_100's 256-bit global accesses; a
+// row-per-half-warp consumer (k_edge_agg) then streams whole 256-byte rows.  (A tile-blocked chunk-major
+// layout was measured: it coalesces the tile kernels better but turns k_edge_agg's 256-byte row reads into
+// eight scattered sectors and costs more than it saves.)
+__host__ __device__ __forceinline__ long long tb_off(long long tile, int r, int kc) {
+  return (tile * TILE + r) * (long long)H + kc * 8;
+}
+__device__ __forceinline__ long long tb_row(long long row, int kc) { return row * (long long)H + kc * 8; }
+__device__ __forceinline__ void st8(float* __restrict__ p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld8(const float* __restrict__ p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
 
 struct GroupTile {          // per-group shared-memory operands
   alignas(128) uint8_t a[2][A_BYTES];     // [hi, lo] activation tile, 8 K chunks

@@ -35,7 +35,7 @@ int pile_get_tensor_cores(void);
 
 /* measurement hook: when device_buf != NULL, one warp of the tcgen05 relation-encoder kernel records
  * (tag << 56 | clock64) stamps of its per-layer phases into device_buf[0..capacity). NULL disables. */
-int pile_debug_set_trace(long long* device_buf, int capacity);
+int pile_debug_set_trace(long long* device_buf, int capacity, int which /*0 relation encoder, 1 particle kernels*/);
 
 /* ---- packed weights ---------------------------------------------------------------------------
  * The host packs the 18 checkpoint tensors into one float buffer; slots are listed in

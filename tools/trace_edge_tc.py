@@ -16,9 +16,10 @@ eng.actions.copy_(torch.from_numpy(synthetic.random_actions(1024, 1, seed=1)))
 eng.evaluate(); torch.cuda.synchronize()
 buf = torch.zeros(4096, dtype=torch.int64, device="cuda")
 lib = _lib.load()
-_lib.check(lib.pile_debug_set_trace(_lib.ptr(buf), 4096), "trace")
+which = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+_lib.check(lib.pile_debug_set_trace(_lib.ptr(buf), 4096, which), "trace")
 eng.evaluate(); torch.cuda.synchronize()
-_lib.check(lib.pile_debug_set_trace(None, 0), "trace")
+_lib.check(lib.pile_debug_set_trace(None, 0, which), "trace")
 v = buf.cpu().numpy()
 v = v[v != 0]
 tags = (v >> 56) & 0xff
