@@ -287,7 +287,8 @@ def main():
             ach = flops[dom] / (kms[dom] * 1e-3) / 1e12
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": bf16_tf, "unit": "TFLOP/s",
                     "frac": ach / bf16_tf, "traffic": None, "peak_source": peak_kind + " bf16 cuBLAS burst",
-                    "note": "FP32 CUDA-core tile GEMM today (fp32 parity anchor); fraction is against the tensor-pipe peak"}
+                    "note": ("tcgen05 bf16 hi/lo split, 3 tensor passes per algorithmic MAC (tensor-pipe MACs = 3x achieved)"
+                             if lib.pile_get_tensor_cores() else "FP32 CUDA-core tile GEMM engine (parity anchor)")}
         else:
             by = hbm_bytes.get(dom, hbm_bytes["propagate0"])
             ach = by / (kms[dom] * 1e-3) / 1e9
@@ -301,6 +302,26 @@ def main():
         roof["E_relations"] = E
         f_ref, f_alg = O.flops_per_sample_step(N, E / samples, H)
         roof["alg_tflops_whole_step"] = f_alg * samples / (step_ms * 1e-3) / 1e12
+
+        # MPC plan latency (BASELINE.json metric, second half): one MPPI planner evaluation of BASELINE config 2
+        # (256 samples x 100 particles x T=10) through the host-buffer call, >= 50 timed calls after 5 warm-ups
+        plan = None
+        if world == 1:
+            s2, n2, t2 = WORKLOADS["cfg2"]
+            eng2 = RolloutEngine(model, planner, s2, n2, t2, device=dev, goal=goal, use_graph=not args.no_graph)
+            st2, dn2 = synthetic.make_pile_batch(1, n2, seed=0)
+            eng2.load_state(st2, dn2)
+            acts2 = [torch.from_numpy(synthetic.random_actions(s2, t2, seed=50 + i)).pin_memory() for i in range(8)]
+            r2 = torch.empty(s2, dtype=torch.float32).pin_memory()
+            rec2 = torch.empty(2 + 4 * t2, dtype=torch.float32).pin_memory()
+            lat = []
+            for i in range(55):
+                t_a = time.perf_counter()
+                eng2.evaluate_host(acts2[i % 8], r2, rec2)
+                lat.append((time.perf_counter() - t_a) * 1e3)
+            lat = sorted(lat[5:])
+            plan = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "calls": len(lat),
+                    "workload": "cfg2: 256 samples x 100 particles x T=10, host actions in -> host reward + MPPI record out"}
 
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -324,6 +345,8 @@ def main():
                         "d2h_bytes_per_step": samples * 4 + (2 + 4 * T) * 4},
                 "gpu_launches": (eng.launches_per_eval() + (1 if world > 1 else 0)) * K,
                 "clocks": clocks, "roofline": roof}
+        if plan:
+            line["mpc_plan_latency"] = plan
         if cpu:
             line["cpu_baseline"] = cpu
         del launches

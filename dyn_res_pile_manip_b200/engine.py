@@ -15,7 +15,9 @@ from .rewards import shape_goal_image
 class RolloutEngine:
     """rows = n_sample * n_batch rollouts of horizon T over N particles on one GPU."""
 
-    LAUNCHES_PER_MODEL_STEP = 6     # nbr_search, node_encode, edge_encode, 3 x propagate
+    # kernels per model step: FP32 engine nbr_search, node_encode, edge_encode, 3 x propagate; tensor engine
+    # nbr_search, node_encode_tc, edge_features, edge_encode_tc, 3 x (edge_agg + node_update_tc)
+    LAUNCHES_PER_MODEL_STEP = {0: 6, 1: 10}
 
     def __init__(self, model_dy, planner, rows, N, T, device=None, goal=None, goal_coor=None, use_graph=True,
                  reward_weight=None):
@@ -64,7 +66,7 @@ class RolloutEngine:
 
     # ---- one evaluation --------------------------------------------------------------------------
     def launches_per_eval(self):
-        n = self.T * self.LAUNCHES_PER_MODEL_STEP
+        n = self.T * self.LAUNCHES_PER_MODEL_STEP[_lib.load().pile_get_tensor_cores()]
         if self.goal_img is not None:
             n += 3      # reward, mppi partials, mppi combine
         return n
