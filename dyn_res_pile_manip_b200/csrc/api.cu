@@ -106,12 +106,13 @@ const char* pile_error_string(int code) { return cudaGetErrorString((cudaError_t
 
 int pile_set_tensor_cores(int enable) {
   const int old = g_use_tensor_cores;
-  g_use_tensor_cores = enable ? 1 : 0;
+  g_use_tensor_cores = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
   return old;
 }
 int pile_get_tensor_cores(void) { return g_use_tensor_cores; }
 
 int pile_debug_set_trace(long long* device_buf, int capacity, int which) {
+  if (which == 2) return set_edge_tmem_trace(device_buf, capacity);
   return which == 0 ? set_edge_trace(device_buf, capacity) : set_node_trace(device_buf, capacity);
 }
 

@@ -20,6 +20,7 @@ constexpr int LDA = H + 4;     // shared-memory activation row stride (conflict-
 constexpr int LDX = 12;        // shared-memory stride of the 8-wide input feature tile
 constexpr int NT = 256;        // threads per GEMM CTA: 8 warps x (4 rows/lane x 8 cols/warp)
 constexpr int NSM = 148;
+constexpr int TC_EDGE2_FLOATS = 13312;  // 52 KB, layout in edge_tmem.cu
 constexpr int TC_NODE_FLOATS = 29952;   // 117 KB of bf16 hi/lo weight images, layout in node_tc.cu
 
 // ---- packed weight buffer (floats). Forward blocks are transposed [K][H]; backward blocks keep the
@@ -48,6 +49,8 @@ enum WSlot {
   TC_EDGE,
   // tensor-core operands of the particle kernels (node_tc.cu): PE0aug, PE1aug, WPaug, [W_r;W_s], W_a, V0aug, V1aug
   TC_NODE,
+  // relation-encoder operands of the A-in-TMEM variant (edge_tmem.cu): W0 [64 x 16], RE1, RE2, W_e [64 x 64]
+  TC_EDGE2,
   W_NUM
 };
 
@@ -60,6 +63,7 @@ __host__ __device__ inline int wslot_size(int s) {
     case B_V1: return 4;
     case TC_EDGE: return 4 * H * H;
     case TC_NODE: return TC_NODE_FLOATS;
+    case TC_EDGE2: return TC_EDGE2_FLOATS;
     default: return H * H;
   }
 }

@@ -159,17 +159,17 @@ k_edge_encode_tc(const float* __restrict__ wpack, const float* __restrict__ efea
   const uint32_t row_off = (r >> 3) * A_SBO + (r & 7) * 16;
 
   const int tps = (KMAX * N + TILE - 1) / TILE;
-  const long long ntiles = (long long)B * tps;
-  const long long stride = (long long)gridDim.x * TC_GROUPS;
+  const int ntiles = B * tps;                  // 32-bit tile arithmetic: 64-bit div/mod is emulated (~100 instr)
+  const int stride = (int)gridDim.x * TC_GROUPS;
 
   // per-tile inputs, fetched one tile ahead: relation count of the sample and this row's 8 features
   struct Pre { int ne; float4 f0, f1; };
-  auto fetch = [&](long long tile) {
+  auto fetch = [&](int tile) {
     Pre p;
     p.ne = 0; p.f0 = make_float4(0.f, 0.f, 0.f, 0.f); p.f1 = p.f0;
     if (tile < ntiles) {
-      const int b = (int)(tile / tps);
-      const long long slot = (long long)b * KMAX * N + (long long)(tile % tps) * TILE + r;
+      const int b = tile / tps;
+      const long long slot = (long long)b * KMAX * N + (tile - b * tps) * TILE + r;
       p.ne = tc::ldg_nc_s32(rowptr + (long long)b * (N + 1) + N);
       if (half == 0) p.f0 = tc::ldg_nc_f4(efeat + slot * 8);   // rows past the sample's last relation read
       p.f1 = tc::ldg_nc_f4(efeat + slot * 8 + 4);              // scratch: harmless, those rows are never stored
@@ -178,14 +178,14 @@ k_edge_encode_tc(const float* __restrict__ wpack, const float* __restrict__ efea
   };
 
   PILE_TRACE_DECL();
-  long long tile = (long long)blockIdx.x * TC_GROUPS + g;
+  int tile = (int)blockIdx.x * TC_GROUPS + g;
   Pre cur = fetch(tile);
   tc::mbar_wait(&S.w_bar, 0);
   uint32_t phase = 0;
 
   while (tile < ntiles) {
-    const int b = (int)(tile / tps);
-    const int e0 = (int)(tile % tps) * TILE;
+    const int b = tile / tps;
+    const int e0 = (tile - b * tps) * TILE;
     const int nrows = min(TILE, cur.ne - e0);
     const long long slot0 = (long long)b * KMAX * N + e0;
     const Pre nxt = fetch(tile + stride);
@@ -270,6 +270,7 @@ int launch_edge_encode_tc(const float* wpack, const float* attr, const float* de
   const dim3 fgrid((KMAX * N + 255) / 256, B);
   k_edge_features<<<fgrid, 256, 0, st>>>(attr, dens, s_cur, s_stride, csr.rowptr, csr.col, csr.row, efeat, B, N);
   PILE_CHECK_LAUNCH();
+  if (g_use_tensor_cores == 2) return launch_edge_encode_tmem(wpack, efeat, csr, mk, Ce, B, N, st);
   const long long ntiles = (long long)B * ((KMAX * N + TILE - 1) / TILE);
   const long long want = (ntiles + TC_GROUPS - 1) / TC_GROUPS;
   const int grid = (int)(want < NSM ? want : NSM);

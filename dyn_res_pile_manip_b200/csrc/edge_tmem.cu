@@ -1,0 +1,311 @@
+// K3, second tensor-core variant: the activation operand never touches shared memory.
+//
+// k_edge_encode_tc (edge_tc.cu) stages every layer's activations in shared memory; with N = 64 an SS-mode
+// MMA then needs 6 KB of shared-memory operands per 32 tensor cycles, more than the SM can deliver, and the
+// st.shared + fence.proxy.async sit in each tile's serial chain.  Here the A operand lives in TENSOR MEMORY:
+//
+//   * a group owns 128 TMEM columns = two 64-column regions X, Y used in ping-pong: layer L reads its A from
+//     one region and accumulates D into the other;
+//   * the epilogue thread (row r = TMEM lane, 32-column half h) loads its 32 accumulator columns, applies
+//     ReLU, splits into bf16 hi/lo and writes the packed pairs back IN PLACE with tcgen05.st (16 columns hi,
+//     16 columns lo: exactly the 32 columns it just read), so no other thread's data is touched;
+//   * biases are pre-loaded into the NEXT accumulator region with tcgen05.st and the layer's MMAs accumulate
+//     on top (enable_input_d = 1 from the first MMA);
+//   * tcgen05.mma takes A from TMEM ([taddr]) and only the 64x16 weight slice (2 KB) from shared memory.
+//
+// Column map of an A region at base P (k = input channel, 2 bf16 per 32-bit column):
+//   hi(k in 0..31) -> P+0..15, lo(k in 0..31) -> P+16..31, hi(k in 32..63) -> P+32..47, lo(k in 32..63) -> P+48..63
+#include "kernels.h"
+#include "tc_tile.cuh"
+
+namespace pile {
+
+constexpr uint32_t TM_W0_BYTES = 2 * b_bytes(64, 16);     // 4 KB   [hi | lo] of W0 [64 x 16] (cols: 6 features)
+constexpr uint32_t TM_WL_BYTES = 2 * b_bytes(64, 64);     // 16 KB  [hi | lo] of RE1 / RE2 / W_e
+constexpr uint32_t TC_EDGE2_BYTES = TM_W0_BYTES + 3 * TM_WL_BYTES;   // 52 KB
+static_assert(TC_EDGE2_BYTES == 4 * TC_EDGE2_FLOATS, "TC_EDGE2 slot size (common.cuh) out of sync");
+
+struct EdgeTmemSmem {
+  alignas(128) uint8_t w0[TM_W0_BYTES];
+  alignas(128) uint8_t wl[3][TM_WL_BYTES];
+  float b_re0[H], b_re1[H], b_re2[H], wd_rp[H], b_rp[H];
+  uint64_t bar[TC_GROUPS];
+  uint64_t w_bar;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void mma_bf16_ts_if(uint32_t pred, uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%6, %6, %6, %6}, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(pred), "r"(0u)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+               :
+               : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 16 fp32 values -> 16 32-bit words (this thread's TMEM lane) starting at column taddr
+__device__ __forceinline__ void tmem_st16f(uint32_t taddr, const float* v) {
+  uint32_t r[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i]);
+  tmem_st16(taddr, r);
+}
+
+// hidden layer: D (+)= A(TMEM region pa) * W^T, three passes x four K-steps, weights [hi | lo] at w
+__device__ __forceinline__ void issue_hidden_ts(uint32_t elected, uint32_t d, uint32_t pa, uint32_t w_hi, uint32_t w_lo,
+                                                uint32_t first_accumulates) {
+  constexpr uint32_t idesc = tc::make_idesc_bf16(TILE, H);
+  constexpr uint32_t BL = b_lbo(H);
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t w = pass == 2 ? w_lo : w_hi;
+    const uint32_t part = pass == 1 ? 16u : 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t a = pa + (k < 2 ? k * 8 : 32 + (k - 2) * 8) + part;
+      mma_bf16_ts_if(elected, d, a, tc::make_desc(w + k * 2 * BL, BL, B_SBO), idesc,
+                     (pass | k) != 0 ? 1u : first_accumulates);
+    }
+  }
+}
+
+template <bool RECORD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ efeat, const int* __restrict__ rowptr,
+                   uint8_t* __restrict__ m_re0, uint8_t* __restrict__ m_re1, uint8_t* __restrict__ m_re2,
+                   float* __restrict__ Ce, int B, int N) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  EdgeTmemSmem& S = *reinterpret_cast<EdgeTmemSmem*>(smem_raw);
+  const int g = threadIdx.x / GROUP_THREADS, t = threadIdx.x % GROUP_THREADS;
+  const int wig = t >> 5;
+  const int r = (wig & 3) * 32 + (t & 31);
+  const int half = wig >> 2;
+
+  if (threadIdx.x < 32) tc::tmem_alloc(&S.tmem_base, 512);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_GROUPS; ++i) tc::mbar_init(&S.bar[i], 1);
+    tc::mbar_init(&S.w_bar, 1);
+    tc::mbar_init_fence();
+  }
+  load_block(S.b_re0, wpack + wslot_offset(B_RE0), H);
+  load_block(S.b_re1, wpack + wslot_offset(B_RE1), H);
+  load_block(S.b_re2, wpack + wslot_offset(B_RE2), H);
+  load_block(S.wd_rp, wpack + wslot_offset(WD_RP), H);
+  load_block(S.b_rp, wpack + wslot_offset(B_RP), H);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (threadIdx.x == 0) {
+    tc::mbar_expect_tx(&S.w_bar, TC_EDGE2_BYTES);
+    tc::bulk_g2s(S.w0, wpack + wslot_offset(TC_EDGE2), TC_EDGE2_BYTES, &S.w_bar);
+  }
+
+  const uint32_t lane_off = (uint32_t)((wig & 3) * 32) << 16;
+  const uint32_t X = S.tmem_base + g * 128, Y = X + 64;          // column bases (lane field 0: MMA operands)
+  const uint32_t Xt = X + lane_off, Yt = Y + lane_off;           // this warp's lane quarter (ld / st)
+  uint64_t* bar = &S.bar[g];
+  uint32_t phase = 0;
+
+  const int tps = (KMAX * N + TILE - 1) / TILE;
+  const int ntiles = B * tps;                  // 32-bit tile arithmetic: 64-bit div/mod is emulated (~100 instr)
+  const int stride = (int)gridDim.x * TC_GROUPS;
+  struct Pre { int ne; float4 f0, f1; };
+  auto fetch = [&](int tile) {
+    Pre p;
+    p.ne = 0; p.f0 = make_float4(0.f, 0.f, 0.f, 0.f); p.f1 = p.f0;
+    if (tile < ntiles) {
+      const int b = tile / tps;
+      const long long slot = (long long)b * KMAX * N + (tile - b * tps) * TILE + r;
+      p.ne = tc::ldg_nc_s32(rowptr + (long long)b * (N + 1) + N);
+      if (half == 0) p.f0 = tc::ldg_nc_f4(efeat + slot * 8);
+      p.f1 = tc::ldg_nc_f4(efeat + slot * 8 + 4);
+    }
+    return p;
+  };
+  // hand the MMAs of one layer to the tensor core and wait for them
+  PILE_TRACE_DECL();
+  auto run = [&](auto issue) {
+    PILE_TRACE(2);
+    tmem_st_wait();                  // this thread's tcgen05.st (A operand, bias pre-load) have landed
+    tc::fence_before_sync();
+    PILE_TRACE(3);
+    group_barrier(g);
+    PILE_TRACE(4);
+    if (wig == 0) {
+      tc::fence_after_sync();
+      const uint32_t elected = tc::elect_one();
+      issue(elected);
+      if (elected) tc::mma_commit(bar);
+      __syncwarp();
+    }
+    tc::mbar_wait(bar, phase);
+    phase ^= 1;
+    tc::fence_after_sync();
+    PILE_TRACE(5);
+  };
+  // ReLU + hi/lo split of this thread's 32 accumulator columns of region `reg`, written back in place as the
+  // next layer's A operand; then pre-load `bias_next` (nullable) into the other region `other`
+  auto epilogue = [&](uint32_t reg, uint32_t other, const float* bias_next, float bias_scale_d, const float* wd_next,
+                      uint8_t* __restrict__ mask, long long mrow, bool valid) {
+    float v[2][16];
+    tc::tmem_ld16(reg + half * 32, v[0]);
+    tc::tmem_ld16(reg + half * 32 + 16, v[1]);
+    tc::tmem_ld_wait();
+    uint32_t hi[16], lo[16], mbits = 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const float a = v[q][j], b = v[q][j + 1];
+        if (RECORD) mbits |= (a > 0.f ? 1u : 0u) << (q * 16 + j) | (b > 0.f ? 1u : 0u) << (q * 16 + j + 1);
+        tc::split2(fmaxf(a, 0.f), fmaxf(b, 0.f), hi[q * 8 + j / 2], lo[q * 8 + j / 2]);
+      }
+    tmem_st16(reg + half * 32, hi);
+    tmem_st16(reg + half * 32 + 16, lo);
+    if (RECORD && valid) *reinterpret_cast<uint32_t*>(mask + mrow * 8 + half * 4) = mbits;
+    if (bias_next != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float bv[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 b4 = ld4(bias_next + half * 32 + q * 16 + j);
+          bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+          if (wd_next != nullptr) {
+            const float4 w4 = ld4(wd_next + half * 32 + q * 16 + j);
+            bv[j] = fmaf(w4.x, bias_scale_d, bv[j]); bv[j + 1] = fmaf(w4.y, bias_scale_d, bv[j + 1]);
+            bv[j + 2] = fmaf(w4.z, bias_scale_d, bv[j + 2]); bv[j + 3] = fmaf(w4.w, bias_scale_d, bv[j + 3]);
+          }
+        }
+        tmem_st16f(other + half * 32 + q * 16, bv);
+      }
+    }
+  };
+
+  int tile = (int)blockIdx.x * TC_GROUPS + g;
+  Pre cur = fetch(tile);
+  tc::mbar_wait(&S.w_bar, 0);
+  const uint32_t w0 = tc::smem_u32(S.w0), wl0 = tc::smem_u32(S.wl[0]), wl1 = tc::smem_u32(S.wl[1]), wl2 = tc::smem_u32(S.wl[2]);
+
+  while (tile < ntiles) {
+    const int b = tile / tps;
+    const int e0 = (tile - b * tps) * TILE;
+    const int nrows = min(TILE, cur.ne - e0);
+    const long long slot0 = (long long)b * KMAX * N + e0;
+    const Pre nxt = fetch(tile + stride);
+    if (nrows > 0) {
+      PILE_TRACE(1);
+      const bool valid = r < nrows;
+      const float d = cur.f1.y;
+      // layer-0 operand (K = 16: 6 features, zeros) into X; bias_0 pre-loaded into Y
+      if (half == 0) {
+        uint32_t hi[8], lo[8];
+        const float f[8] = {valid ? cur.f0.x : 0.f, valid ? cur.f0.y : 0.f, valid ? cur.f0.z : 0.f, valid ? cur.f0.w : 0.f,
+                            valid ? cur.f1.x : 0.f, valid ? cur.f1.y : 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tc::split2(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
+#pragma unroll
+        for (int i = 4; i < 8; ++i) { hi[i] = 0u; lo[i] = 0u; }
+        tmem_st8(Xt, hi);
+        tmem_st8(Xt + 16, lo);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float bv[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 b4 = ld4(S.b_re0 + half * 32 + q * 16 + j);
+          bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+        }
+        tmem_st16f(Yt + half * 32 + q * 16, bv);
+      }
+      // layer 0: A = X (one K-step), D = Y
+      run([&](uint32_t el) {
+        constexpr uint32_t idesc = tc::make_idesc_bf16(TILE, H);
+        constexpr uint32_t BL = b_lbo(H);
+        const uint32_t w_hi = w0, w_lo = w0 + TM_W0_BYTES / 2;
+        mma_bf16_ts_if(el, Y, X, tc::make_desc(w_hi, BL, B_SBO), idesc, 1u);
+        mma_bf16_ts_if(el, Y, X + 16, tc::make_desc(w_hi, BL, B_SBO), idesc, 1u);
+        mma_bf16_ts_if(el, Y, X, tc::make_desc(w_lo, BL, B_SBO), idesc, 1u);
+      });
+      epilogue(Yt, Xt, S.b_re1, 0.f, nullptr, m_re0, slot0 + r, valid);
+      // layer 1: A = Y, D = X
+      run([&](uint32_t el) { issue_hidden_ts(el, X, Y, wl0, wl0 + TM_WL_BYTES / 2, 1u); });
+      epilogue(Xt, Yt, S.b_re2, 0.f, nullptr, m_re1, slot0 + r, valid);
+      // layer 2: A = X, D = Y; then pre-load the hoisted constant w_d d + b of the propagator into X
+      run([&](uint32_t el) { issue_hidden_ts(el, Y, X, wl1, wl1 + TM_WL_BYTES / 2, 1u); });
+      epilogue(Yt, Xt, S.b_rp, d, S.wd_rp, m_re2, slot0 + r, valid);
+      // layer E: A = Y, D = X -> C_e rows
+      run([&](uint32_t el) { issue_hidden_ts(el, X, Y, wl2, wl2 + TM_WL_BYTES / 2, 1u); });
+      {
+        float v[2][16];
+        tc::tmem_ld16(Xt + half * 32, v[0]);
+        tc::tmem_ld16(Xt + half * 32 + 16, v[1]);
+        tc::tmem_ld_wait();
+        if (valid) {
+          float* out = Ce + (slot0 + r) * H + half * 32;
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) st8(out + q * 16 + h * 8, &v[q][h * 8]);
+        }
+      }
+    }
+    PILE_TRACE(6);
+    cur = nxt;
+    tile += stride;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_dealloc(S.tmem_base, 512);
+}
+
+PILE_TRACE_SETTER(set_edge_tmem_trace)
+
+int launch_edge_encode_tmem(const float* wpack, const float* efeat, const Csr& csr, const Masks* mk, float* Ce,
+                            int B, int N, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_edge_encode_tmem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(EdgeTmemSmem));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_edge_encode_tmem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(EdgeTmemSmem));
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const long long ntiles = (long long)B * ((KMAX * N + TILE - 1) / TILE);
+  const long long want = (ntiles + TC_GROUPS - 1) / TC_GROUPS;
+  const int grid = (int)(want < NSM ? want : NSM);
+  if (mk)
+    k_edge_encode_tmem<true><<<grid, TC_THREADS, sizeof(EdgeTmemSmem), st>>>(wpack, efeat, csr.rowptr, mk->re0, mk->re1,
+                                                                             mk->re2, Ce, B, N);
+  else
+    k_edge_encode_tmem<false><<<grid, TC_THREADS, sizeof(EdgeTmemSmem), st>>>(wpack, efeat, csr.rowptr, nullptr, nullptr,
+                                                                              nullptr, Ce, B, N);
+  PILE_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace pile

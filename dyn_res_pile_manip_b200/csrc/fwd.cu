@@ -361,7 +361,7 @@ k_propagate(const float* __restrict__ wpack, const int* __restrict__ rowptr, con
   }
 }
 
-int g_use_tensor_cores = 1;
+int g_use_tensor_cores = 2;   // default: tcgen05 tiles, relation encoder with A in tensor memory
 
 template <typename Kern>
 static int set_smem(Kern k, size_t bytes) {

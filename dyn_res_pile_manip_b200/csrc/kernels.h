@@ -56,14 +56,18 @@ int launch_forward(const float* wpack, const float* attr, const float* dens, con
                    const Masks* masks, float* s_out, long long s_out_stride, int B, int N, cudaStream_t st,
                    cudaEvent_t* ev = nullptr);   // ev: 6 events recorded before each kernel and after the last
 
-// process-wide switch: 1 = tcgen05 GEMM tiles for the relation encoder (default), 0 = FP32 CUDA-core tiles
+// process-wide switch: 0 = FP32 CUDA-core tiles, 1 = tcgen05 tiles with shared-memory activations,
+// 2 = 1 + relation encoder with the activation operand in tensor memory
 extern int g_use_tensor_cores;
 int launch_edge_encode_tc(const float* wpack, const float* attr, const float* dens, const float* s_cur,
                           long long s_stride, const Csr& csr, const Masks* mk, float* efeat, float* Ce, int B, int N,
                           cudaStream_t st);
 
+int launch_edge_encode_tmem(const float* wpack, const float* efeat, const Csr& csr, const Masks* mk, float* Ce,
+                            int B, int N, cudaStream_t st);
 int set_edge_trace(long long* buf, int cap);
 int set_node_trace(long long* buf, int cap);
+int set_edge_tmem_trace(long long* buf, int cap);
 int launch_node_encode_tc(const float* wpack, const float* attr, const float* dens, const float* s_delta,
                           const Masks* mk, const StepScratch& ws, int B, int N, cudaStream_t st);
 // propagation step p on the tensor-core path: k_edge_agg + k_node_update_tc (p == PSTEP-1: + predictor)

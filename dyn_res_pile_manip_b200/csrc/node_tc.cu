@@ -101,18 +101,18 @@ k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr
   uint8_t* const a_lo = S.t[g].a[1];
   const uint32_t row_off = (r >> 3) * A_SBO + (r & 7) * 16;
   const uint32_t w = tc::smem_u32(S.w);
-  const long long R = (long long)B * N;
-  const long long ntiles = (R + TILE - 1) / TILE;
+  const int R = B * N;                         // 32-bit row arithmetic (launcher checks B*N < 2^31)
+  const int ntiles = (R + TILE - 1) / TILE;
   tc::mbar_wait(&S.w_bar, 0);
 
-  for (long long tile = (long long)blockIdx.x * TC_GROUPS + g; tile < ntiles; tile += (long long)gridDim.x * TC_GROUPS) {
-    const long long row = tile * TILE + r;
+  for (int tile = (int)blockIdx.x * TC_GROUPS + g; tile < ntiles; tile += (int)gridDim.x * TC_GROUPS) {
+    const int row = tile * TILE + r;
     const bool valid = row < R;
     float d = 0.f;
     if (valid) d = dens[row / N] / 5000.f;
     if (half == 0) {
       float f[8] = {0.f, 0.f, 0.f, 0.f, d, 1.f, 0.f, 0.f};
-      if (valid) { f[0] = s_delta[row * 3]; f[1] = s_delta[row * 3 + 1]; f[2] = s_delta[row * 3 + 2]; f[3] = attr[row]; }
+      if (valid) { const float* sd = s_delta + (long long)row * 3; f[0] = sd[0]; f[1] = sd[1]; f[2] = sd[2]; f[3] = attr[row]; }
       store_chunk(a_hi, a_lo, row_off, f);
     } else {
       const float f[8] = {1.f, d, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -126,7 +126,7 @@ k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr
       tc::tmem_ld16(c.taddr + half * 32 + q * 16, v);
       tc::tmem_ld_wait();
       const uint32_t m = relu_to_tile<RECORD>(a_hi, a_lo, row_off + (half * 4 + q * 2) * A_LBO, v);
-      if (RECORD && valid) *reinterpret_cast<uint16_t*>(m_pe0 + row * 8 + half * 4 + q * 2) = (uint16_t)m;
+      if (RECORD && valid) *reinterpret_cast<uint16_t*>(m_pe0 + (long long)row * 8 + half * 4 + q * 2) = (uint16_t)m;
     }
     // PE layer 1 -> particle_encode = effect_0
     run_gemm(c, [&](uint32_t el) {
@@ -140,7 +140,7 @@ k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr
       const uint32_t m = relu_to_tile<RECORD>(a_hi, a_lo, row_off + (half * 4 + q * 2) * A_LBO, v);
       if (valid) {
         st16_tb(eff, tile, r, half * 4 + q * 2, v);
-        if (RECORD) *reinterpret_cast<uint16_t*>(m_pe1 + row * 8 + half * 4 + q * 2) = (uint16_t)m;
+        if (RECORD) *reinterpret_cast<uint16_t*>(m_pe1 + (long long)row * 8 + half * 4 + q * 2) = (uint16_t)m;
       }
     }
     // C_p = W_p p_enc + w_d d + b
@@ -182,11 +182,11 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
            float* __restrict__ agg, int B, int N) {
   const int l16 = threadIdx.x & 15;
   const unsigned hmask = 0xffffu << (threadIdx.x & 16);
-  const long long R = (long long)B * N;
-  const long long nhw = (long long)gridDim.x * (blockDim.x >> 4);
+  const int R = B * N;                                   // 32-bit: 64-bit div/mod is emulated
+  const int nhw = (int)gridDim.x * (int)(blockDim.x >> 4);
   const int kc = l16 >> 1, sub = (l16 & 1) * 4;          // this lane's 4 channels inside chunk kc
-  for (long long node = (long long)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); node < R; node += nhw) {
-    const int b = (int)(node / N), i = (int)(node % N);
+  for (int node = (int)blockIdx.x * (int)(blockDim.x >> 4) + (int)(threadIdx.x >> 4); node < R; node += nhw) {
+    const int b = node / N, i = node - b * N;
     const int* rp = rowptr + (long long)b * (N + 1) + i;
     const int e_lo = rp[0], cnt = rp[1] - e_lo;
     const long long slot = (long long)b * KMAX * N + e_lo;
@@ -242,8 +242,8 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
   const uint32_t w_a = LAST ? w : w + NB_WRS;
   const uint32_t w_rs = w;                                  // non-last only
   const uint32_t w_v0 = w + NB_WA, w_v1 = w + NB_WA + NB_K80;   // last only
-  const long long R = (long long)B * N;
-  const long long ntiles = (R + TILE - 1) / TILE;
+  const int R = B * N;
+  const int ntiles = (R + TILE - 1) / TILE;
   PILE_TRACE_DECL();
   if (LAST && half == 1) {       // constant aux chunk (1, 0, ...) for the predictor biases
     const float f[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -251,8 +251,8 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
   }
   tc::mbar_wait(&S.w_bar, 0);
 
-  for (long long tile = (long long)blockIdx.x * TC_GROUPS + g; tile < ntiles; tile += (long long)gridDim.x * TC_GROUPS) {
-    const long long row = tile * TILE + r;
+  for (int tile = (int)blockIdx.x * TC_GROUPS + g; tile < ntiles; tile += (int)gridDim.x * TC_GROUPS) {
+    const int row = tile * TILE + r;
     const bool valid = row < R;
     PILE_TRACE(1);
     // A = split(agg row): four 32-byte loads in flight, then the hi/lo split
@@ -293,7 +293,7 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
       const uint32_t m = relu_to_tile<RECORD>(a_hi, a_lo, row_off + (half * 4 + q * 2) * A_LBO, v);
       if (valid) {
         if (!LAST) st16_tb(eff, tile, r, half * 4 + q * 2, v);
-        if (RECORD) *reinterpret_cast<uint16_t*>(m_eff + row * 8 + half * 4 + q * 2) = (uint16_t)m;
+        if (RECORD) *reinterpret_cast<uint16_t*>(m_eff + (long long)row * 8 + half * 4 + q * 2) = (uint16_t)m;
       }
     }
     if (!LAST) {
@@ -321,7 +321,7 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
         tc::tmem_ld16(c.taddr + half * 32 + q * 16, v);
         tc::tmem_ld_wait();
         const uint32_t m = relu_to_tile<RECORD>(a_hi, a_lo, row_off + (half * 4 + q * 2) * A_LBO, v);
-        if (RECORD && valid) *reinterpret_cast<uint16_t*>(m_q + row * 8 + half * 4 + q * 2) = (uint16_t)m;
+        if (RECORD && valid) *reinterpret_cast<uint16_t*>(m_q + (long long)row * 8 + half * 4 + q * 2) = (uint16_t)m;
       }
       run_gemm(c, [&](uint32_t el) {
         issue_gemm<16, 4, true>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w_v1, w_v1 + NB_V1 / 2);
@@ -331,7 +331,7 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
         tc::tmem_ld16(c.taddr, v);
         tc::tmem_ld_wait();
         if (valid) {
-          const int b = (int)(row / N), i = (int)(row % N);
+          const int b = row / N, i = row - b * N;
           const float* sc = s_cur + (long long)b * s_stride + i * 3;
           float* so = s_out + (long long)b * o_stride + i * 3;
           so[0] = v[0] + sc[0];

@@ -17,7 +17,7 @@ class RolloutEngine:
 
     # kernels per model step: FP32 engine nbr_search, node_encode, edge_encode, 3 x propagate; tensor engine
     # nbr_search, node_encode_tc, edge_features, edge_encode_tc, 3 x (edge_agg + node_update_tc)
-    LAUNCHES_PER_MODEL_STEP = {0: 6, 1: 10}
+    LAUNCHES_PER_MODEL_STEP = {0: 6, 1: 10, 2: 10}
 
     def __init__(self, model_dy, planner, rows, N, T, device=None, goal=None, goal_coor=None, use_graph=True,
                  reward_weight=None):

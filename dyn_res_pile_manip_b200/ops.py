@@ -17,7 +17,7 @@ KMAX = 10
 WSLOTS = ["W_PE0T", "B_PE0", "W_PE1T", "B_PE1", "W_RE0T", "B_RE0", "W_RE1T", "B_RE1", "W_RE2T", "B_RE2",
           "W_ET", "W_RT", "W_ST", "WD_RP", "B_RP", "W_PT", "W_AT", "WD_PP", "B_PP", "W_V0T", "B_V0", "W_V1T", "B_V1",
           "W_PE0", "W_PE1", "W_RE0", "W_RE1", "W_RE2", "W_E", "W_R", "W_S", "W_P", "W_A", "W_V0", "W_V1",
-          "TC_EDGE", "TC_NODE"]
+          "TC_EDGE", "TC_NODE", "TC_EDGE2"]
 
 CKPT_KEYS = [  # reference checkpoint layout, SURVEY.md §8b
     "model.particle_encoder.model.0", "model.particle_encoder.model.2",
@@ -26,10 +26,10 @@ CKPT_KEYS = [  # reference checkpoint layout, SURVEY.md §8b
     "model.particle_predictor.linear_0", "model.particle_predictor.linear_1"]
 
 
-def set_tensor_cores(enable):
-    """Select the GEMM engine of the relation encoder: True = tcgen05 tiles (default), False = FP32 CUDA cores.
-    Returns the previous setting."""
-    return bool(_lib.load().pile_set_tensor_cores(int(bool(enable))))
+def set_tensor_cores(mode):
+    """Select the GEMM engine: 0/False = FP32 CUDA cores, 1/True = tcgen05 tiles, 2 = tcgen05 tiles with the
+    relation encoder's activations in tensor memory.  Returns the previous setting."""
+    return int(_lib.load().pile_set_tensor_cores(int(mode)))
 
 
 def _stream():
@@ -121,6 +121,10 @@ def pack_weights(state, device):
                               tc_operand(pp[:, H:2 * H].contiguous()),
                               tc_operand(tc_augmented(v0, 80, [bv0])),
                               tc_operand(tc_augmented(_pad_rows(v1, 16), 80, [torch.cat([bv1, bv1.new_zeros(13)])]))]),
+        # relation encoder with the activation operand in tensor memory (csrc/edge_tmem.cu): plain weights,
+        # biases are pre-loaded into the accumulator
+        "TC_EDGE2": torch.cat([tc_operand(tc_augmented(re0, 16, [])), tc_operand(re1), tc_operand(re2),
+                               tc_operand(rp[:, 0:H].contiguous())]),
     }
     if lib.pile_wpack_num_slots() != len(WSLOTS):
         raise _lib.PileLibraryError("weight-slot table out of sync with libpilegnn")

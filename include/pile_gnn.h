@@ -27,9 +27,9 @@ int pile_nf_effect(void);        /* hidden width compiled in (config train.parti
 int pile_max_relations(void);    /* 10, model/gnn_dyn.py:231 */
 const char* pile_error_string(int code);
 
-/* GEMM engine of the relation encoder: 1 (default) = tcgen05/TMEM tensor-core tiles with bf16 hi/lo split
- * operands (3 passes, fp32 accumulate), 0 = FP32 CUDA-core tiles (the bit-for-bit stable parity anchor).
- * Process-wide; returns the previous setting. */
+/* GEMM engine: 0 = FP32 CUDA-core tiles (the parity anchor), 1 = tcgen05/TMEM tensor-core tiles with bf16
+ * hi/lo split operands (3 passes, fp32 accumulate) and shared-memory activation tiles, 2 = as 1 with the
+ * relation encoder's activation operand kept in tensor memory.  Process-wide; returns the previous setting. */
 int pile_set_tensor_cores(int enable);
 int pile_get_tensor_cores(void);
 

@@ -14,10 +14,11 @@ POS_TOL = 1e-4       # north_star: positions within 1e-4 relative after one step
 DEV = "cuda"
 
 
-@pytest.fixture(autouse=True, params=["fp32", "tc"])
+@pytest.fixture(autouse=True, params=["fp32", "tc", "tc_tmem"])
 def engine(request):
-    """Every parity test runs on both GEMM engines: FP32 CUDA-core tiles and tcgen05 (bf16 hi/lo split) tiles."""
-    old = ops.set_tensor_cores(request.param == "tc")
+    """Every parity test runs on all GEMM engines: FP32 CUDA-core tiles, tcgen05 (bf16 hi/lo split) tiles with
+    shared-memory activations, and the same with the relation encoder's activations in tensor memory."""
+    old = ops.set_tensor_cores({"fp32": 0, "tc": 1, "tc_tmem": 2}[request.param])
     yield request.param
     ops.set_tensor_cores(old)
 

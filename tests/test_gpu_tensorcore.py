@@ -18,8 +18,9 @@ def model():
     return P.PropNetDiffDenModel(synthetic.default_config(), True).to(DEV)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("N,B", [(7, 5), (50, 9), (100, 64), (300, 40), (13, 700)])
-def test_tc_step_matches_fp32_step(model, N, B):
+def test_tc_step_matches_fp32_step(model, N, B, mode):
     rng = np.random.RandomState(N)
     if N >= 10:
         s, dn = synthetic.make_pile_batch(B, N, seed=N)
@@ -31,7 +32,7 @@ def test_tc_step_matches_fp32_step(model, N, B):
     old = ops.set_tensor_cores(False)
     try:
         ref = model.predict_one_step(*args)
-        ops.set_tensor_cores(True)
+        ops.set_tensor_cores(mode)
         out = model.predict_one_step(*args)
     finally:
         ops.set_tensor_cores(old)
@@ -48,7 +49,7 @@ def test_tc_gradients_match_fp32_gradients(model):
     sd = rng.normal(0, 0.01, size=s.shape).astype(np.float32)
     wgt = torch.tensor(rng.normal(size=s.shape).astype(np.float32), device=DEV)
     grads = []
-    for flag in (False, True):
+    for flag in (0, 2):
         old = ops.set_tensor_cores(flag)
         try:
             s_t = torch.tensor(s, device=DEV, requires_grad=True)

@@ -1,0 +1,47 @@
+"""BASELINE config 4: gradient-based action refinement, forward + backward through a T=20 rollout,
+128 samples x 300 particles (one Adam iteration of PlannerGD's loop; reports fwd / bwd / total)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from dyn_res_pile_manip_b200 import PlannerGD, PropNetDiffDenModel, ops, synthetic
+
+S, N, T = 128, 300, 20
+cfg, env = synthetic.default_config(), synthetic.FakeEnv()
+torch.manual_seed(0)
+model = PropNetDiffDenModel(cfg, True).cuda()
+planner = PlannerGD(cfg, env)
+planner.particle_num = N
+st, dn = synthetic.make_pile_batch(1, N, seed=0)
+s0, dens, attr = torch.tensor(st).cuda(), torch.tensor(dn).cuda(), torch.zeros(1, N).cuda()
+goal = torch.tensor(synthetic.make_goal("bar")).cuda()
+coor = planner.goal_coordinates(goal.cpu().numpy(), "cuda")
+acts = torch.tensor(synthetic.random_actions(S, T, seed=1), device="cuda", requires_grad=True)
+opt = torch.optim.Adam([acts], lr=0.05)
+ev = lambda: torch.cuda.Event(enable_timing=True)
+res = {}
+for engine in ("tensor", "fp32"):
+    ops.set_tensor_cores(2 if engine == "tensor" else 0)
+    f, b, tot = [], [], []
+    for it in range(8):
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        out = planner.ptcl_model_rollout(s0, dens, attr, model, acts)
+        pred = out["model_rollout"]["state_pred"]
+        obs = pred.reshape(S, 1, T, N, 3).permute(0, 2, 1, 3, 4)
+        reward, _ = planner.ptcl_evaluate_traj(obs, goal, coor)
+        e1.record()
+        loss = torch.sum(-reward)
+        opt.zero_grad()
+        loss.backward()
+        e2.record()
+        opt.step()
+        e3.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            f.append(e0.elapsed_time(e1)); b.append(e1.elapsed_time(e2)); tot.append(e0.elapsed_time(e3))
+    res[engine] = {"fwd_ms": float(np.median(f)), "bwd_ms": float(np.median(b)), "iter_ms": float(np.median(tot)),
+                   "particle_steps_per_s_fwd_bwd": S * N * T / (float(np.median(tot)) * 1e-3)}
+ops.set_tensor_cores(2)
+print(json.dumps({"config": "cfg4: fwd+bwd through T=20, 128 samples x 300 particles (rollout + all-step reward + backward + Adam)",
+                  "engines": res}))

@@ -9,6 +9,8 @@ cfg, env = synthetic.default_config(), synthetic.FakeEnv()
 torch.manual_seed(0)
 model = PropNetDiffDenModel(cfg, True).cuda()
 planner = PlannerGD(cfg, env)
+which = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+ops.set_tensor_cores(2 if which == 2 else 1)
 eng = RolloutEngine(model, planner, 1024, 300, 1, use_graph=False)
 st, dn = synthetic.make_pile_batch(1, 300, seed=0)
 eng.load_state(st, dn)
