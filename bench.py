@@ -323,6 +323,23 @@ def main():
             plan = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "calls": len(lat),
                     "workload": "cfg2: 256 samples x 100 particles x T=10, host actions in -> host reward + MPPI record out"}
 
+            # the reference's own MPC entry point with its shipped configuration (config/mpc/config.yaml:38-43,
+            # env/flex_env.py:1020): 50 trajectories x 30 state variants, 100 particles, horizon 1, time budget
+            # 2000 ms -> 27 Adam iterations (planners.py:679-682)
+            st3, dn3 = synthetic.make_pile_batch(30, 100, seed=0)
+            act3 = synthetic.random_actions(50, 1, seed=9).transpose(1, 0, 2).astype(np.float64)
+            gd = []
+            for i in range(8):
+                t_a = time.perf_counter()
+                res = planner.trajectory_optimization_ptcl_multi_traj(
+                    st3, dn3, np.zeros((30, 100), np.float32), goal, model, act3, np.zeros(1), 50, 1, 200, None, None,
+                    time_lim=2000)
+                gd.append((time.perf_counter() - t_a) * 1e3)
+            gd = sorted(gd[2:])
+            plan["gd_planner"] = {"p50_ms": gd[len(gd) // 2], "calls": len(gd), "iterations": int(res["iter_num"]) + 1,
+                                  "workload": "trajectory_optimization_ptcl_multi_traj: 50 traj x 30 variants x 100 particles, "
+                                              "T=1, numpy in -> result dict out (reference budget for this call: 2000 ms)"}
+
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             chunk = 16 if N >= 200 else 32

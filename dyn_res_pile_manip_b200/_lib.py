@@ -45,6 +45,8 @@ SIGNATURES = {
     "pile_rollout_backward": (_I, [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "pile_reward": (_I, [_P, _LL, _LL, _I, _P, _I, _I, _P, _I, _P, _F, _F, _I, _P, _P, _P]),
     "pile_reward_backward": (_I, [_P, _LL, _LL, _I, _P, _I, _I, _P, _I, _P, _F, _F, _I, _P, _P, _P, _LL, _I, _P]),
+    "pile_adam_clamp": (_I, [_P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _P, _P, _P]),
+    "pile_fps": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "pile_mppi_num_chunks": (_I, [_I]),
     "pile_mppi_partials": (_I, [_P, _P, _I, _I, _F, _P, _P]),
     "pile_mppi_combine": (_I, [_P, _I, _I, _P, _P]),

@@ -2,6 +2,7 @@
 #include "../../include/pile_gnn.h"
 #include "common.cuh"
 #include "kernels.h"
+#include <math.h>
 
 using namespace pile;
 
@@ -352,6 +353,22 @@ int pile_reward_backward(const float* states, long long n_states, long long stat
   return launch_reward_bwd(states, n_states, state_stride, N, goal_img, Hh, Ww, goal_coor, M, cam[0], cam[1],
                            cam[2], cam[3], off_x, off_y, normalize, g_reward, argmin, g_states, g_stride,
                            accumulate, (cudaStream_t)stream);
+}
+
+int pile_fps(const float* pts, int n_sets, int n, int dim, int count, int init_idx, float* gap_workspace,
+             int* out_idx, float* out_pts, float* out_radius, void* stream) {
+  if (!pts || !gap_workspace || !out_idx || !out_pts) return (int)cudaErrorInvalidValue;
+  return launch_fps(pts, n_sets, n, dim, count, init_idx, gap_workspace, out_idx, out_pts, out_radius,
+                    (cudaStream_t)stream);
+}
+
+int pile_adam_clamp(float* actions, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, int step,
+                    float lr, float beta1, float beta2, float eps, const float* lo4, const float* hi4, void* stream) {
+  if (!actions || !grad || !exp_avg || !exp_avg_sq || n <= 0 || (n & 3) || step <= 0 || !lo4 || !hi4)
+    return (int)cudaErrorInvalidValue;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  return launch_adam_clamp(actions, grad, exp_avg, exp_avg_sq, n, beta1, beta2, (float)((double)lr / bc1),
+                           (float)sqrt(bc2), eps, lo4, hi4, (cudaStream_t)stream);
 }
 
 int pile_mppi_num_chunks(int S) { return mppi_num_chunks(S); }

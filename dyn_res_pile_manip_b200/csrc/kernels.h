@@ -82,6 +82,10 @@ int launch_reward_bwd(const float* states, long long n_states, long long state_s
                       int Hh, int Ww, const float* goal_coor, int M, float fx, float fy, float cx, float cy,
                       float off_x, float off_y, int normalize, const float* g_reward, const int* argmin_in,
                       float* g_states, long long g_stride, int accumulate, cudaStream_t st);
+int launch_fps(const float* pts, int n_sets, int n, int dim, int count, int init_idx, float* gap_ws, int* out_idx,
+               float* out_pts, float* out_radius, cudaStream_t st);
+int launch_adam_clamp(float* p, const float* g, float* m, float* v, long long n, float b1, float b2, float step_size,
+                      float bc2_sqrt, float eps, const float* lo4, const float* hi4, cudaStream_t st);
 int mppi_num_chunks(int S);
 int launch_mppi_partials(const float* reward, const float* acts, int S, int T, float weight, float* part,
                          cudaStream_t st);

@@ -260,3 +260,121 @@ int launch_mppi_combine(const float* part, int P, int T, float* out, cudaStream_
 }
 
 }  // namespace pile
+
+// ------------------------------------------------------------------------------------------------
+// Farthest-point sampling (reference utils.fps_np, utils.py:451-466; used by the planner to thin the goal
+// pixels, planners.py:620-624, and by the MPC loop to resample observations).  One CTA per point set:
+// start at init_idx, repeatedly take the point farthest from the chosen set (first index on ties, like
+// numpy argmax); distances are sqrt(sum of squares) in float32 with numpy's left-to-right sum.
+// ------------------------------------------------------------------------------------------------
+namespace pile {
+
+constexpr int FPS_THREADS = 1024;
+
+__global__ void __launch_bounds__(FPS_THREADS)
+k_fps(const float* __restrict__ pts, int n, int dim, int count, int init_idx, float* __restrict__ gap_ws,
+      int* __restrict__ out_idx, float* __restrict__ out_pts, float* __restrict__ out_radius) {
+  __shared__ float s_val[FPS_THREADS / 32];
+  __shared__ int s_arg[FPS_THREADS / 32];
+  __shared__ int s_pick;
+  const int set = blockIdx.x;
+  pts += (size_t)set * n * dim;
+  gap_ws += (size_t)set * n;
+  out_idx += (size_t)set * count;
+  out_pts += (size_t)set * count * dim;
+  int pick = init_idx;
+  for (int it = 0; it < count; ++it) {
+    float c[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < dim; ++k) c[k] = pts[(size_t)pick * dim + k];
+    if (threadIdx.x == 0) {
+      out_idx[it] = pick;
+      for (int k = 0; k < dim; ++k) out_pts[(size_t)it * dim + k] = c[k];
+    }
+    float best = -1.f;
+    int arg = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < dim; ++k) {
+        const float d = __fsub_rn(pts[(size_t)i * dim + k], c[k]);
+        s = k == 0 ? __fmul_rn(d, d) : __fadd_rn(s, __fmul_rn(d, d));
+      }
+      float g = __fsqrt_rn(s);
+      if (it > 0) g = fminf(gap_ws[i], g);
+      gap_ws[i] = g;
+      if (g > best) { best = g; arg = i; }       // ascending i per thread: first index wins inside a thread
+    }
+    // block arg-max, lowest index on ties
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = best; s_arg[threadIdx.x >> 5] = arg; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      best = threadIdx.x < (blockDim.x >> 5) ? s_val[threadIdx.x] : -1.f;
+      arg = threadIdx.x < (blockDim.x >> 5) ? s_arg[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+      }
+      if (threadIdx.x == 0) {
+        s_pick = arg;
+        if (it == count - 1 && out_radius) out_radius[set] = best;
+      }
+    }
+    __syncthreads();
+    pick = s_pick;
+  }
+}
+
+int launch_fps(const float* pts, int n_sets, int n, int dim, int count, int init_idx, float* gap_ws, int* out_idx,
+               float* out_pts, float* out_radius, cudaStream_t st) {
+  if (n_sets <= 0 || n <= 0 || dim < 1 || dim > 3 || count <= 0 || count > n || init_idx < 0 || init_idx >= n)
+    return (int)cudaErrorInvalidValue;
+  k_fps<<<n_sets, FPS_THREADS, 0, st>>>(pts, n, dim, count, init_idx, gap_ws, out_idx, out_pts, out_radius);
+  PILE_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace pile
+
+// ------------------------------------------------------------------------------------------------
+// Adam step on the action sequences + clamp to the workspace box, one launch (reference planners.py:674,
+// 742-764: torch.optim.Adam(lr, betas=(0.9, 0.999)) followed by four clamp_ calls).  Same update formula as
+// torch's single-tensor Adam; step_size = lr / (1 - b1^t) and bc2_sqrt = sqrt(1 - b2^t) come from the host.
+// ------------------------------------------------------------------------------------------------
+namespace pile {
+
+struct Box4 { float lo[4], hi[4]; };
+
+__global__ void k_adam_clamp(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n, float b1, float b2, float step_size,
+                             float bc2_sqrt, float eps, Box4 box) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+  const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  float x = p[i] - step_size * (mi / denom);
+  const int c = (int)(i & 3);
+  x = fminf(fmaxf(x, box.lo[c]), box.hi[c]);
+  p[i] = x;
+}
+
+int launch_adam_clamp(float* p, const float* g, float* m, float* v, long long n, float b1, float b2, float step_size,
+                      float bc2_sqrt, float eps, const float* lo4, const float* hi4, cudaStream_t st) {
+  Box4 box;
+  for (int i = 0; i < 4; ++i) { box.lo[i] = lo4[i]; box.hi[i] = hi4[i]; }
+  k_adam_clamp<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, b1, b2, step_size, bc2_sqrt, eps, box);
+  PILE_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace pile

@@ -385,3 +385,29 @@ def mppi_combine(parts, T):
     _lib.check(_lib.load().pile_mppi_combine(_lib.ptr(parts), parts.shape[0], T, _lib.ptr(out), _stream()),
                "pile_mppi_combine")
     return out
+
+
+def fps(pts, count, init_idx=0):
+    """Farthest-point sampling on the GPU (utils.fps_np contract): pts [n, dim] or [sets, n, dim] float32 CUDA
+    -> (picked points [.., count, dim], indices [.., count] int32, covering radius [..])."""
+    pts = _f32(pts)
+    _require_cuda(pts, "pts")
+    single = pts.dim() == 2
+    p3 = pts[None] if single else pts
+    S, n, dim = p3.shape
+    dev = pts.device
+    gap = torch.empty(S, n, dtype=torch.float32, device=dev)
+    idx = torch.empty(S, count, dtype=torch.int32, device=dev)
+    out = torch.empty(S, count, dim, dtype=torch.float32, device=dev)
+    rad = torch.empty(S, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().pile_fps(_lib.ptr(p3.contiguous()), S, n, dim, int(count), int(init_idx), _lib.ptr(gap),
+                                    _lib.ptr(idx), _lib.ptr(out), _lib.ptr(rad), _stream()), "pile_fps")
+    return (out[0], idx[0], rad[0]) if single else (out, idx, rad)
+
+
+def adam_clamp(actions, grad, exp_avg, exp_avg_sq, step, lr, lo4, hi4, betas=(0.9, 0.999), eps=1e-8):
+    """In-place torch.optim.Adam update of `actions` [..., 4] for 1-based `step`, then clamp to the box."""
+    _lib.check(_lib.load().pile_adam_clamp(_lib.ptr(actions), _lib.ptr(grad), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq),
+                                           actions.numel(), int(step), float(lr), float(betas[0]), float(betas[1]),
+                                           float(eps), _lib.host_floats(lo4), _lib.host_floats(hi4), _stream()),
+               "pile_adam_clamp")

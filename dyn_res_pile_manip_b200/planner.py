@@ -89,6 +89,7 @@ class PlannerGD(Planner):
         self.goals = GoalCache()
         self.dist_group = None      # torch.distributed process group for sample-sharded planning
         self.device = torch.device('cuda')
+        self._goal_coor_cache = {}
 
     # ---- workspace box (planners.py:150-155, 756-760) ---------------------------------------------
     def action_box(self, cvx_l=0):
@@ -248,57 +249,75 @@ class PlannerGD(Planner):
         rew_mean_d = torch.zeros(max(n_iter, 1), device=device)
         rew_std_d = torch.zeros(max(n_iter, 1), device=device)
 
+        # ---- static device state of the optimisation (no autograd graph, no host sync inside the loop) --------
+        N, T = self.particle_num, n_act
+        rows = traj_num * n_batch                       # flat row = traj * n_batch + b  (planners.py:661-663)
         act_seqs = np.repeat(act_seq.transpose(1, 0, 2)[:, :, np.newaxis, :], n_batch, axis=0)
-        act_seqs_tensor = torch.tensor(act_seqs, device=device, dtype=torch.float, requires_grad=True)
-        reward_seqs_tensor = torch.ones((traj_num * n_batch, 1), device=device, dtype=torch.float)
+        act_seqs_tensor = torch.tensor(act_seqs, device=device, dtype=torch.float)     # [rows, T, 1, 4]
+        acts = act_seqs_tensor.view(rows, T, 4)
+        net = model_dy.model
+        wpack = net.packed_weights(device)
+        scratch = net.workspace.scratch(rows, N, device)
+        bwd_scratch = net.workspace.bwd(rows, N, device)
+        tape = ops.new_tape(rows, N, T, device)
+        s0 = state_cur_tensor.repeat(traj_num, 1, 1).contiguous()
+        dens = state_param_tensor.repeat(traj_num).contiguous()
+        attr = attr_cur_tensor.repeat(traj_num, 1).contiguous()
+        states = torch.empty(rows, T, N, 3, device=device, dtype=torch.float)
+        g_states = torch.zeros(rows, T, N, 3, device=device, dtype=torch.float)
+        g_reward = torch.full((rows,), -1.0, device=device)        # d(sum(-reward)) / d reward
+        exp_avg = torch.zeros_like(acts)
+        exp_avg_sq = torch.zeros_like(acts)
+        goal_img = self.goals.shaped(obs_goal_tensor)
+        cam = [float(v) for v in self.cam_params]
+        lr = self.config['mpc']['gd']['lr']
+        reward_seqs_tensor = torch.ones((rows, 1), device=device, dtype=torch.float)
         start = time.time()
-        optimizer = torch.optim.Adam([act_seqs_tensor], lr=self.config['mpc']['gd']['lr'], betas=(0.9, 0.999))
         max_reward = -float('inf') * torch.ones(n_batch, device=device, dtype=torch.float)
         max_reward_traj_idx = torch.zeros(n_batch, device=device, dtype=torch.long)
         best_actions_of_samples = torch.zeros((n_batch, n_act, self.action_dim), device=device, dtype=torch.float)
         lo, hi = self.action_box(0)
-        lo_t = torch.tensor(lo, device=device, dtype=torch.float)
-        hi_t = torch.tensor(hi, device=device, dtype=torch.float)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        rollout_ms, optim_ms, timed = [], [], []
+        timed = []
         batch_ids = torch.arange(n_batch, device=device)
+        last = states[:, T - 1]                          # view: last-step states, stride T*N*3
 
         i = -1
         for i in range(n_iter):
-            mdl_inp = act_seqs_tensor.permute(0, 2, 1, 3).reshape(-1, n_act, self.action_dim)
             e0, e1, e2, e3 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             e0.record()
             try:
-                out = self.ptcl_model_rollout(state_cur_tensor, state_param_tensor, attr_cur_tensor, model_dy, mdl_inp,
-                                              enable_grad=True)
+                ops.rollout_forward_raw(wpack, attr, dens, s0, acts, self.cam12, self.global_scale,
+                                        model_dy.adj_thresh, scratch, tape, out=states)
             except _lib.PileLibraryError:
                 print('OOM error')
                 break
             e1.record()
-            pred = out['model_rollout']['state_pred']
-            obs_seqs_tensor = pred.reshape(n_sample * n_batch, 1, n_act, self.particle_num, 3).permute(0, 2, 1, 3, 4)
-            reward_seqs_tensor, _ = self.ptcl_evaluate_traj(obs_seqs_tensor, obs_goal_tensor, obs_goal_coor_tensor,
-                                                            distractor_df_fn=distractor_df_fn,
-                                                            act_seqs_tensor=act_seqs_tensor)
-            reward_seqs_tensor = reward_seqs_tensor.reshape(n_sample, n_batch)
-            with torch.no_grad():
-                # per state variant: keep the best trajectory seen so far (planners.py:721-727), on device
-                cur_max, idx_best = torch.max(reward_seqs_tensor, dim=0)
-                better = cur_max > max_reward
-                max_reward = torch.where(better, cur_max, max_reward)
-                max_reward_traj_idx = torch.where(better, idx_best, max_reward_traj_idx)
-                picked = act_seqs_tensor.detach()[idx_best * n_batch + batch_ids, :, 0]
-                best_actions_of_samples = torch.where(better[:, None, None], picked, best_actions_of_samples)
-                rew_mean_d[i] = reward_seqs_tensor[:, 0].mean()
-                rew_std_d[i] = reward_seqs_tensor[:, 0].std()
+            # the loss only looks at the last step (reward_seqs = next_r[:, -1], planners.py:438)
+            reward, argmin = ops.reward_raw(last, rows, T * N * 3, N, goal_img, obs_goal_coor_tensor, cam, (0., 0.),
+                                            True, want_argmin=True)
+            reward_seqs_tensor = reward.view(n_sample, n_batch)
+            # per state variant: keep the best trajectory seen so far (planners.py:721-727), on device
+            cur_max, idx_best = torch.max(reward_seqs_tensor, dim=0)
+            better = cur_max > max_reward
+            max_reward = torch.where(better, cur_max, max_reward)
+            max_reward_traj_idx = torch.where(better, idx_best, max_reward_traj_idx)
+            picked = acts[idx_best * n_batch + batch_ids]
+            best_actions_of_samples = torch.where(better[:, None, None], picked, best_actions_of_samples)
+            rew_mean_d[i] = reward_seqs_tensor[:, 0].mean()
+            rew_std_d[i] = reward_seqs_tensor[:, 0].std()
             e2.record()
-            loss = torch.sum(-reward_seqs_tensor)
-            optimizer.zero_grad()
-            loss.backward()
-            optimizer.step()
+            try:
+                # loss = sum(-reward); backward through reward, T model steps and the pusher model; Adam; clamp
+                g_states.zero_()
+                ops.reward_backward_raw(last, rows, T * N * 3, N, goal_img, obs_goal_coor_tensor, cam, (0., 0.), True,
+                                        g_reward, argmin, g_states[:, T - 1], T * N * 3, False)
+                g_act = ops.rollout_backward_raw(wpack, dens, s0, acts, self.cam12, self.global_scale, tape, states,
+                                                 g_states, bwd_scratch)
+                ops.adam_clamp(acts, g_act, exp_avg, exp_avg_sq, i + 1, lr, lo, hi)
+            except _lib.PileLibraryError:
+                print('OOM error')
+                break
             e3.record()
-            with torch.no_grad():     # clamp to the workspace box (planners.py:756-764)
-                act_seqs_tensor.data[:, :, 0, :] = torch.minimum(torch.maximum(act_seqs_tensor.data[:, :, 0, :], lo_t), hi_t)
             timed.append((e0, e1, e2, e3))
 
         torch.cuda.synchronize()
@@ -307,6 +326,7 @@ class PlannerGD(Planner):
         done = i + 1 if n_iter > 0 else 0
         rew_mean[0, :done] = rew_mean_d[:done].cpu().numpy()
         rew_std[0, :done] = rew_std_d[:done].cpu().numpy()
+        reward_seqs_tensor = reward_seqs_tensor.reshape(n_sample, n_batch)
 
         reward_seqs = reward_seqs_tensor.data.cpu().numpy()
         act_seqs = act_seqs_tensor.data.cpu().numpy()
@@ -353,12 +373,26 @@ class PlannerGD(Planner):
 
     # ---- helpers -----------------------------------------------------------------------------------------
     def goal_coordinates(self, obs_goal, device):
-        """FPS-thinned (col,row) pixels of the goal region (planners.py:620-624)."""
+        """FPS-thinned (col,row) pixels of the goal region (planners.py:620-624).  On a CUDA device the
+        sampling runs in libpilegnn (`pile_fps`, same picks as utils.fps_np); results are cached per goal."""
         g = np.asarray(obs_goal)
+        key = (g.shape, self.particle_num, str(device), hash(g.tobytes()))
+        hit = self._goal_coor_cache.get(key)
+        if hit is not None:
+            return hit
         rc = np.argwhere(g < 0.5)
         coords = rc[:, ::-1].astype(np.float32)
-        picked, _ = fps_np(coords, min(self.particle_num * 5, coords.shape[0]), 0)
-        return torch.tensor(picked, device=device, dtype=torch.float)
+        count = min(self.particle_num * 5, coords.shape[0])
+        if torch.device(device).type == 'cuda':
+            picked, _, _ = ops.fps(torch.as_tensor(np.ascontiguousarray(coords), device=device), count, 0)
+            out = picked.contiguous()
+        else:
+            picked, _ = fps_np(coords, count, 0)
+            out = torch.tensor(picked, device=device, dtype=torch.float)
+        if len(self._goal_coor_cache) > 8:
+            self._goal_coor_cache.clear()
+        self._goal_coor_cache[key] = out
+        return out
 
     # ---- MPPI planner: sample -> rollout -> score -> softmax-weighted mean, sample-sharded ----------
     def trajectory_optimization_mppi(self, state_cur_np, state_param, attr_cur_np, obs_goal, model_dy, act_seq,

@@ -119,6 +119,20 @@ int pile_reward_backward(const float* states, long long n_states, long long stat
                          const float* g_reward, const int* argmin, float* g_states, long long g_stride,
                          int accumulate, void* stream);
 
+/* ---- action update: replaces optimizer.step() + the clamp_ calls of the GD planner (planners.py:674,
+ * 742-764).  actions/grad/exp_avg/exp_avg_sq: n floats laid out [..., 4] = (sx, sy, ex, ey); torch.optim.Adam's
+ * update for 1-based `step`, then clamp component c to [lo4[c], hi4[c]] (HOST pointers). */
+int pile_adam_clamp(float* actions, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, int step,
+                    float lr, float beta1, float beta2, float eps, const float* lo4, const float* hi4, void* stream);
+
+/* ---- farthest-point sampling: replaces utils.fps_np (utils.py:451-466) as used for the goal pixels
+ * (planners.py:620-624).  pts [n_sets, n, dim] (dim <= 3); per set: start at init_idx, take the farthest
+ * point `count` times (first index on ties).  gap_workspace [n_sets, n] floats; out_idx [n_sets, count],
+ * out_pts [n_sets, count, dim], out_radius (nullable) [n_sets] = covering radius after all picks (the
+ * dist.max() that fps_np returns). */
+int pile_fps(const float* pts, int n_sets, int n, int dim, int count, int init_idx, float* gap_workspace,
+             int* out_idx, float* out_pts, float* out_radius, void* stream);
+
 /* ---- MPPI weighting: replaces PlannerGD.optimize_action (planners.py:549-561) -------------------
  * partials: [pile_mppi_num_chunks(S)][2 + 4T] = (max z, sum exp(z-max), sum exp(z-max)*act) with
  * z = reward_weight*reward; combine merges P such records (chunks and/or ranks) into one record

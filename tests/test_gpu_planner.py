@@ -118,3 +118,21 @@ def test_full_size_properties(setup, N, B, T):
                     torch.zeros(1, N), acts[3:4, :2].cpu())
     err = float((p1[3, :2].cpu() - ref[0]).norm() / ref[0].norm())
     assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("kind,count", [("bar", 300), ("tee", 1500), ("disc", 77)])
+def test_gpu_fps_picks_equal_numpy_fps(setup, kind, count):
+    """pile_fps must reproduce utils.fps_np pick for pick (goal-pixel thinning, planners.py:620-624)."""
+    goal = synthetic.make_goal(kind)
+    coords = np.argwhere(goal < 0.5)[:, ::-1].astype(np.float32)
+    ref, rad = synthetic.fps_np(coords, count, 0)
+    pts, idx, r = ops.fps(torch.tensor(np.ascontiguousarray(coords), device=DEV), count, 0)
+    assert np.array_equal(pts.cpu().numpy(), ref)
+    assert abs(float(r) - float(rad)) < 1e-5
+    # 3-D float coordinates, several sets at once
+    rng = np.random.RandomState(0)
+    clouds = rng.uniform(-1, 1, (3, 2000, 3)).astype(np.float32)
+    got, _, _ = ops.fps(torch.tensor(clouds, device=DEV), 64, 5)
+    for s in range(3):
+        want, _ = synthetic.fps_np(clouds[s], 64, 5)
+        assert np.array_equal(got[s].cpu().numpy(), want)

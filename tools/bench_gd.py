@@ -20,8 +20,8 @@ acts = torch.tensor(synthetic.random_actions(S, T, seed=1), device="cuda", requi
 opt = torch.optim.Adam([acts], lr=0.05)
 ev = lambda: torch.cuda.Event(enable_timing=True)
 res = {}
-for engine in ("tensor", "fp32"):
-    ops.set_tensor_cores(2 if engine == "tensor" else 0)
+for engine in ("tensor", "tensor_smem", "fp32"):
+    ops.set_tensor_cores({"tensor": 2, "tensor_smem": 1, "fp32": 0}[engine])
     f, b, tot = [], [], []
     for it in range(8):
         e0, e1, e2, e3 = ev(), ev(), ev(), ev()
