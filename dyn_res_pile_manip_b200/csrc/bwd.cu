@@ -423,9 +423,14 @@ int launch_step_backward(const float* wpack, const Csr& csr, const Masks& mk, co
                                                         mk.edge[0], mk.pe1, mk.pe0, s.gagg[0], s.gz, s.gcp, nullptr,
                                                         g_s_delta, B, N);
   PILE_CHECK_LAUNCH();
-  k_bwd_edge<<<ge, NT, sizeof(BwdEdgeSmem), st>>>(wpack, csr.rowptr, csr.row, mk.edge[0], mk.edge[1], mk.edge[2],
-                                                  mk.re0, mk.re1, mk.re2, s.gagg[0], s.gagg[1], s.gagg[2], s.gx, B, N);
-  PILE_CHECK_LAUNCH();
+  if (g_use_tensor_cores) {
+    const int e = launch_bwd_edge_tc(wpack, csr, mk, s.gagg[0], s.gagg[1], s.gagg[2], s.gx, B, N, st);
+    if (e) return e;
+  } else {
+    k_bwd_edge<<<ge, NT, sizeof(BwdEdgeSmem), st>>>(wpack, csr.rowptr, csr.row, mk.edge[0], mk.edge[1], mk.edge[2],
+                                                    mk.re0, mk.re1, mk.re2, s.gagg[0], s.gagg[1], s.gagg[2], s.gx, B, N);
+    PILE_CHECK_LAUNCH();
+  }
   k_bwd_positions<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(csr.rowptr, csr.trowptr, csr.tedge, s.gx, g_pred,
                                                                 g_stride, g_s_cur, B, N);
   PILE_CHECK_LAUNCH();

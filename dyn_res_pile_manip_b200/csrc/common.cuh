@@ -21,6 +21,7 @@ constexpr int LDX = 12;        // shared-memory stride of the 8-wide input featu
 constexpr int NT = 256;        // threads per GEMM CTA: 8 warps x (4 rows/lane x 8 cols/warp)
 constexpr int NSM = 148;
 constexpr int TC_EDGE2_FLOATS = 13312;  // 52 KB, layout in edge_tmem.cu
+constexpr int TC_BWD_EDGE_FLOATS = 13312;  // 52 KB, layout in bwd_tc.cu
 constexpr int TC_NODE_FLOATS = 29952;   // 117 KB of bf16 hi/lo weight images, layout in node_tc.cu
 
 // ---- packed weight buffer (floats). Forward blocks are transposed [K][H]; backward blocks keep the
@@ -51,6 +52,8 @@ enum WSlot {
   TC_NODE,
   // relation-encoder operands of the A-in-TMEM variant (edge_tmem.cu): W0 [64 x 16], RE1, RE2, W_e [64 x 64]
   TC_EDGE2,
+  // relation-encoder backward on tcgen05 (bwd_tc.cu): W_e^T, RE2^T, RE1^T [64 x 64], RE0[:, 2:5]^T padded to [16 x 64]
+  TC_BWD_EDGE,
   W_NUM
 };
 
@@ -64,6 +67,7 @@ __host__ __device__ inline int wslot_size(int s) {
     case TC_EDGE: return 4 * H * H;
     case TC_NODE: return TC_NODE_FLOATS;
     case TC_EDGE2: return TC_EDGE2_FLOATS;
+    case TC_BWD_EDGE: return TC_BWD_EDGE_FLOATS;
     default: return H * H;
   }
 }

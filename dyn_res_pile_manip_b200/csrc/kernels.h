@@ -65,6 +65,8 @@ int launch_edge_encode_tc(const float* wpack, const float* attr, const float* de
 
 int launch_edge_encode_tmem(const float* wpack, const float* efeat, const Csr& csr, const Masks* mk, float* Ce,
                             int B, int N, cudaStream_t st);
+int launch_bwd_edge_tc(const float* wpack, const Csr& csr, const Masks& mk, const float* ga0, const float* ga1,
+                       const float* ga2, float* gx, int B, int N, cudaStream_t st);
 int set_edge_trace(long long* buf, int cap);
 int set_node_trace(long long* buf, int cap);
 int set_edge_tmem_trace(long long* buf, int cap);
