@@ -231,6 +231,7 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
                  long long s_stride, float* __restrict__ s_out, long long o_stride, int B, int N) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   NodeUpdSmemTc& S = *reinterpret_cast<NodeUpdSmemTc*>(smem_raw);
+  const long long t_entry = clock64();
   // non-last: [WRS | WA]; last: [WA | V0 | V1]
   GroupCtx c = tile_prologue(S, wpack, LAST ? OFF_WA : OFF_WRS, LAST ? (NB_WA + NB_K80 + NB_V1) : (NB_WRS + NB_WA));
   const int g = c.g, wig = c.wig;
@@ -245,11 +246,14 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
   const int R = B * N;
   const int ntiles = (R + TILE - 1) / TILE;
   PILE_TRACE_DECL();
+  if (trace && tr_cap > 0) trace[tr_n++] = (7ll << 56) | (t_entry & 0x00ffffffffffffffLL);
+  PILE_TRACE(8);
   if (LAST && half == 1) {       // constant aux chunk (1, 0, ...) for the predictor biases
     const float f[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     store_chunk(S.t[g].aux[0], S.t[g].aux[1], row_off, f);
   }
   tc::mbar_wait(&S.w_bar, 0);
+  PILE_TRACE(9);
 
   for (int tile = (int)blockIdx.x * TC_GROUPS + g; tile < ntiles; tile += (int)gridDim.x * TC_GROUPS) {
     const int row = tile * TILE + r;
@@ -267,6 +271,18 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
 #pragma unroll
       for (int j = 0; j < 4; ++j) store_chunk(a_hi, a_lo, row_off + (half * 4 + j) * A_LBO, o[j]);
     }
+    // C_p + eff of the first 16 columns are fetched BEFORE the GEMM is handed to the tensor core, so their HBM/L2
+    // latency overlaps the MMA; the second 16 columns are fetched while the first are processed
+    float x[16], e[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { x[j] = 0.f; e[j] = 0.f; }
+    if (valid) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        ld8(Cp + tb_off(tile, r, half * 4 + h), x + h * 8);
+        ld8(eff + tb_off(tile, r, half * 4 + h), e + h * 8);
+      }
+    }
     PILE_TRACE(2);
     run_gemm(c, [&](uint32_t el) {
       issue_gemm<64, 4, false>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w_a, w_a + NB_WA / 2);
@@ -275,21 +291,22 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
     // eff <- ReLU(W_a agg + C_p + eff)
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      float a[16], e[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { a[j] = 0.f; e[j] = 0.f; }
-      if (valid) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          ld8(Cp + tb_off(tile, r, half * 4 + q * 2 + h), a + h * 8);
-          ld8(eff + tb_off(tile, r, half * 4 + q * 2 + h), e + h * 8);
-        }
-      }
       float v[16];
       tc::tmem_ld16(c.taddr + half * 32 + q * 16, v);
       tc::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] += a[j] + e[j];
+      for (int j = 0; j < 16; ++j) v[j] += x[j] + e[j];
+      if (q == 0) {          // prefetch the second half now that x / e are consumed
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { x[j] = 0.f; e[j] = 0.f; }
+        if (valid) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            ld8(Cp + tb_off(tile, r, half * 4 + 2 + h), x + h * 8);
+            ld8(eff + tb_off(tile, r, half * 4 + 2 + h), e + h * 8);
+          }
+        }
+      }
       const uint32_t m = relu_to_tile<RECORD>(a_hi, a_lo, row_off + (half * 4 + q * 2) * A_LBO, v);
       if (valid) {
         if (!LAST) st16_tb(eff, tile, r, half * 4 + q * 2, v);
@@ -342,6 +359,7 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
     }
     PILE_TRACE(6);
   }
+  PILE_TRACE(10);
   tile_epilogue(S);
 }
 

@@ -330,6 +330,11 @@ class PlannerGD(Planner):
 
         reward_seqs = reward_seqs_tensor.data.cpu().numpy()
         act_seqs = act_seqs_tensor.data.cpu().numpy()
+        # trajectories sharded over ranks (set planner.dist_group / traj_offset): the only exchange of the GD
+        # planner is this one merge of the per-variant winners
+        max_reward, max_reward_traj_idx, best_actions_of_samples = merge_best_across_ranks(
+            max_reward, max_reward_traj_idx + int(getattr(self, 'traj_offset', 0)), best_actions_of_samples,
+            self.dist_group)
         # vote over state variants for the winning trajectory, then the best variant of it (planners.py:771-781)
         max_reward_traj_count = torch.bincount(max_reward_traj_idx)
         idx_best_act = torch.argmax(max_reward_traj_count).item()
@@ -439,6 +444,28 @@ class PlannerGD(Planner):
                     rec = ops.mppi_combine(allrec.view(world, -1), T)
             mean = (rec[2:] / rec[1]).reshape(T, 1, 4).double().cpu().numpy()
         return {'action_sequence': mean[:, 0, :], 'reward': rewards.cpu().numpy(), 'record': rec.cpu().numpy()}
+
+
+def merge_best_across_ranks(max_reward, traj_idx, best_actions, group=None):
+    """Per state variant keep the best (reward, global trajectory index, action sequence) over all ranks.
+    max_reward [n_batch], traj_idx [n_batch] (already global), best_actions [n_batch, T, 4]; ties go to the lower
+    global trajectory index, which makes the result independent of the sharding.  No-op without a process group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return max_reward, traj_idx, best_actions
+    world = dist.get_world_size(group)
+    n_batch = max_reward.shape[0]
+    mine = torch.cat([max_reward.reshape(n_batch, 1).float(), traj_idx.reshape(n_batch, 1).float(),
+                      best_actions.reshape(n_batch, -1).float()], dim=1).contiguous()
+    everyone = torch.empty(world * mine.numel(), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(everyone, mine.reshape(-1), group=group)
+    everyone = everyone.view(world, n_batch, -1)
+    rew, idx = everyone[:, :, 0], everyone[:, :, 1]
+    best_rew = rew.max(dim=0).values
+    cand = torch.where(rew == best_rew[None], idx, torch.full_like(idx, float('inf')))
+    win = cand.argmin(dim=0)                                   # rank holding the winner of each variant
+    picked = everyone[win, torch.arange(n_batch, device=mine.device)]
+    return picked[:, 0], picked[:, 1].long(), picked[:, 2:].reshape(best_actions.shape)
 
 
 def shard_size(n_sample, world):

@@ -136,3 +136,22 @@ def test_gpu_fps_picks_equal_numpy_fps(setup, kind, count):
     for s in range(3):
         want, _ = synthetic.fps_np(clouds[s], 64, 5)
         assert np.array_equal(got[s].cpu().numpy(), want)
+
+
+def test_adam_clamp_kernel_equals_torch_adam():
+    """pile_adam_clamp == torch.optim.Adam(lr=0.05, betas=(0.9, 0.999)) + clamp (planners.py:674, 756-764)."""
+    rng = np.random.RandomState(0)
+    p0 = rng.uniform(-4, 4, (37, 5, 4)).astype(np.float32)
+    lo, hi = [-5., -5., -3.5, -3.5], [5., 5., 3.5, 3.5]
+    ref = torch.tensor(p0, requires_grad=True)
+    opt = torch.optim.Adam([ref], lr=0.05, betas=(0.9, 0.999))
+    mine = torch.tensor(p0, device=DEV)
+    m, v = torch.zeros_like(mine), torch.zeros_like(mine)
+    for step in range(1, 6):
+        g = rng.normal(size=p0.shape).astype(np.float32) * (10.0 ** rng.randint(-3, 2))
+        ref.grad = torch.tensor(g)
+        opt.step()
+        with torch.no_grad():
+            ref.data = torch.minimum(torch.maximum(ref.data, torch.tensor(lo)), torch.tensor(hi))
+        ops.adam_clamp(mine, torch.tensor(g, device=DEV), m, v, step, 0.05, lo, hi)
+        np.testing.assert_allclose(mine.cpu().numpy(), ref.detach().numpy(), rtol=0, atol=2e-6)

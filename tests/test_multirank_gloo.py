@@ -69,6 +69,35 @@ def test_two_ranks_give_the_single_rank_plan(tmp_path):
     np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)
 
 
+def _merge_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(7)
+    rew = torch.randn(world, 5, generator=g)
+    rew[1, 2] = rew[0, 2]                                   # a tie between ranks: lower trajectory index must win
+    idx = torch.tensor([[3, 1, 4, 0, 2], [7, 9, 5, 8, 6]])
+    acts = torch.randn(world, 5, 3, 4, generator=g)
+    r, i, a = planner_mod.merge_best_across_ranks(rew[rank], idx[rank], acts[rank])
+    if rank == 0:
+        torch.save((r, i, a, rew, idx, acts), out)
+    dist.destroy_process_group()
+
+
+def test_gd_best_merge_across_two_ranks(tmp_path):
+    out = str(tmp_path / "merge.pt")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_merge_worker, args=(2, port, out), nprocs=2, join=True)
+    r, i, a, rew, idx, acts = torch.load(out)
+    for v in range(5):
+        w = 0 if (rew[0, v] > rew[1, v] or (rew[0, v] == rew[1, v] and idx[0, v] < idx[1, v])) else 1
+        assert r[v] == rew[w, v] and i[v] == idx[w, v] and torch.equal(a[v], acts[w, v])
+    # single process: identity
+    r1, i1, a1 = planner_mod.merge_best_across_ranks(rew[0], idx[0], acts[0])
+    assert torch.equal(r1, rew[0]) and torch.equal(i1, idx[0])
+
+
 def test_shard_bounds_partition_the_samples():
     for world in (1, 2, 4, 8):
         spans = [planner_mod.shard_bounds(1024, r, world) for r in range(world)]

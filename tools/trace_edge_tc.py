@@ -26,7 +26,7 @@ v = buf.cpu().numpy()
 v = v[v != 0]
 tags = (v >> 56) & 0xff
 clk = v & ((1 << 56) - 1)
-names = {1: "tile start", 2: "layer top", 3: "fences done", 4: "barrier passed", 5: "mma done", 6: "tile end"}
+names = {1: "tile start", 2: "layer top", 3: "fences done", 4: "barrier passed", 5: "mma done", 6: "tile end", 7: "kernel entry", 8: "prologue done", 9: "weights landed", 10: "loop done"}
 t0 = clk[0]
 prev = t0
 for i, (tg, c) in enumerate(zip(tags, clk)):
