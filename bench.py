@@ -37,6 +37,7 @@ WORKLOADS = {   # name -> (samples per GPU, particles, horizon)   (BASELINE.json
     "cfg3_n50": (1024, 50, 20),
     "cfg2": (256, 100, 10),
     "cfg5": (2048, 300, 30),
+    "cfg1": (1, 100, 1),          # the reference's own CPU-runnable case (reference arm / parity only)
 }
 
 
@@ -86,26 +87,30 @@ class ClockSampler:
                 "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows), "reasons": sorted(reasons)}
 
 
-def cpu_reference_rate(N, T, chunk, min_seconds, warmup=0, steps=None):
-    """Time the CPU oracle (dense one-hot formulation = the reference's own algorithm) on a bounded sample
-    of the workload: `chunk` action sequences x N particles x T steps per pass (rollout + last-step reward)."""
+def cpu_reference_rate(N, T, chunk, min_seconds, warmup=0, steps=None, device="cpu"):
+    """Time the oracle (dense one-hot formulation = the reference's own algorithm) on a bounded sample of the
+    workload: `chunk` action sequences x N particles x T steps per pass (rollout + last-step reward).
+    device="cpu": the reference's CPU path on all host cores; device="cuda": the same torch code on the B200
+    (cuBLAS/ATen kernels), reported as the 'existing GPU path' comparator."""
     from dyn_res_pile_manip_b200 import synthetic
     from oracle import pile_oracle as O
     torch.set_num_threads(os.cpu_count())
     env = synthetic.FakeEnv()
-    W = O.weights_from_seed(0)
+    W = {k: v.to(device) for k, v in O.weights_from_seed(0).items()}
     st, dn = synthetic.make_pile_batch(1, N, seed=0)
     goal = synthetic.make_goal("bar")
     coords = np.argwhere(goal < 0.5)[:, ::-1].astype(np.float32)
     coor, _ = synthetic.fps_np(coords, min(5 * N, len(coords)), 0)
-    goal_t, coor_t = torch.from_numpy(goal), torch.from_numpy(coor)
-    s0, dens, attr = torch.from_numpy(st), torch.from_numpy(dn), torch.zeros(1, N)
+    goal_t, coor_t = torch.from_numpy(goal), torch.from_numpy(coor).to(device)
+    s0, dens, attr = torch.from_numpy(st).to(device), torch.from_numpy(dn).to(device), torch.zeros(1, N, device=device)
 
     def one_pass(seed):
-        acts = torch.from_numpy(synthetic.random_actions(chunk, T, seed=seed))
+        acts = torch.from_numpy(synthetic.random_actions(chunk, T, seed=seed)).to(device)
         with torch.no_grad():
             pred = O.rollout(W, 0.08, env.get_cam_extrinsics(), synthetic.GLOBAL_SCALE, s0, dens, attr, acts)
             O.reward_ptcl(pred[:, -1], goal_t, env.get_cam_params(), coor_t)
+        if device != "cpu":
+            torch.cuda.synchronize()
 
     for w in range(warmup):
         one_pass(100 + w)
@@ -130,8 +135,9 @@ def run_reference(args, samples, N, T):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    chunk = 16 if N >= 200 else 32
-    rate, times, cores = cpu_reference_rate(N, T, chunk, 0, warmup=min(args.warmup, 1), steps=max(1, min(args.steps, 3)))
+    chunk = 1 if args.workload == "cfg1" else (16 if N >= 200 else 32)
+    rate, times, cores = cpu_reference_rate(N, T, chunk, 0, warmup=min(args.warmup, 1),
+                                            steps=max(1, min(args.steps, 50 if args.workload == "cfg1" else 3)))
     sample = "%d of %d action sequences x %d particles x T=%d per step (oracle/pile_oracle.py, dense one-hot form)" % (
         chunk, samples, N, T)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
@@ -341,8 +347,16 @@ def main():
                                               "T=1, numpy in -> result dict out (reference budget for this call: 2000 ms)"}
 
         cpu = None
+        torch_cuda = None
         if world == 1 and not args.no_cpu_baseline:
             chunk = 16 if N >= 200 else 32
+            # the reference algorithm with torch's own CUDA kernels on this B200 (dense one-hot bmm path)
+            try:
+                r_gpu, t_gpu, _ = cpu_reference_rate(N, T, chunk, 3.0, warmup=1, device="cuda")
+                torch_cuda = {"value": r_gpu, "unit": UNIT, "kind": "oracle port on torch-CUDA (cuBLAS/ATen), same B200",
+                              "sample": "%d passes of %d action sequences x %d particles x T=%d" % (len(t_gpu), chunk, N, T)}
+            except RuntimeError as err:      # e.g. out of memory for the dense [B, 10N, N] tensors
+                torch_cuda = {"value": None, "error": str(err)[:120]}
             rate, times, cores = cpu_reference_rate(N, T, chunk, 12.0)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d passes of %d of %d action sequences x %d particles x T=%d (oracle/pile_oracle.py, "
@@ -366,6 +380,8 @@ def main():
             line["mpc_plan_latency"] = plan
         if cpu:
             line["cpu_baseline"] = cpu
+        if torch_cuda:
+            line["torch_cuda_reference"] = torch_cuda
         del launches
     if world > 1:
         dist.barrier()

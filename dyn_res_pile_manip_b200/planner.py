@@ -288,7 +288,7 @@ class PlannerGD(Planner):
             try:
                 ops.rollout_forward_raw(wpack, attr, dens, s0, acts, self.cam12, self.global_scale,
                                         model_dy.adj_thresh, scratch, tape, out=states)
-            except _lib.PileLibraryError:
+            except (_lib.PileLibraryError, torch.cuda.OutOfMemoryError):
                 print('OOM error')
                 break
             e1.record()
@@ -314,7 +314,7 @@ class PlannerGD(Planner):
                 g_act = ops.rollout_backward_raw(wpack, dens, s0, acts, self.cam12, self.global_scale, tape, states,
                                                  g_states, bwd_scratch)
                 ops.adam_clamp(acts, g_act, exp_avg, exp_avg_sq, i + 1, lr, lo, hi)
-            except _lib.PileLibraryError:
+            except (_lib.PileLibraryError, torch.cuda.OutOfMemoryError):
                 print('OOM error')
                 break
             e3.record()

@@ -4,7 +4,8 @@ This file is the checker, never the product: only `tests/`, `__graft_entry__.smo
 `bench.py`'s CPU-baseline / `--impl reference` legs may import it.  The shipped path
 (`dyn_res_pile_manip_b200`) never imports anything from `oracle/` and has no CPU fallback.
 
-It is a plain torch-CPU (fp32) restatement of the reference algorithm, written in the
+It is a plain torch (fp32, CPU by default, device-agnostic so bench.py can also time the same dense
+algorithm with torch's CUDA kernels as the "existing GPU path" comparator) restatement of the reference algorithm, written in the
 reference's own dense formulation (one-hot receiver/sender matrices multiplied with
 `bmm`) so that timing it is an honest stand-in for "the reference's PyTorch CPU path":
 
@@ -73,7 +74,7 @@ def edge_lists(adj):
     out = []
     for b in range(adj.shape[0]):
         rs = adj[b].nonzero()
-        out.append((rs[:, 0].to(torch.int32).numpy().copy(), rs[:, 1].to(torch.int32).numpy().copy()))
+        out.append((rs[:, 0].to(torch.int32).cpu().numpy().copy(), rs[:, 1].to(torch.int32).cpu().numpy().copy()))
     return out
 
 
@@ -82,11 +83,11 @@ def one_hot_relations(adj, dtype=torch.float32):
     B, N, _ = adj.shape
     counts = adj.sum(dim=(1, 2))
     n_rel = int(counts.max())
-    Rr = torch.zeros(B, n_rel, N, dtype=dtype)
-    Rs = torch.zeros(B, n_rel, N, dtype=dtype)
+    Rr = torch.zeros(B, n_rel, N, dtype=dtype, device=adj.device)
+    Rs = torch.zeros(B, n_rel, N, dtype=dtype, device=adj.device)
     for b in range(B):
         rs = adj[b].nonzero()
-        slot = torch.arange(rs.shape[0])
+        slot = torch.arange(rs.shape[0], device=adj.device)
         Rr[b, slot, rs[:, 0]] = 1
         Rs[b, slot, rs[:, 1]] = 1
     return Rr, Rs
@@ -152,14 +153,14 @@ def world_to_cam_matrix(cam_extrinsic):
 
 
 def world2cam(cam_extrinsic, global_scale, pts):
-    M = world_to_cam_matrix(cam_extrinsic)
-    homog = torch.cat([pts, torch.ones(pts.shape[0], 1, dtype=pts.dtype)], dim=1)
+    M = world_to_cam_matrix(cam_extrinsic).to(pts.device)
+    homog = torch.cat([pts, torch.ones(pts.shape[0], 1, dtype=pts.dtype, device=pts.device)], dim=1)
     return torch.matmul(M, homog.T).T[:, :3] / global_scale
 
 
 def gen_s_delta(cam_extrinsic, global_scale, s_cur, action):
     """s_cur [B,N,3], action [B,4]=(sx,sy,ex,ey) -> s_delta [B,N,3]   (planners.py:211-257)."""
-    zero = torch.zeros(action.shape[0], 1, dtype=action.dtype)
+    zero = torch.zeros(action.shape[0], 1, dtype=action.dtype, device=action.device)
     start = world2cam(cam_extrinsic, global_scale, torch.cat([action[:, 0:1], zero, -action[:, 1:2]], 1))
     end = world2cam(cam_extrinsic, global_scale, torch.cat([action[:, 2:3], zero, -action[:, 3:4]], 1))
     push = end - start
@@ -216,7 +217,7 @@ def reward_ptcl(state, goal, cam_params, goal_coor, normalize=True, offset=(0., 
     B, N, _ = state.shape
     H, Wd = goal.shape
     fx, fy, cx, cy = cam_params
-    img = torch.from_numpy(shaped_goal_image(goal.detach().numpy())).to(state.dtype)
+    img = torch.from_numpy(shaped_goal_image(goal.detach().cpu().numpy())).to(device=state.device, dtype=state.dtype)
     px = state[..., 0] * fx / state[..., 2] + cx + offset[0]
     py = state[..., 1] * fy / state[..., 2] + cy + offset[1]
     pix = torch.stack([px, py], dim=-1)                  # (col,row)
