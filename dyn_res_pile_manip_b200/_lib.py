@@ -10,7 +10,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libpilegnn.so")
+LIB_PATH = os.environ.get("PILE_GNN_LIB") or os.path.join(CSRC, "libpilegnn.so")   # override: a prebuilt library
 
 _P = C.c_void_p
 _I = C.c_int

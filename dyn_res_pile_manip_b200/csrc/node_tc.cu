@@ -77,10 +77,24 @@ __device__ __forceinline__ void tile_epilogue(Smem& S) {
   if (threadIdx.x < 32) tc::tmem_dealloc(S.tmem_base, TC_GROUPS * NODE_TMEM_PER_GROUP);
 }
 
-// 16 consecutive channels (chunks kc, kc+1) of tile row r -> tile-blocked array
-__device__ __forceinline__ void st16_tb(float* __restrict__ base, long long tile, int r, int kc, const float (&v)[16]) {
-  st8(base + tb_off(tile, r, kc), &v[0]);
-  st8(base + tb_off(tile, r, kc + 1), &v[8]);
+// accumulator columns [0, 64) = P_r, [64, 128) = P_s of the group's tile -> row-major global arrays, one array at
+// a time through the staging tile (the A tile: its last MMA has completed).  Ends with the group barrier that
+// frees the tile for the next A operand.
+__device__ __forceinline__ void store_pr_ps(const GroupCtx& c, uint8_t* stage, int t, int r, int half,
+                                            float* __restrict__ Pr, float* __restrict__ Ps, long long row0, long long R) {
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float v[16];
+      tc::tmem_ld16(c.taddr + which * 64 + half * 32 + q * 16, v);
+      tc::tmem_ld_wait();
+      stage_put16(stage, r, half * 32 + q * 16, v);
+    }
+    group_barrier(c.g);
+    stage_flush(stage, t, which == 0 ? Pr : Ps, row0, R);
+    group_barrier(c.g);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -95,7 +109,7 @@ k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr
   extern __shared__ __align__(128) unsigned char smem_raw[];
   NodeEncSmemTc& S = *reinterpret_cast<NodeEncSmemTc*>(smem_raw);
   GroupCtx c = tile_prologue(S, wpack, OFF_PE0, OFF_WA);
-  const int g = c.g, wig = c.wig;
+  const int g = c.g, wig = c.wig, t = threadIdx.x % GROUP_THREADS;
   const int r = (wig & 3) * 32 + (threadIdx.x & 31), half = wig >> 2;
   uint8_t* const a_hi = S.t[g].a[0];
   uint8_t* const a_lo = S.t[g].a[1];
@@ -139,7 +153,7 @@ k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr
       tc::tmem_ld_wait();
       const uint32_t m = relu_to_tile<RECORD>(a_hi, a_lo, row_off + (half * 4 + q * 2) * A_LBO, v);
       if (valid) {
-        st16_tb(eff, tile, r, half * 4 + q * 2, v);
+        st16_tbc(eff, tile, r, half * 4 + q * 2, v);
         if (RECORD) *reinterpret_cast<uint16_t*>(m_pe1 + (long long)row * 8 + half * 4 + q * 2) = (uint16_t)m;
       }
     }
@@ -152,22 +166,13 @@ k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr
       float v[16];
       tc::tmem_ld16(c.taddr + half * 32 + q * 16, v);
       tc::tmem_ld_wait();
-      if (valid) st16_tb(Cp, tile, r, half * 4 + q * 2, v);
+      if (valid) st16_tbc(Cp, tile, r, half * 4 + q * 2, v);
     }
     // (P_r, P_s) = (W_r, W_s) p_enc : one N = 128 product, column half 0 -> P_r, half 1 -> P_s
     run_gemm(c, [&](uint32_t el) {
       issue_gemm<128, 4, false>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w + OFF_WRS, w + OFF_WRS + NB_WRS / 2);
     });
-    {
-      float* dst = half == 0 ? Pr : Ps;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v[16];
-        tc::tmem_ld16(c.taddr + half * 64 + q * 16, v);
-        tc::tmem_ld_wait();
-        if (valid) st16_tb(dst, tile, r, q * 2, v);
-      }
-    }
+    store_pr_ps(c, a_hi, t, r, half, Pr, Ps, (long long)tile * TILE, R);
   }
   tile_epilogue(S);
 }
@@ -234,7 +239,7 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
   const long long t_entry = clock64();
   // non-last: [WRS | WA]; last: [WA | V0 | V1]
   GroupCtx c = tile_prologue(S, wpack, LAST ? OFF_WA : OFF_WRS, LAST ? (NB_WA + NB_K80 + NB_V1) : (NB_WRS + NB_WA));
-  const int g = c.g, wig = c.wig;
+  const int g = c.g, wig = c.wig, t = threadIdx.x % GROUP_THREADS;
   const int r = (wig & 3) * 32 + (threadIdx.x & 31), half = wig >> 2;
   uint8_t* const a_hi = S.t[g].a[0];
   uint8_t* const a_lo = S.t[g].a[1];
@@ -259,18 +264,8 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
     const int row = tile * TILE + r;
     const bool valid = row < R;
     PILE_TRACE(1);
-    // A = split(agg row): four 32-byte loads in flight, then the hi/lo split
-    {
-      float o[4][8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[j][i] = 0.f;
-        if (valid) ld8(agg + tb_off(tile, r, half * 4 + j), o[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) store_chunk(a_hi, a_lo, row_off + (half * 4 + j) * A_LBO, o[j]);
-    }
+    // A = split(agg tile): whole 128-byte lines per request, then the hi/lo split into the canonical tile
+    load_rows_to_tile(agg, (long long)tile * TILE, R, t, a_hi, a_lo);
     // C_p + eff of the first 16 columns are fetched BEFORE the GEMM is handed to the tensor core, so their HBM/L2
     // latency overlaps the MMA; the second 16 columns are fetched while the first are processed
     float x[16], e[16];
@@ -279,8 +274,8 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
     if (valid) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        ld8(Cp + tb_off(tile, r, half * 4 + h), x + h * 8);
-        ld8(eff + tb_off(tile, r, half * 4 + h), e + h * 8);
+        ld8_tbc(Cp, tile, r, half * 4 + h, x + h * 8);
+        ld8_tbc(eff, tile, r, half * 4 + h, e + h * 8);
       }
     }
     PILE_TRACE(2);
@@ -302,14 +297,14 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
         if (valid) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            ld8(Cp + tb_off(tile, r, half * 4 + 2 + h), x + h * 8);
-            ld8(eff + tb_off(tile, r, half * 4 + 2 + h), e + h * 8);
+            ld8_tbc(Cp, tile, r, half * 4 + 2 + h, x + h * 8);
+            ld8_tbc(eff, tile, r, half * 4 + 2 + h, e + h * 8);
           }
         }
       }
       const uint32_t m = relu_to_tile<RECORD>(a_hi, a_lo, row_off + (half * 4 + q * 2) * A_LBO, v);
       if (valid) {
-        if (!LAST) st16_tb(eff, tile, r, half * 4 + q * 2, v);
+        if (!LAST) st16_tbc(eff, tile, r, half * 4 + q * 2, v);
         if (RECORD) *reinterpret_cast<uint16_t*>(m_eff + (long long)row * 8 + half * 4 + q * 2) = (uint16_t)m;
       }
     }
@@ -319,14 +314,7 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
         issue_gemm<128, 4, false>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w_rs, w_rs + NB_WRS / 2);
       });
       PILE_TRACE(5);
-      float* dst = half == 0 ? PrOut : PsOut;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v[16];
-        tc::tmem_ld16(c.taddr + half * 64 + q * 16, v);
-        tc::tmem_ld_wait();
-        if (valid) st16_tb(dst, tile, r, q * 2, v);
-      }
+      store_pr_ps(c, a_hi, t, r, half, PrOut, PsOut, (long long)tile * TILE, R);
     } else {
       // predictor: q = ReLU(V0 eff + c0);  s_pred = s_cur + V1 q + c1
       run_gemm(c, [&](uint32_t el) {

@@ -42,15 +42,22 @@ __host__ __device__ constexpr uint32_t b_lbo(int n_rows) { return (uint32_t)(n_r
 // bytes of one part (hi or lo) of a canonical [n_rows x k] bf16 weight image
 __host__ __device__ constexpr uint32_t b_bytes(int n_rows, int k) { return (uint32_t)(k / 8) * b_lbo(n_rows); }
 
-// Feature arrays stay row-major ([rows][64] fp32).  The tile kernels own one row per thread, so they move
-// 8 consecutive channels (one 32-byte sector) per instruction with sm_100's 256-bit global accesses; a
-// row-per-half-warp consumer (k_edge_agg) then streams whole 256-byte rows.  (A tile-blocked chunk-major
-// layout was measured: it coalesces the tile kernels better but turns k_edge_agg's 256-byte row reads into
-// eight scattered sectors and costs more than it saves.)
+// Arrays that k_edge_agg touches (agg, P_r, P_s, C_e) stay row-major ([rows][64] fp32): a half-warp there streams
+// whole 256-byte rows.  The tile kernels own one row per thread, so a direct access moves one 32-byte sector per
+// lane and 32 different lines per instruction -- measured to be what bounds the particle kernels (the LSU/L1
+// request rate, not HBM).  They therefore go through shared memory for these arrays (load_rows_to_tile,
+// stage_put16 / stage_flush below: whole 128-byte lines per request).  (Making ALL arrays tile-blocked was
+// measured too: it turns k_edge_agg's row reads into eight scattered sectors and costs more than it saves.)
 __host__ __device__ __forceinline__ long long tb_off(long long tile, int r, int kc) {
   return (tile * TILE + r) * (long long)H + kc * 8;
 }
 __device__ __forceinline__ long long tb_row(long long row, int kc) { return row * (long long)H + kc * 8; }
+// C_p and eff are touched by the tile kernels only (one row per thread), so they use a tile-blocked chunk-major
+// layout [tile][chunk 0..7][row 0..127][8 floats]: the 32 lanes of a warp (32 consecutive rows, same chunk) move
+// one contiguous 1 KB block per instruction.
+__host__ __device__ __forceinline__ long long tbc_off(long long tile, int r, int kc) {
+  return ((tile * 8 + kc) * TILE + r) * 8;
+}
 __device__ __forceinline__ void st8(float* __restrict__ p, const float* v) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
@@ -60,6 +67,14 @@ __device__ __forceinline__ void ld8(const float* __restrict__ p, float* v) {
   asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                : "l"(p));
+}
+
+__device__ __forceinline__ void ld8_tbc(const float* __restrict__ base, long long tile, int r, int kc, float* v) {
+  ld8(base + tbc_off(tile, r, kc), v);
+}
+__device__ __forceinline__ void st16_tbc(float* __restrict__ base, long long tile, int r, int kc, const float (&v)[16]) {
+  st8(base + tbc_off(tile, r, kc), &v[0]);
+  st8(base + tbc_off(tile, r, kc + 1), &v[8]);
 }
 
 struct GroupTile {          // per-group shared-memory operands
@@ -134,6 +149,48 @@ __device__ __forceinline__ uint32_t relu_to_tile(uint8_t* a_hi, uint8_t* a_lo, u
     store_chunk(a_hi, a_lo, off0 + h * A_LBO, o);
   }
   return m;
+}
+
+// ---- row-major [128 x 64] fp32 tiles <-> one-row-per-thread registers, through the (dead) A tile --------
+// The epilogue thread owns a whole row, a row-major global array wants whole 128-byte lines per request.  A
+// 32 KB staging tile (the group's a[0..1], free once its last MMA has completed) transposes between the two:
+// 16-byte slots, XOR-swizzled by the row so both sides are bank-conflict free.
+__device__ __forceinline__ uint32_t stage_off(int r, int slot) { return (uint32_t)r * 256u + (uint32_t)((slot ^ (r & 7)) << 4); }
+// this thread's 16 values of row r, columns c0 .. c0+15
+__device__ __forceinline__ void stage_put16(uint8_t* stage, int r, int c0, const float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(stage + stage_off(r, (c0 >> 2) + i)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+// all 256 threads of the group: staging tile -> rows [row0, row0 + 128) of a row-major [R][64] array
+__device__ __forceinline__ void stage_flush(const uint8_t* stage, int t, float* __restrict__ dst, long long row0, long long R) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int idx = it * GROUP_THREADS + t;
+    const int row = idx >> 4, slot = idx & 15;
+    const float4 v = *reinterpret_cast<const float4*>(stage + stage_off(row, slot));
+    if (row0 + row < R) st4(dst + (row0 + row) * H + slot * 4, v);
+  }
+}
+// all 256 threads of the group: rows [row0, row0+128) of a row-major [R][64] array -> hi/lo A tile (rows past R
+// are zero-filled).  A warp instruction covers 8 rows x 128 bytes (whole lines) and 8 consecutive rows of one
+// chunk per quarter-warp on the shared-memory side (conflict-free).
+__device__ __forceinline__ void load_rows_to_tile(const float* __restrict__ src, long long row0, long long R, int t,
+                                                  uint8_t* a_hi, uint8_t* a_lo) {
+  const int w = t >> 5, lane = t & 31;
+  float o[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = w * 16 + (j >> 1) * 8 + (lane & 7), kc = (j & 1) * 4 + (lane >> 3);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[j][i] = 0.f;
+    if (row0 + row < R) ld8(src + (row0 + row) * H + kc * 8, o[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = w * 16 + (j >> 1) * 8 + (lane & 7), kc = (j & 1) * 4 + (lane >> 3);
+    store_chunk(a_hi, a_lo, (row >> 3) * A_SBO + (row & 7) * 16 + kc * A_LBO, o[j]);
+  }
 }
 
 // everything a group needs to hand a layer to the tensor cores and wait for it

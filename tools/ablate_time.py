@@ -1,0 +1,26 @@
+"""Per-kernel-bucket times of one model step for the library named by PILE_GNN_LIB (measurement aid)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dyn_res_pile_manip_b200 import PlannerGD, PropNetDiffDenModel, _lib, ops, synthetic
+from dyn_res_pile_manip_b200.engine import RolloutEngine
+
+B, N = int(os.environ.get("ABL_B", 1024)), int(os.environ.get("ABL_N", 300))
+cfg, env = synthetic.default_config(), synthetic.FakeEnv()
+torch.manual_seed(0)
+model = PropNetDiffDenModel(cfg, True).cuda()
+planner = PlannerGD(cfg, env)
+eng = RolloutEngine(model, planner, B, N, 1, use_graph=False)
+st, dn = synthetic.make_pile_batch(1, N, seed=0)
+eng.load_state(st, dn)
+eng.actions.copy_(torch.from_numpy(synthetic.random_actions(B, 1, seed=1)))
+eng.evaluate(); torch.cuda.synchronize()
+lib = _lib.load()
+ms6 = (_lib.C.c_float * 6)()
+s_out = torch.empty(B, N, 3, device="cuda")
+wpack = model.model.packed_weights(torch.device("cuda"))
+_lib.check(lib.pile_profile_step(_lib.ptr(wpack), _lib.ptr(eng.attr), _lib.ptr(eng.dens), _lib.ptr(eng.s0),
+                                 _lib.ptr(eng.actions), 4, _lib.host_floats(planner.cam12),
+                                 float(planner.global_scale), 0.08, B, N, _lib.ptr(eng.scratch),
+                                 _lib.ptr(s_out), 10, ms6, ops._stream()), "pile_profile_step")
+print(os.path.basename(os.environ.get("PILE_GNN_LIB", "default")), " ".join("%.1f" % (1e3 * v) for v in ms6), "us  sum %.1f" % (1e3 * sum(ms6)))
