@@ -29,6 +29,7 @@ struct EdgeTmemSmem {
   alignas(128) uint8_t w0[TM_W0_BYTES];
   alignas(128) uint8_t wl[3][TM_WL_BYTES];
   float b_re0[H], b_re1[H], b_re2[H], wd_rp[H], b_rp[H];
+  alignas(128) uint8_t stage[TC_GROUPS][TILE * H * 4];     // C_e rows on their way out (tc_tile.cuh: stage_*)
   uint64_t bar[TC_GROUPS];
   uint64_t w_bar;
   uint32_t tmem_base;
@@ -263,13 +264,12 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
         tc::tmem_ld16(Xt + half * 32, v[0]);
         tc::tmem_ld16(Xt + half * 32 + 16, v[1]);
         tc::tmem_ld_wait();
-        if (valid) {
-          float* out = Ce + (slot0 + r) * H + half * 32;
-#pragma unroll
-          for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) st8(out + q * 16 + h * 8, &v[q][h * 8]);
-        }
+        // one row per thread -> whole 128-byte lines per store request, through the group's staging tile.  The
+        // next write to it is a full tile chain (several group barriers) away, so no trailing barrier is needed.
+        stage_put16(S.stage[g], r, half * 32, v[0]);
+        stage_put16(S.stage[g], r, half * 32 + 16, v[1]);
+        group_barrier(g);
+        stage_flush(S.stage[g], t, Ce, slot0, slot0 + nrows);
       }
     }
     PILE_TRACE(6);
