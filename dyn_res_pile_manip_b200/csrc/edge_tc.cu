@@ -209,7 +209,7 @@ k_edge_encode_tc(const float* __restrict__ wpack, const float* __restrict__ efea
         PILE_TRACE(3);
         group_barrier(g);
         PILE_TRACE(4);
-        if (wig == 0) {                  // warp-uniform: the whole warp walks the descriptors, one lane issues
+        if (wig == g) {                  // (issuer warps of the 4 groups sit on 4 different SM sub-partitions) warp-uniform: the whole warp walks the descriptors, one lane issues
           tc::fence_after_sync();
           const uint32_t elected = tc::elect_one();
           if (layer == 0) {

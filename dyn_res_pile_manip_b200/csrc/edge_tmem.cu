@@ -73,19 +73,19 @@ __device__ __forceinline__ void tmem_st16f(uint32_t taddr, const float* v) {
   tmem_st16(taddr, r);
 }
 
-// hidden layer: D (+)= A(TMEM region pa) * W^T, three passes x four K-steps, weights [hi | lo] at w
-__device__ __forceinline__ void issue_hidden_ts(uint32_t elected, uint32_t d, uint32_t pa, uint32_t w_hi, uint32_t w_lo,
+// hidden layer: D (+)= A(TMEM region pa) * W^T, three passes x four K-steps; dw = descriptor of the weight image's
+// hi part (the lo part follows TM_WL_BYTES / 2 later), built once per kernel so that an MMA costs one add
+__device__ __forceinline__ void issue_hidden_ts(uint32_t elected, uint32_t d, uint32_t pa, uint64_t dw,
                                                 uint32_t first_accumulates) {
   constexpr uint32_t idesc = tc::make_idesc_bf16(TILE, H);
   constexpr uint32_t BL = b_lbo(H);
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
-    const uint32_t w = pass == 2 ? w_lo : w_hi;
     const uint32_t part = pass == 1 ? 16u : 0u;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t a = pa + (k < 2 ? k * 8 : 32 + (k - 2) * 8) + part;
-      mma_bf16_ts_if(elected, d, a, tc::make_desc(w + k * 2 * BL, BL, B_SBO), idesc,
+      mma_bf16_ts_if(elected, d, a, tc::desc_advance(dw, (pass == 2 ? TM_WL_BYTES / 2 : 0u) + k * 2 * BL), idesc,
                      (pass | k) != 0 ? 1u : first_accumulates);
     }
   }
@@ -146,25 +146,27 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
   };
   // hand the MMAs of one layer to the tensor core and wait for them
   PILE_TRACE_DECL();
-  auto run = [&](auto issue) {
+  auto run = [&](auto issue, auto during) {
     PILE_TRACE(2);
     tmem_st_wait();                  // this thread's tcgen05.st (A operand, bias pre-load) have landed
     tc::fence_before_sync();
     PILE_TRACE(3);
     group_barrier(g);
     PILE_TRACE(4);
-    if (wig == 0) {
+    if (wig == g) {          // issuer warp g*8+g: the four groups issue from four different SM sub-partitions
       tc::fence_after_sync();
       const uint32_t elected = tc::elect_one();
       issue(elected);
       if (elected) tc::mma_commit(bar);
       __syncwarp();
     }
+    during();                        // work that overlaps the tensor pipe
     tc::mbar_wait(bar, phase);
     phase ^= 1;
     tc::fence_after_sync();
     PILE_TRACE(5);
   };
+  auto nothing = [] {};
   // ReLU + hi/lo split of this thread's 32 accumulator columns of region `reg`, written back in place as the
   // next layer's A operand; then pre-load `bias_next` (nullable) into the other region `other`
   auto epilogue = [&](uint32_t reg, uint32_t other, const float* bias_next, float bias_scale_d, const float* wd_next,
@@ -180,7 +182,7 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
       for (int j = 0; j < 16; j += 2) {
         const float a = v[q][j], b = v[q][j + 1];
         if (RECORD) mbits |= (a > 0.f ? 1u : 0u) << (q * 16 + j) | (b > 0.f ? 1u : 0u) << (q * 16 + j + 1);
-        tc::split2(fmaxf(a, 0.f), fmaxf(b, 0.f), hi[q * 8 + j / 2], lo[q * 8 + j / 2]);
+        tc::split2_relu(a, b, hi[q * 8 + j / 2], lo[q * 8 + j / 2]);
       }
     tmem_st16(reg + half * 32, hi);
     tmem_st16(reg + half * 32 + 16, lo);
@@ -207,7 +209,13 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
   int tile = (int)blockIdx.x * TC_GROUPS + g;
   Pre cur = fetch(tile);
   tc::mbar_wait(&S.w_bar, 0);
-  const uint32_t w0 = tc::smem_u32(S.w0), wl0 = tc::smem_u32(S.wl[0]), wl1 = tc::smem_u32(S.wl[1]), wl2 = tc::smem_u32(S.wl[2]);
+  const uint64_t dw0 = tc::make_desc(tc::smem_u32(S.w0), b_lbo(H), B_SBO);
+  const uint64_t dwl0 = tc::make_desc(tc::smem_u32(S.wl[0]), b_lbo(H), B_SBO);
+  const uint64_t dwl1 = tc::desc_advance(dwl0, TM_WL_BYTES), dwl2 = tc::desc_advance(dwl0, 2 * TM_WL_BYTES);
+  // C_e rows of the previous tile wait in the staging tile and leave while the next tile's first MMAs run
+  bool pending = false;
+  long long p_slot0 = 0;
+  int p_nrows = 0;
 
   while (tile < ntiles) {
     const int b = tile / tps;
@@ -244,37 +252,44 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
       // layer 0: A = X (one K-step), D = Y
       run([&](uint32_t el) {
         constexpr uint32_t idesc = tc::make_idesc_bf16(TILE, H);
-        constexpr uint32_t BL = b_lbo(H);
-        const uint32_t w_hi = w0, w_lo = w0 + TM_W0_BYTES / 2;
-        mma_bf16_ts_if(el, Y, X, tc::make_desc(w_hi, BL, B_SBO), idesc, 1u);
-        mma_bf16_ts_if(el, Y, X + 16, tc::make_desc(w_hi, BL, B_SBO), idesc, 1u);
-        mma_bf16_ts_if(el, Y, X, tc::make_desc(w_lo, BL, B_SBO), idesc, 1u);
+        const uint64_t d_lo = tc::desc_advance(dw0, TM_W0_BYTES / 2);
+        mma_bf16_ts_if(el, Y, X, dw0, idesc, 1u);
+        mma_bf16_ts_if(el, Y, X + 16, dw0, idesc, 1u);
+        mma_bf16_ts_if(el, Y, X, d_lo, idesc, 1u);
+      }, [&] {
+        if (pending) stage_flush(S.stage[g], t, Ce, p_slot0, p_slot0 + p_nrows);
+        pending = false;
       });
       epilogue(Yt, Xt, S.b_re1, 0.f, nullptr, m_re0, slot0 + r, valid);
       // layer 1: A = Y, D = X
-      run([&](uint32_t el) { issue_hidden_ts(el, X, Y, wl0, wl0 + TM_WL_BYTES / 2, 1u); });
+      run([&](uint32_t el) { issue_hidden_ts(el, X, Y, dwl0, 1u); }, nothing);
       epilogue(Xt, Yt, S.b_re2, 0.f, nullptr, m_re1, slot0 + r, valid);
       // layer 2: A = X, D = Y; then pre-load the hoisted constant w_d d + b of the propagator into X
-      run([&](uint32_t el) { issue_hidden_ts(el, Y, X, wl1, wl1 + TM_WL_BYTES / 2, 1u); });
+      run([&](uint32_t el) { issue_hidden_ts(el, Y, X, dwl1, 1u); }, nothing);
       epilogue(Yt, Xt, S.b_rp, d, S.wd_rp, m_re2, slot0 + r, valid);
       // layer E: A = Y, D = X -> C_e rows
-      run([&](uint32_t el) { issue_hidden_ts(el, X, Y, wl2, wl2 + TM_WL_BYTES / 2, 1u); });
+      run([&](uint32_t el) { issue_hidden_ts(el, X, Y, dwl2, 1u); }, nothing);
       {
         float v[2][16];
         tc::tmem_ld16(Xt + half * 32, v[0]);
         tc::tmem_ld16(Xt + half * 32 + 16, v[1]);
         tc::tmem_ld_wait();
-        // one row per thread -> whole 128-byte lines per store request, through the group's staging tile.  The
-        // next write to it is a full tile chain (several group barriers) away, so no trailing barrier is needed.
+        // one row per thread -> whole 128-byte lines per store request, through the group's staging tile; the
+        // tile is flushed after the group barrier of the NEXT tile's first layer (or after the loop)
         stage_put16(S.stage[g], r, half * 32, v[0]);
         stage_put16(S.stage[g], r, half * 32 + 16, v[1]);
-        group_barrier(g);
-        stage_flush(S.stage[g], t, Ce, slot0, slot0 + nrows);
+        pending = true;
+        p_slot0 = slot0;
+        p_nrows = nrows;
       }
     }
     PILE_TRACE(6);
     cur = nxt;
     tile += stride;
+  }
+  if (pending) {             // group-uniform
+    group_barrier(g);
+    stage_flush(S.stage[g], t, Ce, p_slot0, p_slot0 + p_nrows);
   }
   tc::fence_before_sync();
   __syncthreads();

@@ -32,6 +32,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
+// descriptor of the same matrix `bytes` further on (start-address field only; smem addresses fit its 14 bits)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) {
+  return (d & 0xffffffff00000000ull) | (uint32_t)((uint32_t)d + (bytes >> 4));
+}
+
 // ---- instruction descriptor (32 bit) for kind::f16, bf16 x bf16 -> fp32, both operands K-major -------
 // [4,6) c_format = 1 (F32) | [7,10) a_format = 1 (BF16) | [10,13) b_format = 1 | [17,23) N >> 3 | [24,29) M >> 4
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
@@ -168,6 +173,16 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ReLU fused into the split: hi = bf16_rz(max(x, 0)), lo = bf16_rn(max(x - trunc16(x), 0)).  With a TRUNCATED hi
+// part the residual has the sign of x, so the .relu of both conversions implements the ReLU and no separate max
+// is needed (6 instructions per pair instead of 8); hi + lo still carries 16 significant bits.
+__device__ __forceinline__ void split2_relu(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const float ra = a - __uint_as_float(__float_as_uint(a) & 0xffff0000u);
+  const float rb = b - __uint_as_float(__float_as_uint(b) & 0xffff0000u);
+  asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 
 }  // namespace tc

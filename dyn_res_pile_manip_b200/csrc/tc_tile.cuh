@@ -209,7 +209,7 @@ __device__ __forceinline__ void run_gemm(GroupCtx& c, Issue issue) {
   tc::fence_async_smem();          // st.shared of the A tile -> visible to the tensor core
   tc::fence_before_sync();         // this thread's tcgen05.ld of the previous accumulator are complete
   group_barrier(c.g);
-  if (c.wig == 0) {
+  if (c.wig == c.g) {      // issuer warp g*8+g: the four groups issue from four different SM sub-partitions
     tc::fence_after_sync();
     const uint32_t elected = tc::elect_one();
     issue(elected);
