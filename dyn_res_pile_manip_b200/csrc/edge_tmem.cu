@@ -257,7 +257,7 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
         mma_bf16_ts_if(el, Y, X + 16, dw0, idesc, 1u);
         mma_bf16_ts_if(el, Y, X, d_lo, idesc, 1u);
       }, [&] {
-        if (pending) stage_flush(S.stage[g], t, Ce, p_slot0, p_slot0 + p_nrows);
+        if (pending) stage_flush_packed(S.stage[g], t, reinterpret_cast<uint8_t*>(Ce), p_slot0, p_slot0 + p_nrows);
         pending = false;
       });
       epilogue(Yt, Xt, S.b_re1, 0.f, nullptr, m_re0, slot0 + r, valid);
@@ -289,7 +289,7 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
   }
   if (pending) {             // group-uniform
     group_barrier(g);
-    stage_flush(S.stage[g], t, Ce, p_slot0, p_slot0 + p_nrows);
+    stage_flush_packed(S.stage[g], t, reinterpret_cast<uint8_t*>(Ce), p_slot0, p_slot0 + p_nrows);
   }
   tc::fence_before_sync();
   __syncthreads();

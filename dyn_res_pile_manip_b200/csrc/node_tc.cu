@@ -180,48 +180,99 @@ k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr
 // ------------------------------------------------------------------------------------------------
 // receiver-segmented sum of the relation effects (memory-bound; no weights, high occupancy)
 // ------------------------------------------------------------------------------------------------
-template <bool RECORD>
+template <bool RECORD, bool PACKED>
 __global__ void __launch_bounds__(256)
 k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ Ce,
            const float* __restrict__ Pr, const float* __restrict__ Ps, uint8_t* __restrict__ m_edge,
            float* __restrict__ agg, int B, int N) {
-  const int l16 = threadIdx.x & 15;
-  const unsigned hmask = 0xffffu << (threadIdx.x & 16);
+  // A half-warp owns one receiver at a time; lane l16 owns channels 4*l16 .. 4*l16+3.  The kernel is bound by
+  // the memory latency of the chain rowptr -> col -> (C_e row, P_s row), so the first two levels are prefetched:
+  // rowptr two receivers ahead, col (one sender index per lane) and P_r one receiver ahead.
+  // All loop bounds are made warp-uniform so that the two half-warps stay converged and the shuffles can use the
+  // full mask (half-warp masks make the compiler split the warp, which doubles the issued instructions).
+  const int l16 = threadIdx.x & 15, hbase = threadIdx.x & 16;
+  constexpr unsigned FULL = 0xffffffffu;
   const int R = B * N;                                   // 32-bit: 64-bit div/mod is emulated
   const int nhw = (int)gridDim.x * (int)(blockDim.x >> 4);
-  const int kc = l16 >> 1, sub = (l16 & 1) * 4;          // this lane's 4 channels inside chunk kc
-  for (int node = (int)blockIdx.x * (int)(blockDim.x >> 4) + (int)(threadIdx.x >> 4); node < R; node += nhw) {
-    const int b = node / N, i = node - b * N;
-    const int* rp = rowptr + (long long)b * (N + 1) + i;
-    const int e_lo = rp[0], cnt = rp[1] - e_lo;
-    const long long slot = (long long)b * KMAX * N + e_lo;
-    const float4 pr = ld4(Pr + tb_row(node, kc) + sub);
+  struct Seg { int b, e_lo, cnt; };
+  auto load_seg = [&](int nd) {
+    Seg s;
+    s.b = 0; s.e_lo = 0; s.cnt = 0;
+    if (nd < R) {
+      s.b = nd / N;
+      const int* rp = rowptr + (long long)s.b * (N + 1) + (nd - s.b * N);
+      s.e_lo = __ldg(rp);
+      s.cnt = __ldg(rp + 1) - s.e_lo;
+    }
+    return s;
+  };
+  const long long e_last = (long long)B * KMAX * N - 1;
+  int node = (int)blockIdx.x * (int)(blockDim.x >> 4) + (int)(threadIdx.x >> 4);
+  Seg cur = load_seg(node), nxt = load_seg(node + nhw);
+  int mycol = 0;
+  float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (node < R) {
+    if (l16 < cur.cnt) mycol = __ldg(col + (long long)cur.b * KMAX * N + cur.e_lo + l16);
+    pr = ld4(Pr + (long long)node * H + 4 * l16);
+  }
+  while (__any_sync(FULL, node < R)) {
+    // prefetch for the next two receivers of this half-warp
+    const int n1 = node + nhw;
+    int mycol1 = 0;
+    float4 pr1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n1 < R) {
+      if (l16 < nxt.cnt) mycol1 = __ldg(col + (long long)nxt.b * KMAX * N + nxt.e_lo + l16);
+      pr1 = ld4(Pr + (long long)n1 * H + 4 * l16);
+    }
+    const Seg nn = load_seg(n1 + nhw);
+
+    const int cnt = cur.cnt;
+    const long long slot = (long long)cur.b * KMAX * N + cur.e_lo;
+    const float* ps_base = Ps + (long long)cur.b * N * H + 4 * l16;
+    const int cntw = max(cnt, __shfl_xor_sync(FULL, cnt, 16));
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k0 = 0; k0 < cnt; k0 += 5) {
+    for (int k0 = 0; k0 < cntw; k0 += 5) {
       float4 ce[5], ps[5];
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        if (k0 + k < cnt) {
-          const int s = col[slot + k0 + k];
-          ce[k] = ld4(Ce + (slot + k0 + k) * H + 4 * l16);
-          ps[k] = ld4(Ps + tb_row((long long)b * N + s, kc) + sub);
+        // unconditional loads (rows past the segment are clamped into the buffer and ignored below): predicated
+        // loads made the compiler copy each result right after its load, which serialised the whole batch
+        const int s = __shfl_sync(FULL, mycol, hbase + k0 + k);
+        const long long e = min(slot + k0 + k, e_last);
+        if (PACKED) {            // raw words now (keeps all loads of the batch in flight), unpacked when consumed
+          const uint8_t* row = reinterpret_cast<const uint8_t*>(Ce) + e * CE_PACKED_ROW;
+          const uint2 hi = __ldg(reinterpret_cast<const uint2*>(row + l16 * 8));
+          ce[k].x = __uint_as_float(hi.x);
+          ce[k].y = __uint_as_float(hi.y);
+          ce[k].z = __uint_as_float(__ldg(reinterpret_cast<const uint32_t*>(row + 128 + l16 * 4)));
+        } else {
+          ce[k] = ld4(Ce + e * H + 4 * l16);
         }
+        ps[k] = ld4(ps_base + (long long)s * H);
       }
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        if (k0 + k < cnt) {
-          float4 v = make_float4(ce[k].x + pr.x + ps[k].x, ce[k].y + pr.y + ps[k].y, ce[k].z + pr.z + ps[k].z,
-                                 ce[k].w + pr.w + ps[k].w);
-          if (RECORD) {
-            const unsigned m4 = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
-            const unsigned hi = __shfl_down_sync(hmask, m4, 1);
-            if ((l16 & 1) == 0) m_edge[(slot + k0 + k) * 8 + (l16 >> 1)] = (uint8_t)(m4 | (hi << 4));
-          }
+        const bool act = k0 + k < cnt;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) {
+          if (PACKED) ce[k] = unpack24(make_uint2(__float_as_uint(ce[k].x), __float_as_uint(ce[k].y)), __float_as_uint(ce[k].z));
+          v = make_float4(ce[k].x + pr.x + ps[k].x, ce[k].y + pr.y + ps[k].y, ce[k].z + pr.z + ps[k].z,
+                          ce[k].w + pr.w + ps[k].w);
           sum.x += fmaxf(v.x, 0.f); sum.y += fmaxf(v.y, 0.f); sum.z += fmaxf(v.z, 0.f); sum.w += fmaxf(v.w, 0.f);
+        }
+        if (RECORD) {          // sign bits of 8 channels per byte: even lanes collect their right neighbour's nibble
+          const unsigned m4 = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
+          const unsigned hi = __shfl_down_sync(FULL, m4, 1);
+          if (act && (l16 & 1) == 0) m_edge[(slot + k0 + k) * 8 + (l16 >> 1)] = (uint8_t)(m4 | (hi << 4));
         }
       }
     }
-    st4(agg + tb_row(node, kc) + sub, sum);
+    if (node < R) st4(agg + (long long)node * H + 4 * l16, sum);
+    node = n1;
+    cur = nxt;
+    nxt = nn;
+    mycol = mycol1;
+    pr = pr1;
   }
 }
 
@@ -394,10 +445,12 @@ int launch_propagate_tc(const float* wpack, const Csr& csr, const StepScratch& w
   const long long R = (long long)B * N;
   const long long ntiles = (R + TILE - 1) / TILE;
   const int agg_blocks = (int)((R + 15) / 16 < 8 * NSM ? (R + 15) / 16 : 8 * NSM);
-  if (mk)
-    k_edge_agg<true><<<agg_blocks, 256, 0, st>>>(csr.rowptr, csr.col, ws.Ce, ws.Pr[in], ws.Ps[in], mk->edge[p], ws.agg, B, N);
-  else
-    k_edge_agg<false><<<agg_blocks, 256, 0, st>>>(csr.rowptr, csr.col, ws.Ce, ws.Pr[in], ws.Ps[in], nullptr, ws.agg, B, N);
+  // tensor engine 2 (edge_tmem.cu) writes packed C_e rows, engine 1 (edge_tc.cu) plain fp32 rows
+  const bool packed = g_use_tensor_cores == 2;
+  uint8_t* me = mk ? mk->edge[p] : nullptr;
+  auto agg_kernel = mk ? (packed ? k_edge_agg<true, true> : k_edge_agg<true, false>)
+                       : (packed ? k_edge_agg<false, true> : k_edge_agg<false, false>);
+  agg_kernel<<<agg_blocks, 256, 0, st>>>(csr.rowptr, csr.col, ws.Ce, ws.Pr[in], ws.Ps[in], me, ws.agg, B, N);
   PILE_CHECK_LAUNCH();
   const int grid = tc_grid(ntiles);
   const size_t sm = sizeof(NodeUpdSmemTc);

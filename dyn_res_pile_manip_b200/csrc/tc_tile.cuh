@@ -172,6 +172,46 @@ __device__ __forceinline__ void stage_flush(const uint8_t* stage, int t, float* 
     if (row0 + row < R) st4(dst + (row0 + row) * H + slot * 4, v);
   }
 }
+// ---- packed C_e rows (tensor engine 2) ------------------------------------------------------------------
+// k_edge_agg re-reads C_e once per propagation step and sits on the HBM roofline, so the tensor engine stores the
+// rows as 24-bit words (fp32 rounded to 15 explicit mantissa bits: relative error <= 2^-16, the same as the bf16
+// hi/lo operands of the products that made them): per row 64 x 16-bit upper halves (128 bytes) followed by
+// 64 x 8-bit third bytes (64 bytes) = 192 bytes instead of 256.
+constexpr int CE_PACKED_ROW = 192;
+__device__ __forceinline__ void pack24(const float4& v, uint2& hi, uint32_t& lo) {
+  const uint32_t a = __float_as_uint(v.x) + 0x80u, b = __float_as_uint(v.y) + 0x80u;
+  const uint32_t c = __float_as_uint(v.z) + 0x80u, d = __float_as_uint(v.w) + 0x80u;
+  hi.x = __byte_perm(a, b, 0x7632);                                         // [a.2 a.3 b.2 b.3]
+  hi.y = __byte_perm(c, d, 0x7632);
+  lo = __byte_perm(__byte_perm(a, b, 0x0051), __byte_perm(c, d, 0x0051), 0x5410);   // [a.1 b.1 c.1 d.1]
+}
+__device__ __forceinline__ float4 unpack24(const uint2& hi, uint32_t lo) {
+  float4 v;
+  v.x = __uint_as_float(__byte_perm(hi.x, lo, 0x1044) & 0xffffff00u);       // [junk lo.0 hi.0 hi.1] & mask
+  v.y = __uint_as_float(__byte_perm(hi.x, lo, 0x3254) & 0xffffff00u);
+  v.z = __uint_as_float(__byte_perm(hi.y, lo, 0x1064) & 0xffffff00u);
+  v.w = __uint_as_float(__byte_perm(hi.y, lo, 0x3274) & 0xffffff00u);
+  return v;
+}
+// all 256 threads of the group: staging tile -> packed rows [row0, row_end) (row_end - row0 <= 128)
+__device__ __forceinline__ void stage_flush_packed(const uint8_t* stage, int t, uint8_t* __restrict__ dst, long long row0,
+                                                   long long row_end) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int idx = it * GROUP_THREADS + t;
+    const int row = idx >> 4, slot = idx & 15;
+    const float4 v = *reinterpret_cast<const float4*>(stage + stage_off(row, slot));
+    uint2 hi;
+    uint32_t lo;
+    pack24(v, hi, lo);
+    if (row0 + row < row_end) {
+      uint8_t* p = dst + (row0 + row) * CE_PACKED_ROW;
+      *reinterpret_cast<uint2*>(p + slot * 8) = hi;
+      *reinterpret_cast<uint32_t*>(p + 128 + slot * 4) = lo;
+    }
+  }
+}
+
 // all 256 threads of the group: rows [row0, row0+128) of a row-major [R][64] array -> hi/lo A tile (rows past R
 // are zero-filled).  A warp instruction covers 8 rows x 128 bytes (whole lines) and 8 consecutive rows of one
 // chunk per quarter-warp on the shared-memory side (conflict-free).
