@@ -180,16 +180,31 @@ k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr
 // ------------------------------------------------------------------------------------------------
 // receiver-segmented sum of the relation effects (memory-bound; no weights, high occupancy)
 // ------------------------------------------------------------------------------------------------
+constexpr int AGG_THREADS = 256;
+template <bool PACKED>
+__host__ __device__ constexpr int agg_edge_bytes() { return (PACKED ? CE_PACKED_ROW : H * 4) + H * 4; }      // C_e row + P_s row
+template <bool PACKED>
+__host__ __device__ constexpr int agg_smem_bytes() { return (AGG_THREADS / 16) * KMAX * agg_edge_bytes<PACKED>(); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
 template <bool RECORD, bool PACKED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(AGG_THREADS)
 k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ Ce,
            const float* __restrict__ Pr, const float* __restrict__ Ps, uint8_t* __restrict__ m_edge,
            float* __restrict__ agg, int B, int N) {
-  // A half-warp owns one receiver at a time; lane l16 owns channels 4*l16 .. 4*l16+3.  The kernel is bound by
-  // the memory latency of the chain rowptr -> col -> (C_e row, P_s row), so the first two levels are prefetched:
-  // rowptr two receivers ahead, col (one sender index per lane) and P_r one receiver ahead.
-  // All loop bounds are made warp-uniform so that the two half-warps stay converged and the shuffles can use the
-  // full mask (half-warp masks make the compiler split the warp, which doubles the issued instructions).
+  // A half-warp owns one receiver at a time; lane l16 owns channels 4*l16 .. 4*l16+3.  The kernel streams C_e once
+  // and gathers one P_s row per relation; what bounds it is how many of those row reads an SM keeps in flight.
+  // So the rows do not pass through registers: every half-warp cp.async's ALL rows of its receiver (up to 10 C_e
+  // rows and 10 P_s rows) into its own shared-memory slab and only then sums them; the first two levels of the
+  // dependent chain rowptr -> col -> rows are prefetched (rowptr two receivers ahead, col and P_r one ahead).
+  // All loop bounds are warp-uniform so that the two half-warps stay converged and shuffles use the full mask.
+  extern __shared__ __align__(16) unsigned char agg_smem[];
+  constexpr int CE_ROW = PACKED ? CE_PACKED_ROW : H * 4;
+  constexpr int EDGE_BYTES = agg_edge_bytes<PACKED>();
+  unsigned char* slab = agg_smem + (threadIdx.x >> 4) * (KMAX * EDGE_BYTES);
   const int l16 = threadIdx.x & 15, hbase = threadIdx.x & 16;
   constexpr unsigned FULL = 0xffffffffu;
   const int R = B * N;                                   // 32-bit: 64-bit div/mod is emulated
@@ -206,7 +221,6 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
     }
     return s;
   };
-  const long long e_last = (long long)B * KMAX * N - 1;
   int node = (int)blockIdx.x * (int)(blockDim.x >> 4) + (int)(threadIdx.x >> 4);
   Seg cur = load_seg(node), nxt = load_seg(node + nhw);
   int mycol = 0;
@@ -216,7 +230,23 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
     pr = ld4(Pr + (long long)node * H + 4 * l16);
   }
   while (__any_sync(FULL, node < R)) {
-    // prefetch for the next two receivers of this half-warp
+    const int cnt = cur.cnt;
+    const long long slot = (long long)cur.b * KMAX * N + cur.e_lo;
+    const int cntw = max(cnt, __shfl_xor_sync(FULL, cnt, 16));
+    // all row copies of this receiver
+    {
+      const unsigned char* ce_rows = reinterpret_cast<const unsigned char*>(Ce) + slot * CE_ROW + l16 * 16;
+      const float* ps_base = Ps + (long long)cur.b * N * H + 4 * l16;
+      for (int k = 0; k < cntw; ++k) {
+        const int s = __shfl_sync(FULL, mycol, hbase + k);
+        if (k < cnt) {
+          if (l16 * 16 < CE_ROW) cp_async16(slab + k * EDGE_BYTES + l16 * 16, ce_rows + (long long)k * CE_ROW);
+          cp_async16(slab + k * EDGE_BYTES + CE_ROW + l16 * 16, ps_base + (long long)s * H);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // prefetch for the next two receivers of this half-warp while the rows are on their way
     const int n1 = node + nhw;
     int mycol1 = 0;
     float4 pr1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -225,49 +255,32 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
       pr1 = ld4(Pr + (long long)n1 * H + 4 * l16);
     }
     const Seg nn = load_seg(n1 + nhw);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
 
-    const int cnt = cur.cnt;
-    const long long slot = (long long)cur.b * KMAX * N + cur.e_lo;
-    const float* ps_base = Ps + (long long)cur.b * N * H + 4 * l16;
-    const int cntw = max(cnt, __shfl_xor_sync(FULL, cnt, 16));
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k0 = 0; k0 < cntw; k0 += 5) {
-      float4 ce[5], ps[5];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        // unconditional loads (rows past the segment are clamped into the buffer and ignored below): predicated
-        // loads made the compiler copy each result right after its load, which serialised the whole batch
-        const int s = __shfl_sync(FULL, mycol, hbase + k0 + k);
-        const long long e = min(slot + k0 + k, e_last);
-        if (PACKED) {            // raw words now (keeps all loads of the batch in flight), unpacked when consumed
-          const uint8_t* row = reinterpret_cast<const uint8_t*>(Ce) + e * CE_PACKED_ROW;
-          const uint2 hi = __ldg(reinterpret_cast<const uint2*>(row + l16 * 8));
-          ce[k].x = __uint_as_float(hi.x);
-          ce[k].y = __uint_as_float(hi.y);
-          ce[k].z = __uint_as_float(__ldg(reinterpret_cast<const uint32_t*>(row + 128 + l16 * 4)));
-        } else {
-          ce[k] = ld4(Ce + e * H + 4 * l16);
-        }
-        ps[k] = ld4(ps_base + (long long)s * H);
+    for (int k = 0; k < cntw; ++k) {
+      const bool act = k < cnt;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (act) {
+        const unsigned char* e = slab + k * EDGE_BYTES;
+        float4 ce;
+        if (PACKED)
+          ce = unpack24(*reinterpret_cast<const uint2*>(e + l16 * 8), *reinterpret_cast<const uint32_t*>(e + 128 + l16 * 4));
+        else
+          ce = *reinterpret_cast<const float4*>(e + l16 * 16);
+        const float4 ps = *reinterpret_cast<const float4*>(e + CE_ROW + l16 * 16);
+        v = make_float4(ce.x + pr.x + ps.x, ce.y + pr.y + ps.y, ce.z + pr.z + ps.z, ce.w + pr.w + ps.w);
+        sum.x += fmaxf(v.x, 0.f); sum.y += fmaxf(v.y, 0.f); sum.z += fmaxf(v.z, 0.f); sum.w += fmaxf(v.w, 0.f);
       }
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const bool act = k0 + k < cnt;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (act) {
-          if (PACKED) ce[k] = unpack24(make_uint2(__float_as_uint(ce[k].x), __float_as_uint(ce[k].y)), __float_as_uint(ce[k].z));
-          v = make_float4(ce[k].x + pr.x + ps[k].x, ce[k].y + pr.y + ps[k].y, ce[k].z + pr.z + ps[k].z,
-                          ce[k].w + pr.w + ps[k].w);
-          sum.x += fmaxf(v.x, 0.f); sum.y += fmaxf(v.y, 0.f); sum.z += fmaxf(v.z, 0.f); sum.w += fmaxf(v.w, 0.f);
-        }
-        if (RECORD) {          // sign bits of 8 channels per byte: even lanes collect their right neighbour's nibble
-          const unsigned m4 = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
-          const unsigned hi = __shfl_down_sync(FULL, m4, 1);
-          if (act && (l16 & 1) == 0) m_edge[(slot + k0 + k) * 8 + (l16 >> 1)] = (uint8_t)(m4 | (hi << 4));
-        }
+      if (RECORD) {          // sign bits of 8 channels per byte: even lanes collect their right neighbour's nibble
+        const unsigned m4 = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
+        const unsigned hi = __shfl_down_sync(FULL, m4, 1);
+        if (act && (l16 & 1) == 0) m_edge[(slot + k) * 8 + (l16 >> 1)] = (uint8_t)(m4 | (hi << 4));
       }
     }
     if (node < R) st4(agg + (long long)node * H + 4 * l16, sum);
+    __syncwarp();          // the slab is rewritten by the next receiver's copies
     node = n1;
     cur = nxt;
     nxt = nn;
@@ -425,6 +438,10 @@ int launch_node_encode_tc(const float* wpack, const float* attr, const float* de
     if ((e = set_smem_tc(k_node_update_tc<false, true>, sizeof(NodeUpdSmemTc)))) return e;
     if ((e = set_smem_tc(k_node_update_tc<true, false>, sizeof(NodeUpdSmemTc)))) return e;
     if ((e = set_smem_tc(k_node_update_tc<true, true>, sizeof(NodeUpdSmemTc)))) return e;
+    if ((e = set_smem_tc(k_edge_agg<false, false>, agg_smem_bytes<false>()))) return e;
+    if ((e = set_smem_tc(k_edge_agg<true, false>, agg_smem_bytes<false>()))) return e;
+    if ((e = set_smem_tc(k_edge_agg<false, true>, agg_smem_bytes<true>()))) return e;
+    if ((e = set_smem_tc(k_edge_agg<true, true>, agg_smem_bytes<true>()))) return e;
     configured = true;
   }
   const long long ntiles = ((long long)B * N + TILE - 1) / TILE;
@@ -450,7 +467,8 @@ int launch_propagate_tc(const float* wpack, const Csr& csr, const StepScratch& w
   uint8_t* me = mk ? mk->edge[p] : nullptr;
   auto agg_kernel = mk ? (packed ? k_edge_agg<true, true> : k_edge_agg<true, false>)
                        : (packed ? k_edge_agg<false, true> : k_edge_agg<false, false>);
-  agg_kernel<<<agg_blocks, 256, 0, st>>>(csr.rowptr, csr.col, ws.Ce, ws.Pr[in], ws.Ps[in], me, ws.agg, B, N);
+  const int agg_smem = packed ? agg_smem_bytes<true>() : agg_smem_bytes<false>();
+  agg_kernel<<<agg_blocks, AGG_THREADS, agg_smem, st>>>(csr.rowptr, csr.col, ws.Ce, ws.Pr[in], ws.Ps[in], me, ws.agg, B, N);
   PILE_CHECK_LAUNCH();
   const int grid = tc_grid(ntiles);
   const size_t sm = sizeof(NodeUpdSmemTc);
