@@ -168,11 +168,12 @@ int pile_predict_step(const float* wpack, const float* attr, const float* dens, 
   Csr csr = sv.csr;
   if (tape) { tv = carve_tape(tape, B, N); csr = tv.csr; }
   PushCam none{};
+  const bool tc = g_use_tensor_cores != 0;      // the tensor engine takes its relation rows from the search kernel
   int e = launch_nbr_search(s_cur, (long long)N * 3, s_delta, nullptr, 0, none, nullptr, particle_nums, B, N,
-                            adj_thresh * adj_thresh, csr, st);
+                            adj_thresh * adj_thresh, csr, st, tc ? attr : nullptr, dens, tc ? sv.ws.efeat : nullptr);
   if (e) return e;
   return launch_forward(wpack, attr, dens, s_cur, (long long)N * 3, s_delta, csr, sv.ws, tape ? &tv.mk : nullptr,
-                        s_pred, (long long)N * 3, B, N, st);
+                        s_pred, (long long)N * 3, B, N, st, nullptr, tc);
 }
 
 int pile_rollout_forward(const float* wpack, const float* attr, const float* dens, const float* s0,
@@ -185,6 +186,7 @@ int pile_rollout_forward(const float* wpack, const float* attr, const float* den
   const PushCam cam = make_cam(cam_m12, global_scale);
   const size_t tape_step = carve_tape(nullptr, B, N).bytes;
   const long long sstride = (long long)T * N * 3;
+  const bool tc = g_use_tensor_cores != 0;      // the tensor engine takes its relation rows from the search kernel
   for (int t = 0; t < T; ++t) {
     const float* s_cur = t == 0 ? s0 : states + (size_t)(t - 1) * N * 3;
     const long long cur_stride = t == 0 ? (long long)N * 3 : sstride;
@@ -192,10 +194,11 @@ int pile_rollout_forward(const float* wpack, const float* attr, const float* den
     Csr csr = sv.csr;
     if (tape) { tv = carve_tape(static_cast<char*>(tape) + (size_t)t * tape_step, B, N); csr = tv.csr; }
     int e = launch_nbr_search(s_cur, cur_stride, nullptr, actions + (size_t)t * 4, T * 4, cam, sv.ws.s_delta,
-                              nullptr, B, N, adj_thresh * adj_thresh, csr, st);
+                              nullptr, B, N, adj_thresh * adj_thresh, csr, st, tc ? attr : nullptr, dens,
+                              tc ? sv.ws.efeat : nullptr);
     if (e) return e;
     e = launch_forward(wpack, attr, dens, s_cur, cur_stride, sv.ws.s_delta, csr, sv.ws, tape ? &tv.mk : nullptr,
-                       states + (size_t)t * N * 3, sstride, B, N, st);
+                       states + (size_t)t * N * 3, sstride, B, N, st, nullptr, tc);
     if (e) return e;
   }
   return 0;
@@ -268,13 +271,14 @@ int pile_profile_step(const float* wpack, const float* attr, const float* dens, 
   for (auto& e : ev) cudaEventCreate(&e);
   for (int k = 0; k < NK; ++k) ms_out[k] = 0.f;
   int rc = 0;
+  const bool tc = g_use_tensor_cores != 0;
   for (int r = 0; r < reps && !rc; ++r) {
     cudaEventRecord(ev[0], st);
     rc = launch_nbr_search(s_cur, (long long)N * 3, nullptr, action, act_stride, cam, sv.ws.s_delta, nullptr, B, N,
-                           adj_thresh * adj_thresh, sv.csr, st);
+                           adj_thresh * adj_thresh, sv.csr, st, tc ? attr : nullptr, dens, tc ? sv.ws.efeat : nullptr);
     if (rc) break;
     rc = launch_forward(wpack, attr, dens, s_cur, (long long)N * 3, sv.ws.s_delta, sv.csr, sv.ws, nullptr, s_out,
-                        (long long)N * 3, B, N, st, ev + 1);
+                        (long long)N * 3, B, N, st, ev + 1, tc);
     if (rc) break;
     cudaEventSynchronize(ev[NK]);
     for (int k = 0; k < NK; ++k) {

@@ -256,7 +256,7 @@ PILE_TRACE_SETTER(set_edge_trace)
 
 int launch_edge_encode_tc(const float* wpack, const float* attr, const float* dens, const float* s_cur,
                           long long s_stride, const Csr& csr, const Masks* mk, float* efeat, float* Ce, int B, int N,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool efeat_ready) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_edge_encode_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -267,9 +267,11 @@ int launch_edge_encode_tc(const float* wpack, const float* attr, const float* de
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const dim3 fgrid((KMAX * N + 255) / 256, B);
-  k_edge_features<<<fgrid, 256, 0, st>>>(attr, dens, s_cur, s_stride, csr.rowptr, csr.col, csr.row, efeat, B, N);
-  PILE_CHECK_LAUNCH();
+  if (!efeat_ready) {          // relations that did not come from launch_nbr_search (which writes the rows itself)
+    const dim3 fgrid((KMAX * N + 255) / 256, B);
+    k_edge_features<<<fgrid, 256, 0, st>>>(attr, dens, s_cur, s_stride, csr.rowptr, csr.col, csr.row, efeat, B, N);
+    PILE_CHECK_LAUNCH();
+  }
   if (g_use_tensor_cores == 2) return launch_edge_encode_tmem(wpack, efeat, csr, mk, Ce, B, N, st);
   const long long ntiles = (long long)B * ((KMAX * N + TILE - 1) / TILE);
   const long long want = (ntiles + TC_GROUPS - 1) / TC_GROUPS;

@@ -371,7 +371,7 @@ static int set_smem(Kern k, size_t bytes) {
 int launch_forward(const float* wpack, const float* attr, const float* dens, const float* s_cur,
                    long long s_cur_stride, const float* s_delta, const Csr& csr, const StepScratch& ws,
                    const Masks* mk, float* s_out, long long s_out_stride, int B, int N, cudaStream_t st,
-                   cudaEvent_t* ev) {
+                   cudaEvent_t* ev, bool efeat_ready) {
   static bool configured = false;
   if (!configured) {
     int e;
@@ -395,7 +395,7 @@ int launch_forward(const float* wpack, const float* attr, const float* dens, con
     if (ev) cudaEventRecord(ev[0], st);
     if ((e = launch_node_encode_tc(wpack, attr, dens, s_delta, mk, ws, B, N, st))) return e;
     if (ev) cudaEventRecord(ev[1], st);
-    if ((e = launch_edge_encode_tc(wpack, attr, dens, s_cur, s_cur_stride, csr, mk, ws.efeat, ws.Ce, B, N, st))) return e;
+    if ((e = launch_edge_encode_tc(wpack, attr, dens, s_cur, s_cur_stride, csr, mk, ws.efeat, ws.Ce, B, N, st, efeat_ready))) return e;
     for (int p = 0; p < PSTEP; ++p) {
       if (ev) cudaEventRecord(ev[2 + p], st);
       if ((e = launch_propagate_tc(wpack, csr, ws, mk, p, s_cur, s_cur_stride, s_out, s_out_stride, B, N, st))) return e;

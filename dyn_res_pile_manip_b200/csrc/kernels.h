@@ -47,21 +47,24 @@ size_t nbr_smem_bytes(int N);
 // s_delta either given (s_delta_in) or computed from `action` and written to s_delta_out
 int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_delta_in, const float* action,
                       int act_stride, const PushCam& cam, float* s_delta_out, const int* particle_nums, int B,
-                      int N, float thr, const Csr& csr, cudaStream_t st);
+                      int N, float thr, const Csr& csr, cudaStream_t st,
+                      // optional (tensor engine): also write the relation encoder's input rows to efeat
+                      const float* attr = nullptr, const float* dens = nullptr, float* efeat = nullptr);
 
 // forward of the propagation network on a prepared CSR; s_cur / s_out are [B, N, 3] with a per-sample
 // stride in floats (so slices of [B, T, N, 3] work in place)
 int launch_forward(const float* wpack, const float* attr, const float* dens, const float* s_cur,
                    long long s_cur_stride, const float* s_delta, const Csr& csr, const StepScratch& ws,
                    const Masks* masks, float* s_out, long long s_out_stride, int B, int N, cudaStream_t st,
-                   cudaEvent_t* ev = nullptr);   // ev: 6 events recorded before each kernel and after the last
+                   cudaEvent_t* ev = nullptr,    // ev: 6 events recorded before each kernel and after the last
+                   bool efeat_ready = false);    // ws.efeat already written by launch_nbr_search
 
 // process-wide switch: 0 = FP32 CUDA-core tiles, 1 = tcgen05 tiles with shared-memory activations,
 // 2 = 1 + relation encoder with the activation operand in tensor memory
 extern int g_use_tensor_cores;
 int launch_edge_encode_tc(const float* wpack, const float* attr, const float* dens, const float* s_cur,
                           long long s_stride, const Csr& csr, const Masks* mk, float* efeat, float* Ce, int B, int N,
-                          cudaStream_t st);
+                          cudaStream_t st, bool efeat_ready = false);
 
 int launch_edge_encode_tmem(const float* wpack, const float* efeat, const Csr& csr, const Masks* mk, float* Ce,
                             int B, int N, cudaStream_t st);

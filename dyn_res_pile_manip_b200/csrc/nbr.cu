@@ -130,7 +130,8 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
              const float* __restrict__ action, int act_stride, PushCam cam, float* __restrict__ s_delta_out,
              const int* __restrict__ particle_nums, int N, float thr,
              int* __restrict__ rowptr, int* __restrict__ col, int* __restrict__ row,
-             int* __restrict__ trowptr, int* __restrict__ trecv, int* __restrict__ tedge) {
+             int* __restrict__ trowptr, int* __restrict__ trecv, int* __restrict__ tedge,
+             const float* __restrict__ attr, const float* __restrict__ dens, float* __restrict__ efeat) {
   extern __shared__ __align__(16) float smem[];
   float4* pos = reinterpret_cast<float4*>(smem);      // pushed positions (x, y, z, 0): one 16-byte load per pair
   float* cutd = smem + 4 * N;
@@ -243,11 +244,23 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
   int* rp = rowptr + (size_t)b * (N + 1);
   for (int i = threadIdx.x; i <= N; i += blockDim.x) rp[i] = roff[i];
   const size_t ebase = (size_t)b * KMAX * N;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const int o = roff[i], n = deg[i];
-    for (int s = 0; s < n; ++s) {
-      col[ebase + o + s] = sel[i * KMAX + s];
-      row[ebase + o + s] = i;
+  // one (receiver, slot) pair per thread: consecutive threads write consecutive relations
+  const float dn = efeat != nullptr ? dens[b] / 5000.f : 0.f;
+  for (int idx = threadIdx.x; idx < N * KMAX; idx += blockDim.x) {
+    const int i = idx / KMAX, s = idx - i * KMAX;
+    if (s >= deg[i]) continue;
+    const int c = sel[idx];
+    const size_t e = ebase + roff[i] + s;
+    col[e] = c;
+    row[e] = i;
+    // optional: the relation encoder's input rows (attr_r, attr_s, s_cur_r - s_cur_s, density; gnn_dyn.py:164-172)
+    // for the tensor engine, the same values k_edge_features (edge_tc.cu) writes
+    if (efeat != nullptr) {
+      const float* pr = s_cur + (long long)b * s_stride + i * 3;
+      const float* ps = s_cur + (long long)b * s_stride + c * 3;
+      float* out = efeat + e * 8;
+      *reinterpret_cast<float4*>(out) = make_float4(attr[base + i], attr[base + c], pr[0] - ps[0], pr[1] - ps[1]);
+      *reinterpret_cast<float4*>(out + 4) = make_float4(pr[2] - ps[2], dn, 0.f, 0.f);
     }
   }
 
@@ -448,7 +461,8 @@ size_t nbr_smem_bytes(int N) { return sizeof(float) * (size_t)(4 * N + N) + size
 
 int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_delta_in, const float* action,
                       int act_stride, const PushCam& cam, float* s_delta_out, const int* particle_nums, int B,
-                      int N, float thr, const Csr& csr, cudaStream_t st) {
+                      int N, float thr, const Csr& csr, cudaStream_t st, const float* attr, const float* dens,
+                      float* efeat) {
   const size_t smem = nbr_smem_bytes(N);
   if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
   static bool attr_set = false;
@@ -461,7 +475,7 @@ int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_del
   threads = threads < 64 ? 64 : (threads > NBR_THREADS ? NBR_THREADS : threads);
   k_nbr_search<<<B, threads, smem, st>>>(s_cur, s_stride, s_delta_in, action, act_stride, cam, s_delta_out,
                                              particle_nums, N, thr, csr.rowptr, csr.col, csr.row, csr.trowptr,
-                                             csr.trecv, csr.tedge);
+                                             csr.trecv, csr.tedge, attr, dens, efeat);
   PILE_CHECK_LAUNCH();
   return 0;
 }
