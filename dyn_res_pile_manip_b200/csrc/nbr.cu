@@ -181,6 +181,8 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
     const int ic = active ? i : 0;
     const float4 pi = pos[ic];
     const float xi = pi.x, yi = pi.y, zi = pi.z;
+    // admission bound min(radius^2, current 10th best); -1 keeps lanes without a receiver out (d >= 0)
+    float lim = active ? thr : -1.f;
     // pop the oldest parked candidate (if any) and insert it keeping (d, index) ascending; candidates of a
     // lane are inserted in ascending j, so equal distances keep the lower index first
     auto drain_one = [&]() {
@@ -198,13 +200,14 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
           bd[s] = nd; id[s] = ni;
         }
         if (d < bd[0]) { bd[0] = d; id[0] = j; }
+        lim = fminf(thr, bd[KMAX - 1]);
       }
     };
 #pragma unroll 2
     for (int j = 0; j < N; ++j) {
       const float4 pj = pos[j];
       const float d = sqdist_rn(xi, yi, zi, pj.x, pj.y, pj.z);
-      if (active && d < thr && d < bd[KMAX - 1]) {
+      if (d < lim) {
         if (qn == 0) { qd0 = d; qj0 = j; } else if (qn == 1) { qd1 = d; qj1 = j; } else { qd2 = d; qj2 = j; }
         ++qn;
       }
