@@ -16,8 +16,9 @@ class RolloutEngine:
     """rows = n_sample * n_batch rollouts of horizon T over N particles on one GPU."""
 
     # kernels per model step: FP32 engine nbr_search, node_encode, edge_encode, 3 x propagate; tensor engine
-    # nbr_search, node_encode_tc, edge_features, edge_encode_tc, 3 x (edge_agg + node_update_tc)
-    LAUNCHES_PER_MODEL_STEP = {0: 6, 1: 10, 2: 10}
+    # nbr_search (also writes the relation-encoder input rows), node_encode_tc, edge_encode, 3 x (edge_agg +
+    # node_update_tc)
+    LAUNCHES_PER_MODEL_STEP = {0: 6, 1: 9, 2: 9}
 
     def __init__(self, model_dy, planner, rows, N, T, device=None, goal=None, goal_coor=None, use_graph=True,
                  reward_weight=None):
