@@ -186,29 +186,35 @@ __host__ __device__ constexpr int agg_edge_bytes() { return (PACKED ? CE_PACKED_
 template <bool PACKED>
 __host__ __device__ constexpr int agg_smem_bytes() { return (AGG_THREADS / 16) * KMAX * agg_edge_bytes<PACKED>(); }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-
 template <bool RECORD, bool PACKED>
 __global__ void __launch_bounds__(AGG_THREADS)
 k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ Ce,
            const float* __restrict__ Pr, const float* __restrict__ Ps, uint8_t* __restrict__ m_edge,
            float* __restrict__ agg, int B, int N) {
   // A half-warp owns one receiver at a time; lane l16 owns channels 4*l16 .. 4*l16+3.  The kernel streams C_e once
-  // and gathers one P_s row per relation; what bounds it is how many of those row reads an SM keeps in flight.
-  // So the rows do not pass through registers: every half-warp cp.async's ALL rows of its receiver (up to 10 C_e
-  // rows and 10 P_s rows) into its own shared-memory slab and only then sums them; the first two levels of the
+  // and gathers one P_s row per relation; what bounds it is how many of those row reads an SM keeps in flight and
+  // how many instructions it spends to issue them.  So the rows do not pass through registers: per receiver ONE
+  // bulk copy (TMA, cp.async.bulk) brings its contiguous C_e rows and one bulk copy per relation (issued by the
+  // lane that holds that relation's sender index) its P_s row into the half-warp's shared-memory slab, completion
+  // counted on the half-warp's mbarrier; then the rows are summed from the slab.  The first two levels of the
   // dependent chain rowptr -> col -> rows are prefetched (rowptr two receivers ahead, col and P_r one ahead).
-  // All loop bounds are warp-uniform so that the two half-warps stay converged and shuffles use the full mask.
-  extern __shared__ __align__(16) unsigned char agg_smem[];
+  // All loop bounds are warp-uniform so that the two half-warps stay converged.
+  extern __shared__ __align__(128) unsigned char agg_smem[];
+  __shared__ uint64_t bars[AGG_THREADS / 16];
   constexpr int CE_ROW = PACKED ? CE_PACKED_ROW : H * 4;
   constexpr int EDGE_BYTES = agg_edge_bytes<PACKED>();
-  unsigned char* slab = agg_smem + (threadIdx.x >> 4) * (KMAX * EDGE_BYTES);
-  const int l16 = threadIdx.x & 15, hbase = threadIdx.x & 16;
+  const int hw = threadIdx.x >> 4;
+  unsigned char* slab_ce = agg_smem + hw * (KMAX * EDGE_BYTES);
+  unsigned char* slab_ps = slab_ce + KMAX * CE_ROW;
+  uint64_t* bar = &bars[hw];
+  const int l16 = threadIdx.x & 15;
   constexpr unsigned FULL = 0xffffffffu;
   const int R = B * N;                                   // 32-bit: 64-bit div/mod is emulated
   const int nhw = (int)gridDim.x * (int)(blockDim.x >> 4);
+  if (l16 == 0) tc::mbar_init(bar, 1);
+  tc::mbar_init_fence();
+  __syncthreads();
+  uint32_t phase = 0;
   struct Seg { int b, e_lo, cnt; };
   auto load_seg = [&](int nd) {
     Seg s;
@@ -221,7 +227,7 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
     }
     return s;
   };
-  int node = (int)blockIdx.x * (int)(blockDim.x >> 4) + (int)(threadIdx.x >> 4);
+  int node = (int)blockIdx.x * (int)(blockDim.x >> 4) + hw;
   Seg cur = load_seg(node), nxt = load_seg(node + nhw);
   int mycol = 0;
   float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -233,19 +239,13 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
     const int cnt = cur.cnt;
     const long long slot = (long long)cur.b * KMAX * N + cur.e_lo;
     const int cntw = max(cnt, __shfl_xor_sync(FULL, cnt, 16));
-    // all row copies of this receiver
-    {
-      const unsigned char* ce_rows = reinterpret_cast<const unsigned char*>(Ce) + slot * CE_ROW + l16 * 16;
-      const float* ps_base = Ps + (long long)cur.b * N * H + 4 * l16;
-      for (int k = 0; k < cntw; ++k) {
-        const int s = __shfl_sync(FULL, mycol, hbase + k);
-        if (k < cnt) {
-          if (l16 * 16 < CE_ROW) cp_async16(slab + k * EDGE_BYTES + l16 * 16, ce_rows + (long long)k * CE_ROW);
-          cp_async16(slab + k * EDGE_BYTES + CE_ROW + l16 * 16, ps_base + (long long)s * H);
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+    // all rows of this receiver
+    if (l16 == 0) {
+      tc::mbar_expect_tx(bar, (uint32_t)(cnt * EDGE_BYTES));
+      if (cnt > 0) tc::bulk_g2s(slab_ce, reinterpret_cast<const unsigned char*>(Ce) + slot * CE_ROW, (uint32_t)(cnt * CE_ROW), bar);
     }
+    __syncwarp();
+    if (l16 < cnt) tc::bulk_g2s(slab_ps + l16 * (H * 4), Ps + ((long long)cur.b * N + mycol) * H, H * 4, bar);
     // prefetch for the next two receivers of this half-warp while the rows are on their way
     const int n1 = node + nhw;
     int mycol1 = 0;
@@ -255,21 +255,23 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
       pr1 = ld4(Pr + (long long)n1 * H + 4 * l16);
     }
     const Seg nn = load_seg(n1 + nhw);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
+    tc::mbar_wait(bar, phase);
+    phase ^= 1;
 
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < cntw; ++k) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k >= cntw) break;          // warp-uniform
       const bool act = k < cnt;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (act) {
-        const unsigned char* e = slab + k * EDGE_BYTES;
+        const unsigned char* e = slab_ce + k * CE_ROW;
         float4 ce;
         if (PACKED)
           ce = unpack24(*reinterpret_cast<const uint2*>(e + l16 * 8), *reinterpret_cast<const uint32_t*>(e + 128 + l16 * 4));
         else
           ce = *reinterpret_cast<const float4*>(e + l16 * 16);
-        const float4 ps = *reinterpret_cast<const float4*>(e + CE_ROW + l16 * 16);
+        const float4 ps = *reinterpret_cast<const float4*>(slab_ps + k * (H * 4) + l16 * 16);
         v = make_float4(ce.x + pr.x + ps.x, ce.y + pr.y + ps.y, ce.z + pr.z + ps.z, ce.w + pr.w + ps.w);
         sum.x += fmaxf(v.x, 0.f); sum.y += fmaxf(v.y, 0.f); sum.z += fmaxf(v.z, 0.f); sum.w += fmaxf(v.w, 0.f);
       }
