@@ -284,9 +284,10 @@ def main():
                  "node_encode": R * 2 * (5 * H + 4 * H * H),
                  "propagate0": R * 2 * (3 * H * H) + E * 3 * H, "propagate1": R * 2 * (3 * H * H) + E * 3 * H,
                  "propagate2_predict": R * 2 * (2 * H * H + 3 * H) + E * 3 * H}
-        hbm_bytes = {"nbr_search": R * 24 + 4 * (samples * (N + 1)) + 8 * E,
-                     "edge_encode": E * (8 + H * 4) + R * 16,
-                     "propagate0": E * (H * 4 + 4) + R * H * 4 * 7}
+        ce_row = 192 if lib.pile_get_tensor_cores() == 2 else H * 4     # tensor engine 2 stores C_e as 24-bit words
+        hbm_bytes = {"nbr_search": R * 24 + 4 * (samples * (N + 1)) + 8 * E + 32 * E,
+                     "edge_encode": E * (32 + ce_row),
+                     "propagate0": E * (ce_row + 4) + R * H * 4 * 7}
         dom = max(kms, key=kms.get)
         step_ms = sum(kms.values())
         if dom in ("edge_encode", "node_encode"):
