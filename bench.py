@@ -347,6 +347,31 @@ def main():
                                   "workload": "trajectory_optimization_ptcl_multi_traj: 50 traj x 30 variants x 100 particles, "
                                               "T=1, numpy in -> result dict out (reference budget for this call: 2000 ms)"}
 
+            # the other planner-side piece of an MPC step: RGB-D observation -> 30 particle
+            # re-samplings (env/flex_env.py:933-951), host observation in -> host particles out
+            from dyn_res_pile_manip_b200 import observation as OBS
+            st4, _ = synthetic.make_pile_batch(1, 300, seed=0)
+            obs4 = synthetic.render_observation(st4[0], env)
+            ol = []
+            for i in range(12):
+                t_a = time.perf_counter()
+                OBS.obs2ptcl_fixed_num_batch(obs4, 100, 30, env.get_cam_params(), env.global_scale, seed=i)
+                ol.append((time.perf_counter() - t_a) * 1e3)
+            ol = sorted(ol[2:])
+            plan["obs_to_particles"] = {"p50_ms": ol[len(ol) // 2], "calls": len(ol),
+                                        "workload": "obs2ptcl_fixed_num_batch: 720x720 RGB-D -> 30 x 100 particles "
+                                                    "(depth2fgpcd, 1 cm voxel downsample, FPS, recenter), numpy in -> numpy out"}
+            if not args.no_cpu_baseline:
+                from oracle import obs_oracle as OO
+                t_a = time.perf_counter()
+                depth4 = obs4[..., -1] / env.global_scale
+                for i in range(2):      # the reference repeats all four stages for each of the 30 re-samplings
+                    fg4 = OO.voxel_down_sample(OO.depth2fgpcd(depth4, depth4 < 0.599 / 0.8, env.get_cam_params()), 0.01)
+                    pk4, r4 = OO.fps(fg4, 100, i)
+                    OO.recenter(fg4, pk4, r=min(0.02, 0.5 * r4))
+                plan["obs_to_particles"]["cpu_port_ms"] = (time.perf_counter() - t_a) * 1e3 / 2 * 30
+                plan["obs_to_particles"]["cpu_sample"] = "2 of 30 re-samplings timed (oracle/obs_oracle.py, numpy), scaled to 30"
+
         cpu = None
         torch_cuda = None
         if world == 1 and not args.no_cpu_baseline:

@@ -16,6 +16,7 @@ _P = C.c_void_p
 _I = C.c_int
 _F = C.c_float
 _LL = C.c_longlong
+_D = C.c_double
 
 # name -> (restype, argtypes); mirrors include/pile_gnn.h one to one
 SIGNATURES = {
@@ -47,6 +48,13 @@ SIGNATURES = {
     "pile_reward_backward": (_I, [_P, _LL, _LL, _I, _P, _I, _I, _P, _I, _P, _F, _F, _I, _P, _P, _P, _LL, _I, _P]),
     "pile_adam_clamp": (_I, [_P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _P, _P, _P]),
     "pile_fps": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "pile_fps_sets": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P]),
+    "pile_depth_counts_len": (_I, [_I, _I]),
+    "pile_depth_to_points": (_I, [_P, _I, _I, _P, _F, _P, _I, _P, _P, _P]),
+    "pile_voxel_downsample_bytes": (_LL, [_I]),
+    "pile_voxel_downsample": (_I, [_P, _I, _D, _P, _P, _P, _P]),
+    "pile_cover_radius": (_I, [_P, _I, _P, _I, _I, _P, _P]),
+    "pile_recenter": (_I, [_P, _I, _P, _I, _I, _P, _D, _D, _P, _P]),
     "pile_mppi_num_chunks": (_I, [_I]),
     "pile_mppi_partials": (_I, [_P, _P, _I, _I, _F, _P, _P]),
     "pile_mppi_combine": (_I, [_P, _I, _I, _P, _P]),
@@ -103,3 +111,7 @@ def ptr(t):
 def host_floats(values):
     arr = (C.c_float * len(values))(*[float(v) for v in values])
     return arr
+
+
+def host_doubles(values):
+    return (C.c_double * len(values))(*[float(v) for v in values])

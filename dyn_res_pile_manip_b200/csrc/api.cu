@@ -366,6 +366,42 @@ int pile_fps(const float* pts, int n_sets, int n, int dim, int count, int init_i
                     (cudaStream_t)stream);
 }
 
+int pile_fps_sets(const float* pts, int shared_cloud, int n_sets, int n, int dim, int count, const int* init_idx,
+                  int squared, float* gap_workspace, int* out_idx, float* out_pts, float* out_radius, void* stream) {
+  if (!pts || !gap_workspace || !out_idx || !out_pts) return (int)cudaErrorInvalidValue;
+  return launch_fps_sets(pts, shared_cloud, n_sets, n, dim, count, init_idx, squared, gap_workspace, out_idx, out_pts,
+                         out_radius, (cudaStream_t)stream);
+}
+
+int pile_depth_counts_len(int H, int W) { return (int)(((long long)H * W + 1023) / 1024); }
+
+int pile_depth_to_points(const float* depth, int H, int W, const double* cam4, float max_depth, double* out_pts,
+                         int capacity, int* n_out, int* counts_workspace, void* stream) {
+  if (!depth || !cam4 || !out_pts || !n_out || !counts_workspace) return (int)cudaErrorInvalidValue;
+  return launch_depth_to_points(depth, H, W, cam4, max_depth, out_pts, capacity, n_out, counts_workspace,
+                                (cudaStream_t)stream);
+}
+
+long long pile_voxel_downsample_bytes(int n) { return (long long)voxel_downsample_bytes(n); }
+
+int pile_voxel_downsample(const double* pts, int n, double voxel_size, double* out_pts, int* m_out, void* workspace,
+                          void* stream) {
+  if (!pts || !out_pts || !m_out || !workspace) return (int)cudaErrorInvalidValue;
+  return launch_voxel_downsample(pts, n, voxel_size, out_pts, m_out, workspace, (cudaStream_t)stream);
+}
+
+int pile_cover_radius(const double* cloud, int m, const float* picks, int n_sets, int count, double* radius,
+                      void* stream) {
+  if (!cloud || !picks || !radius) return (int)cudaErrorInvalidValue;
+  return launch_cover_radius(cloud, m, picks, n_sets, count, radius, (cudaStream_t)stream);
+}
+
+int pile_recenter(const double* cloud, int m, const float* picks, int n_sets, int count, const double* radius,
+                  double r_cap, double r_scale, float* out, void* stream) {
+  if (!cloud || !picks || !radius || !out) return (int)cudaErrorInvalidValue;
+  return launch_recenter(cloud, m, picks, n_sets, count, radius, r_cap, r_scale, out, (cudaStream_t)stream);
+}
+
 int pile_adam_clamp(float* actions, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, int step,
                     float lr, float beta1, float beta2, float eps, const float* lo4, const float* hi4, void* stream) {
   if (!actions || !grad || !exp_avg || !exp_avg_sq || n <= 0 || (n & 3) || step <= 0 || !lo4 || !hi4)

@@ -89,6 +89,19 @@ int launch_reward_bwd(const float* states, long long n_states, long long state_s
                       float* g_states, long long g_stride, int accumulate, cudaStream_t st);
 int launch_fps(const float* pts, int n_sets, int n, int dim, int count, int init_idx, float* gap_ws, int* out_idx,
                float* out_pts, float* out_radius, cudaStream_t st);
+int launch_fps_sets(const float* pts, int shared_cloud, int n_sets, int n, int dim, int count, const int* init_idx,
+                    int squared, float* gap_ws, int* out_idx, float* out_pts, float* out_radius, cudaStream_t st);
+
+// observation -> particles (obs.cu)
+int launch_depth_to_points(const float* depth, int H, int W, const double* cam4, float max_depth, double* out_pts,
+                           int cap, int* n_out, int* ws_counts, cudaStream_t st);
+size_t voxel_downsample_bytes(int n);
+int launch_voxel_downsample(const double* pts, int n, double voxel, double* out_pts, int* m_out, void* ws,
+                            cudaStream_t st);
+int launch_cover_radius(const double* pcd, int m, const float* picks, int S, int N, double* radius, cudaStream_t st);
+int launch_recenter(const double* pcd, int m, const float* picks, int S, int N, const double* radius, double r_cap,
+                    double r_scale, float* out, cudaStream_t st);
+
 int launch_adam_clamp(float* p, const float* g, float* m, float* v, long long n, float b1, float b2, float step_size,
                       float bc2_sqrt, float eps, const float* lo4, const float* hi4, cudaStream_t st);
 int mppi_num_chunks(int S);

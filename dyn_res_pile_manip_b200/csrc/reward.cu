@@ -272,17 +272,18 @@ namespace pile {
 constexpr int FPS_THREADS = 1024;
 
 __global__ void __launch_bounds__(FPS_THREADS)
-k_fps(const float* __restrict__ pts, int n, int dim, int count, int init_idx, float* __restrict__ gap_ws,
-      int* __restrict__ out_idx, float* __restrict__ out_pts, float* __restrict__ out_radius) {
+k_fps(const float* __restrict__ pts, long long set_stride, int n, int dim, int count, int init_idx,
+      const int* __restrict__ init_arr, int squared, float* __restrict__ gap_ws, int* __restrict__ out_idx,
+      float* __restrict__ out_pts, float* __restrict__ out_radius) {
   __shared__ float s_val[FPS_THREADS / 32];
   __shared__ int s_arg[FPS_THREADS / 32];
   __shared__ int s_pick;
   const int set = blockIdx.x;
-  pts += (size_t)set * n * dim;
+  pts += (size_t)set * set_stride;          // set_stride = 0: every set samples the same cloud
   gap_ws += (size_t)set * n;
   out_idx += (size_t)set * count;
   out_pts += (size_t)set * count * dim;
-  int pick = init_idx;
+  int pick = init_arr ? min(max(init_arr[set], 0), n - 1) : init_idx;
   for (int it = 0; it < count; ++it) {
     float c[3] = {0.f, 0.f, 0.f};
     for (int k = 0; k < dim; ++k) c[k] = pts[(size_t)pick * dim + k];
@@ -298,7 +299,7 @@ k_fps(const float* __restrict__ pts, int n, int dim, int count, int init_idx, fl
         const float d = __fsub_rn(pts[(size_t)i * dim + k], c[k]);
         s = k == 0 ? __fmul_rn(d, d) : __fadd_rn(s, __fmul_rn(d, d));
       }
-      float g = __fsqrt_rn(s);
+      float g = squared ? s : __fsqrt_rn(s);       // dgl's sampler compares squared distances, fps_np norms
       if (it > 0) g = fminf(gap_ws[i], g);
       gap_ws[i] = g;
       if (g > best) { best = g; arg = i; }       // ascending i per thread: first index wins inside a thread
@@ -335,7 +336,18 @@ int launch_fps(const float* pts, int n_sets, int n, int dim, int count, int init
                float* out_pts, float* out_radius, cudaStream_t st) {
   if (n_sets <= 0 || n <= 0 || dim < 1 || dim > 3 || count <= 0 || count > n || init_idx < 0 || init_idx >= n)
     return (int)cudaErrorInvalidValue;
-  k_fps<<<n_sets, FPS_THREADS, 0, st>>>(pts, n, dim, count, init_idx, gap_ws, out_idx, out_pts, out_radius);
+  k_fps<<<n_sets, FPS_THREADS, 0, st>>>(pts, (long long)n * dim, n, dim, count, init_idx, nullptr, 0, gap_ws, out_idx,
+                                        out_pts, out_radius);
+  PILE_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_fps_sets(const float* pts, int shared_cloud, int n_sets, int n, int dim, int count, const int* init_idx,
+                    int squared, float* gap_ws, int* out_idx, float* out_pts, float* out_radius, cudaStream_t st) {
+  if (n_sets <= 0 || n <= 0 || dim < 1 || dim > 3 || count <= 0 || count > n || !init_idx)
+    return (int)cudaErrorInvalidValue;
+  k_fps<<<n_sets, FPS_THREADS, 0, st>>>(pts, shared_cloud ? 0 : (long long)n * dim, n, dim, count, 0, init_idx,
+                                        squared, gap_ws, out_idx, out_pts, out_radius);
   PILE_CHECK_LAUNCH();
   return 0;
 }

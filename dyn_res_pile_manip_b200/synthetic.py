@@ -118,3 +118,30 @@ def make_goal(kind="bar", size=SCREEN):
 def random_actions(n_rows, horizon, seed=0, lim=4.0):
     rng = np.random.RandomState(seed + 7)
     return rng.uniform(-lim, lim, size=(n_rows, horizon, 4)).astype(np.float32)
+
+
+def render_observation(state, env=None, particle_radius=0.008, table_depth=0.75, size=SCREEN):
+    """Synthetic top-down RGB-D observation of a pile in the layout FlexEnv.render returns ([H,W,5] float32: RGB,
+    unused, depth * global_scale): every particle (camera-frame x, y, z) is drawn as a sphere above a flat table at
+    `table_depth` (reference scenes: table at 0.75, foreground test depth < 0.599/0.8, flex_env.py:927)."""
+    env = env if env is not None else FakeEnv()
+    fx, fy, cx, cy = env.get_cam_params()
+    depth = np.full((size, size), table_depth, dtype=np.float64)
+    for x, y, z in np.asarray(state, dtype=np.float64):
+        u0, v0 = x * fx / z + cx, y * fy / z + cy
+        rp = particle_radius * fx / z
+        ua, ub = max(int(u0 - rp) - 1, 0), min(int(u0 + rp) + 2, size)
+        va, vb = max(int(v0 - rp) - 1, 0), min(int(v0 + rp) + 2, size)
+        if ua >= ub or va >= vb:
+            continue
+        uu, vv = np.meshgrid(np.arange(ua, ub), np.arange(va, vb))
+        rho2 = ((uu - u0) / fx * z) ** 2 + ((vv - v0) / fy * z) ** 2
+        inside = rho2 < particle_radius ** 2
+        surf = z - np.sqrt(np.maximum(particle_radius ** 2 - rho2, 0.0))
+        patch = depth[va:vb, ua:ub]
+        patch[inside] = np.minimum(patch[inside], surf[inside])
+    obs = np.zeros((size, size, 5), dtype=np.float32)
+    obs[..., :3] = 255.0
+    obs[depth < table_depth, :3] = 128.0
+    obs[..., 4] = (depth * env.global_scale).astype(np.float32)
+    return obs

@@ -133,6 +133,37 @@ int pile_adam_clamp(float* actions, const float* grad, float* exp_avg, float* ex
 int pile_fps(const float* pts, int n_sets, int n, int dim, int count, int init_idx, float* gap_workspace,
              int* out_idx, float* out_pts, float* out_radius, void* stream);
 
+/* Same sampler with one start index per set (device int[n_sets]); shared_cloud != 0: every set samples the same
+ * [n, dim] cloud; squared != 0: compare squared distances (dgl.geometry.farthest_point_sampler, used by utils.fps,
+ * utils.py:423-437) instead of norms (fps_np).  out_radius then holds the squared gap. */
+int pile_fps_sets(const float* pts, int shared_cloud, int n_sets, int n, int dim, int count, const int* init_idx,
+                  int squared, float* gap_workspace, int* out_idx, float* out_pts, float* out_radius, void* stream);
+
+/* ---- observation -> particles: the planner-side work of an MPC step before the rollout
+ * (env/flex_env.py:910-951 obs2ptcl_fixed_num_batch, called with batch_size 30 at :1028 and :1086) -------------
+ * pile_depth_to_points: utils.depth2fgpcd (utils.py:491-506) with mask = (0 < depth < max_depth) as at
+ * flex_env.py:927.  depth [H,W] float32 (already divided by global_scale), cam4 = HOST doubles (fx, fy, cx, cy);
+ * out_pts [capacity,3] float64 in row-major pixel order, *n_out (device) = number of foreground pixels,
+ * counts_workspace: pile_depth_counts_len(H, W) ints. */
+int pile_depth_counts_len(int H, int W);
+int pile_depth_to_points(const float* depth, int H, int W, const double* cam4, float max_depth, double* out_pts,
+                         int capacity, int* n_out, int* counts_workspace, void* stream);
+/* pile_voxel_downsample: utils.downsample_pcd (utils.py:533-544) = open3d PointCloud::VoxelDownSample: voxel index
+ * floor((p - (min_bound - voxel/2)) / voxel), one output point per occupied voxel = mean of its points (summed in
+ * input order).  Output order: ascending (ix, iy, iz) (open3d's hash-map order is unspecified).  pts [n,3] float64,
+ * out_pts [n,3] capacity, *m_out (device) = number of voxels, workspace pile_voxel_downsample_bytes(n) bytes. */
+long long pile_voxel_downsample_bytes(int n);
+int pile_voxel_downsample(const double* pts, int n, double voxel_size, double* out_pts, int* m_out, void* workspace,
+                          void* stream);
+/* pile_cover_radius: particle_r of utils.fps (utils.py:435-437): max over cloud points of the distance to the nearest
+ * pick.  cloud [m,3] float64, picks [n_sets,count,3] float32, radius [n_sets] float64. */
+int pile_cover_radius(const double* cloud, int m, const float* picks, int n_sets, int count, double* radius,
+                      void* stream);
+/* pile_recenter: utils.recenter (utils.py:468-477) with r = min(r_cap, r_scale * radius[set]) (flex_env.py:949):
+ * out[set][k] = mean of the cloud points closer than r to pick k, float32 like the reference's zeros_like(picks). */
+int pile_recenter(const double* cloud, int m, const float* picks, int n_sets, int count, const double* radius,
+                  double r_cap, double r_scale, float* out, void* stream);
+
 /* ---- MPPI weighting: replaces PlannerGD.optimize_action (planners.py:549-561) -------------------
  * partials: [pile_mppi_num_chunks(S)][2 + 4T] = (max z, sum exp(z-max), sum exp(z-max)*act) with
  * z = reward_weight*reward; combine merges P such records (chunks and/or ranks) into one record
