@@ -30,6 +30,7 @@ struct EdgeTmemSmem {
   alignas(128) uint8_t wl[3][TM_WL_BYTES];
   float b_re0[H], b_re1[H], b_re2[H], wd_rp[H], b_rp[H];
   alignas(128) uint8_t stage[TC_GROUPS][TILE * H * 4];     // C_e rows on their way out (tc_tile.cuh: stage_*)
+  alignas(16) float4 feat[TC_GROUPS][2][TILE][2];         // next tile's input rows, one private copy per thread
   uint64_t bar[TC_GROUPS];
   uint64_t w_bar;
   uint32_t tmem_base;
@@ -131,18 +132,21 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
   const int tps = (KMAX * N + TILE - 1) / TILE;
   const int ntiles = B * tps;                  // 32-bit tile arithmetic: 64-bit div/mod is emulated (~100 instr)
   const int stride = (int)gridDim.x * TC_GROUPS;
-  struct Pre { int ne; float4 f0, f1; };
-  auto fetch = [&](int tile) {
-    Pre p;
-    p.ne = 0; p.f0 = make_float4(0.f, 0.f, 0.f, 0.f); p.f1 = p.f0;
+  // The next tile's relation rows (32 bytes each) are fetched with cp.async into a slot that only the issuing
+  // thread reads, so no registers are tied up across the tile chain and no barrier is needed
+  float4* my_feat = &S.feat[g][half][r][0];
+  const uint32_t my_feat_u32 = tc::smem_u32(my_feat);
+  auto fetch = [&](int tile) {          // -> relation count of the tile's sample
+    int ne = 0;
     if (tile < ntiles) {
       const int b = tile / tps;
       const long long slot = (long long)b * KMAX * N + (tile - b * tps) * TILE + r;
-      p.ne = tc::ldg_nc_s32(rowptr + (long long)b * (N + 1) + N);
-      if (half == 0) p.f0 = tc::ldg_nc_f4(efeat + slot * 8);
-      p.f1 = tc::ldg_nc_f4(efeat + slot * 8 + 4);
+      ne = tc::ldg_nc_s32(rowptr + (long long)b * (N + 1) + N);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(my_feat_u32), "l"(efeat + slot * 8) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(my_feat_u32 + 16), "l"(efeat + slot * 8 + 4) : "memory");
     }
-    return p;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    return ne;
   };
   // hand the MMAs of one layer to the tensor core and wait for them
   PILE_TRACE_DECL();
@@ -207,7 +211,7 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
   };
 
   int tile = (int)blockIdx.x * TC_GROUPS + g;
-  Pre cur = fetch(tile);
+  int cur_ne = fetch(tile);
   tc::mbar_wait(&S.w_bar, 0);
   const uint64_t dw0 = tc::make_desc(tc::smem_u32(S.w0), b_lbo(H), B_SBO);
   const uint64_t dwl0 = tc::make_desc(tc::smem_u32(S.wl[0]), b_lbo(H), B_SBO);
@@ -220,18 +224,20 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
   while (tile < ntiles) {
     const int b = tile / tps;
     const int e0 = (tile - b * tps) * TILE;
-    const int nrows = min(TILE, cur.ne - e0);
+    const int nrows = min(TILE, cur_ne - e0);
     const long long slot0 = (long long)b * KMAX * N + e0;
-    const Pre nxt = fetch(tile + stride);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const float4 f0 = my_feat[0], f1 = my_feat[1];
+    const int nxt_ne = fetch(tile + stride);          // overwrites the slot just read
     if (nrows > 0) {
       PILE_TRACE(1);
       const bool valid = r < nrows;
-      const float d = cur.f1.y;
+      const float d = f1.y;
       // layer-0 operand (K = 16: 6 features, zeros) into X; bias_0 pre-loaded into Y
       if (half == 0) {
         uint32_t hi[8], lo[8];
-        const float f[8] = {valid ? cur.f0.x : 0.f, valid ? cur.f0.y : 0.f, valid ? cur.f0.z : 0.f, valid ? cur.f0.w : 0.f,
-                            valid ? cur.f1.x : 0.f, valid ? cur.f1.y : 0.f, 0.f, 0.f};
+        const float f[8] = {valid ? f0.x : 0.f, valid ? f0.y : 0.f, valid ? f0.z : 0.f, valid ? f0.w : 0.f,
+                            valid ? f1.x : 0.f, valid ? f1.y : 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 4; ++i) tc::split2(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
 #pragma unroll
@@ -284,7 +290,7 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
       }
     }
     PILE_TRACE(6);
-    cur = nxt;
+    cur_ne = nxt_ne;
     tile += stride;
   }
   if (pending) {             // group-uniform
