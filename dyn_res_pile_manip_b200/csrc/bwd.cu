@@ -30,6 +30,8 @@ struct BwdScratch {
   float* gcp;       // [R,H] accumulated g_Cp
   float* gagg[PSTEP];
   float* gx;        // [E,4]
+  float* gpr;       // [R,H] receiver-side sums of the masked relation gradients of the current propagation step
+  float* gps;       // [R,H] sender-side sums
   size_t bytes;
 };
 
@@ -43,6 +45,8 @@ static BwdScratch carve_bwd(void* p, int B, int N) {
   s.gcp = take(R * H);
   for (int i = 0; i < PSTEP; ++i) s.gagg[i] = take(R * H);
   s.gx = take(E * 4);
+  s.gpr = take(R * H);
+  s.gps = take(R * H);
   s.bytes = off;
   return s;
 }
@@ -159,6 +163,54 @@ k_bwd_head(const float* __restrict__ wpack, const float* __restrict__ g_pred, lo
 // propagation step p backward (gathers + node GEMMs), then either g_z/g_agg of step p-1 or (FIRST) the
 // particle-encoder backward producing g_s_delta
 // ------------------------------------------------------------------------------------------------
+// g_Pr[i] = sum_{e in row i} g_m(e),  g_Ps[i] = sum_{e: send e = i} g_m(e)  with  g_m(e) = g_agg[recv e] * [m(e) > 0].
+// Latency-bound gathers (mask bytes, transposed CSR, rows of g_agg), so they run in their own high-occupancy
+// kernel (a half-warp per particle, lane = 4 channels) instead of inside the one-CTA-per-SM GEMM kernel.  The
+// sums run in CSR order: deterministic.
+__global__ void __launch_bounds__(256)
+k_bwd_gather(const int* __restrict__ rowptr, const int* __restrict__ trowptr, const int* __restrict__ trecv,
+             const int* __restrict__ tedge, const uint8_t* __restrict__ m_edge, const float* __restrict__ gagg_p,
+             float* __restrict__ gpr_out, float* __restrict__ gps_out, int B, int N) {
+  const int l16 = threadIdx.x & 15;
+  const int mb = l16 >> 1, msh = (l16 & 1) * 4;
+  const int R = B * N;
+  const int nhw = (int)gridDim.x * (int)(blockDim.x >> 4);
+  for (int node = (int)blockIdx.x * (int)(blockDim.x >> 4) + (int)(threadIdx.x >> 4); node < R; node += nhw) {
+    const int b = node / N, i = node - b * N;
+    const long long slot = (long long)b * KMAX * N;
+    const int* rp = rowptr + (long long)b * (N + 1) + i;
+    const int* tp = trowptr + (long long)b * (N + 1) + i;
+    const int e0 = rp[0], e1 = rp[1], k0 = tp[0], k1 = tp[1];
+    const float4 ga = ld4(gagg_p + (long long)node * H + 4 * l16);
+    float4 gpr = make_float4(0.f, 0.f, 0.f, 0.f), gps = gpr;
+    for (int e = e0; e < e1; ++e) {
+      const unsigned nib = (m_edge[(slot + e) * 8 + mb] >> msh) & 15u;
+      const float4 v = mask4(ga, nib);
+      gpr.x += v.x; gpr.y += v.y; gpr.z += v.z; gpr.w += v.w;
+    }
+    for (int k = k0; k < k1; k += 4) {          // four independent gathers in flight
+      float4 g[4];
+      unsigned nib[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kk = min(k + u, k1 - 1);
+        const int rc = trecv[slot + kk], e = tedge[slot + kk];
+        nib[u] = (m_edge[(slot + e) * 8 + mb] >> msh) & 15u;
+        g[u] = ld4(gagg_p + ((long long)b * N + rc) * H + 4 * l16);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k + u < k1) {
+          const float4 v = mask4(g[u], nib[u]);
+          gps.x += v.x; gps.y += v.y; gps.z += v.z; gps.w += v.w;
+        }
+      }
+    }
+    st4(gpr_out + (long long)node * H + 4 * l16, gpr);
+    st4(gps_out + (long long)node * H + 4 * l16, gps);
+  }
+}
+
 struct BwdPropSmem {
   float w_r[H * H], w_s[H * H], w_x[H * H], w_y[H * H];   // w_x: W_a (or W_p when FIRST); w_y: W_PE1 (FIRST)
   float w_pe0[8 * H];
@@ -168,11 +220,10 @@ struct BwdPropSmem {
 
 template <bool FIRST>
 __global__ void __launch_bounds__(NT, 1)
-k_bwd_prop(const float* __restrict__ wpack, const int* __restrict__ rowptr, const int* __restrict__ trowptr,
-           const int* __restrict__ trecv, const int* __restrict__ tedge, const uint8_t* __restrict__ m_edge,
+k_bwd_prop(const float* __restrict__ wpack, const float* __restrict__ gpr_in, const float* __restrict__ gps_in,
            const uint8_t* __restrict__ m_next /* eff[p-1] or pe1 */, const uint8_t* __restrict__ m_pe0,
-           const float* __restrict__ gagg_p, float* __restrict__ gz, float* __restrict__ gcp,
-           float* __restrict__ gagg_out, float* __restrict__ g_s_delta, int B, int N) {
+           float* __restrict__ gz, float* __restrict__ gcp, float* __restrict__ gagg_out,
+           float* __restrict__ g_s_delta, int B, int N) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdPropSmem& S = *reinterpret_cast<BwdPropSmem*>(smem_raw);
   load_block(S.w_r, wpack + wslot_offset(W_R), H * H);
@@ -193,26 +244,11 @@ k_bwd_prop(const float* __restrict__ wpack, const int* __restrict__ rowptr, cons
     const long long row0 = (long long)tile * TILE;
     const int nrows = (int)min((long long)TILE, R - row0);
     __syncthreads();
-    for (int r = hw; r < TILE; r += NT / 16) {
+    for (int r = hw; r < TILE; r += NT / 16) {          // the gathered sums of this tile (k_bwd_gather)
       float4 gpr = make_float4(0.f, 0.f, 0.f, 0.f), gps = gpr;
       if (r < nrows) {
-        const long long node = row0 + r;
-        const int b = (int)(node / N), i = (int)(node % N);
-        const long long slot = (long long)b * KMAX * N;
-        const int* rp = rowptr + (long long)b * (N + 1) + i;
-        const float4 ga = ld4(gagg_p + node * H + 4 * l16);
-        for (int e = rp[0]; e < rp[1]; ++e) {
-          const unsigned nib = (m_edge[(slot + e) * 8 + mb] >> msh) & 15u;
-          const float4 v = mask4(ga, nib);
-          gpr.x += v.x; gpr.y += v.y; gpr.z += v.z; gpr.w += v.w;
-        }
-        const int* tp = trowptr + (long long)b * (N + 1) + i;
-        for (int k = tp[0]; k < tp[1]; ++k) {
-          const int rc = trecv[slot + k], e = tedge[slot + k];
-          const unsigned nib = (m_edge[(slot + e) * 8 + mb] >> msh) & 15u;
-          const float4 v = mask4(ld4(gagg_p + ((long long)b * N + rc) * H + 4 * l16), nib);
-          gps.x += v.x; gps.y += v.y; gps.z += v.z; gps.w += v.w;
-        }
+        gpr = ld4(gpr_in + (row0 + r) * H + 4 * l16);
+        gps = ld4(gps_in + (row0 + r) * H + 4 * l16);
       }
       st4(S.A1 + r * LDA + 4 * l16, gpr);
       st4(S.A2 + r * LDA + 4 * l16, gps);
@@ -413,16 +449,25 @@ int launch_step_backward(const float* wpack, const Csr& csr, const Masks& mk, co
   k_bwd_head<<<g2, NT, sizeof(BwdHeadSmem), st>>>(wpack, g_pred, g_stride, mk.q, mk.eff[2], s.gz, s.gcp, s.gagg[2],
                                                   B, N);
   PILE_CHECK_LAUNCH();
-  for (int p = PSTEP - 1; p >= 1; --p) {
-    k_bwd_prop<false><<<g1, NT, sizeof(BwdPropSmem), st>>>(wpack, csr.rowptr, csr.trowptr, csr.trecv, csr.tedge,
-                                                           mk.edge[p], mk.eff[p - 1], nullptr, s.gagg[p], s.gz,
-                                                           s.gcp, s.gagg[p - 1], nullptr, B, N);
+  const int gg = (int)((R + 15) / 16 < 16 * NSM ? (R + 15) / 16 : 16 * NSM);
+  for (int p = PSTEP - 1; p >= 0; --p) {
+    k_bwd_gather<<<gg, 256, 0, st>>>(csr.rowptr, csr.trowptr, csr.trecv, csr.tedge, mk.edge[p], s.gagg[p], s.gpr, s.gps,
+                                     B, N);
+    PILE_CHECK_LAUNCH();
+    if (g_use_tensor_cores) {
+      const int e = launch_bwd_prop_tc(wpack, p == 0, s.gpr, s.gps, p >= 1 ? mk.eff[p - 1] : mk.pe1, mk.pe0, s.gz,
+                                       s.gcp, p >= 1 ? s.gagg[p - 1] : nullptr, g_s_delta, B, N, st);
+      if (e) return e;
+      continue;
+    }
+    if (p >= 1)
+      k_bwd_prop<false><<<g1, NT, sizeof(BwdPropSmem), st>>>(wpack, s.gpr, s.gps, mk.eff[p - 1], nullptr, s.gz, s.gcp,
+                                                             s.gagg[p - 1], nullptr, B, N);
+    else
+      k_bwd_prop<true><<<g1, NT, sizeof(BwdPropSmem), st>>>(wpack, s.gpr, s.gps, mk.pe1, mk.pe0, s.gz, s.gcp, nullptr,
+                                                            g_s_delta, B, N);
     PILE_CHECK_LAUNCH();
   }
-  k_bwd_prop<true><<<g1, NT, sizeof(BwdPropSmem), st>>>(wpack, csr.rowptr, csr.trowptr, csr.trecv, csr.tedge,
-                                                        mk.edge[0], mk.pe1, mk.pe0, s.gagg[0], s.gz, s.gcp, nullptr,
-                                                        g_s_delta, B, N);
-  PILE_CHECK_LAUNCH();
   if (g_use_tensor_cores) {
     const int e = launch_bwd_edge_tc(wpack, csr, mk, s.gagg[0], s.gagg[1], s.gagg[2], s.gx, B, N, st);
     if (e) return e;

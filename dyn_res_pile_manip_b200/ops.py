@@ -17,7 +17,7 @@ KMAX = 10
 WSLOTS = ["W_PE0T", "B_PE0", "W_PE1T", "B_PE1", "W_RE0T", "B_RE0", "W_RE1T", "B_RE1", "W_RE2T", "B_RE2",
           "W_ET", "W_RT", "W_ST", "WD_RP", "B_RP", "W_PT", "W_AT", "WD_PP", "B_PP", "W_V0T", "B_V0", "W_V1T", "B_V1",
           "W_PE0", "W_PE1", "W_RE0", "W_RE1", "W_RE2", "W_E", "W_R", "W_S", "W_P", "W_A", "W_V0", "W_V1",
-          "TC_EDGE", "TC_NODE", "TC_EDGE2", "TC_BWD_EDGE"]
+          "TC_EDGE", "TC_NODE", "TC_EDGE2", "TC_BWD_EDGE", "TC_BWD_NODE"]
 
 CKPT_KEYS = [  # reference checkpoint layout, SURVEY.md §8b
     "model.particle_encoder.model.0", "model.particle_encoder.model.2",
@@ -129,6 +129,11 @@ def pack_weights(state, device):
         "TC_BWD_EDGE": torch.cat([tc_operand(rp[:, 0:H].t().contiguous()), tc_operand(re2.t().contiguous()),
                                   tc_operand(re1.t().contiguous()),
                                   tc_operand(_pad_rows(re0[:, 2:5].t().contiguous(), 16))]),
+        # particle-side dgrad on tcgen05 (csrc/bwd_node_tc.cu): W_a^T, W_r^T, W_s^T, W_p^T, PE1^T, PE0[:, 0:3]^T
+        "TC_BWD_NODE": torch.cat([tc_operand(pp[:, H:2 * H].t().contiguous()), tc_operand(rp[:, H:2 * H].t().contiguous()),
+                                  tc_operand(rp[:, 2 * H:3 * H].t().contiguous()), tc_operand(pp[:, 0:H].t().contiguous()),
+                                  tc_operand(pe1.t().contiguous()),
+                                  tc_operand(_pad_rows(pe0[:, 0:3].t().contiguous(), 16))]),
     }
     if lib.pile_wpack_num_slots() != len(WSLOTS):
         raise _lib.PileLibraryError("weight-slot table out of sync with libpilegnn")
