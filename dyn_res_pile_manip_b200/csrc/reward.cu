@@ -137,20 +137,30 @@ k_reward_bwd(const float* __restrict__ states, long long state_stride, int N, co
   }
   for (int m = threadIdx.x; m < M; m += blockDim.x) arg[m] = argmin_in[s * M + m];
   __syncthreads();
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+  // one warp per particle: the lanes stride over the goal points that picked it (fixed order + fixed shuffle tree:
+  // deterministic), lane 0 adds the bilinear image term and writes the three position gradients
+  const int lane = threadIdx.x & 31, nwarps = (int)(blockDim.x >> 5);
+  for (int n = (int)(threadIdx.x >> 5); n < N; n += nwarps) {
     const float px = pxs[n], py = pys[n];
-    const Bilinear q = bilinear_setup(px, py, Hh, Ww);
-    const float v00 = img_at(goal_img, q.y0, q.x0, Hh, Ww), v01 = img_at(goal_img, q.y0, q.x0 + 1, Hh, Ww);
-    const float v10 = img_at(goal_img, q.y0 + 1, q.x0, Hh, Ww), v11 = img_at(goal_img, q.y0 + 1, q.x0 + 1, Hh, Ww);
-    float gpx = ((v01 - v00) * (1.f - q.wy) + (v11 - v10) * q.wy) * q.gx_scale;
-    float gpy = ((v10 - v00) * (1.f - q.wx) + (v11 - v01) * q.wx) * q.gy_scale;
-    for (int m = 0; m < M; ++m) {
+    float ax = 0.f, ay = 0.f;
+    for (int m = lane; m < M; m += 32) {
       if (arg[m] == n) {
         const float dx = px - goal_coor[m * 2 + 0], dy = py - goal_coor[m * 2 + 1];
         const float d = sqrtf(dx * dx + dy * dy);
-        if (d > 0.f) { gpx += dx / d; gpy += dy / d; }
+        if (d > 0.f) { ax += dx / d; ay += dy / d; }
       }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ax += __shfl_xor_sync(0xffffffffu, ax, o);
+      ay += __shfl_xor_sync(0xffffffffu, ay, o);
+    }
+    if (lane != 0) continue;
+    const Bilinear q = bilinear_setup(px, py, Hh, Ww);
+    const float v00 = img_at(goal_img, q.y0, q.x0, Hh, Ww), v01 = img_at(goal_img, q.y0, q.x0 + 1, Hh, Ww);
+    const float v10 = img_at(goal_img, q.y0 + 1, q.x0, Hh, Ww), v11 = img_at(goal_img, q.y0 + 1, q.x0 + 1, Hh, Ww);
+    float gpx = ((v01 - v00) * (1.f - q.wy) + (v11 - v10) * q.wy) * q.gx_scale + ax;
+    float gpy = ((v10 - v00) * (1.f - q.wx) + (v11 - v01) * q.wx) * q.gy_scale + ay;
     gpx *= scale;
     gpy *= scale;
     const float x = st[n * 3 + 0], y = st[n * 3 + 1], z = st[n * 3 + 2];
