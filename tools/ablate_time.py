@@ -1,4 +1,7 @@
-"""Per-kernel-bucket times of one model step for the library named by PILE_GNN_LIB (measurement aid)."""
+"""Per-kernel-bucket times of one model step (pile_profile_step) for the library named by PILE_GNN_LIB, default the
+in-tree build.  Used for the ablation measurements quoted in DESIGN.md section 5: a variant library is built with
+one group of loads / stores / GEMMs compiled out (temporary `#if` guards around them, never committed) and this
+script prints the six bucket times for it."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
