@@ -124,7 +124,7 @@ __device__ __forceinline__ int block_exscan(int v, int* warp_sums, int* total) {
 }
 
 // One CTA per sample.  Optional fused s_delta (action != nullptr).
-// dynamic smem: pos[N] (float4) | cutd[N] | cuti[N] | deg[N] | roff[N+1] | sel[N*KMAX]
+// dynamic smem: pos[N] (float4) | cutd[N] | cuti[N] | deg[N] | roff[N+1] | sel[N*KMAX] | perm[N]
 __global__ void __launch_bounds__(NBR_THREADS)
 k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* __restrict__ s_delta_in,
              const float* __restrict__ action, int act_stride, PushCam cam, float* __restrict__ s_delta_out,
@@ -139,8 +139,11 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
   int* deg = cuti + N;
   int* roff = deg + N;           // N+1
   int* sel = roff + (N + 1);     // N*KMAX
+  int* perm = sel + N * KMAX;    // N: receivers in coarse spatial order (which lane handles which receiver)
   __shared__ int warp_sums[NBR_THREADS / 32];
   __shared__ int total_s;
+  __shared__ float box[6];
+  __shared__ int cell_cnt[65];
 
   const int b = blockIdx.x;
   const int nvalid = particle_nums ? min(particle_nums[b], N) : N;
@@ -164,14 +167,70 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
   }
   __syncthreads();
 
+  // Which lane handles which receiver does not change any result (every receiver scans all candidates in ascending
+  // index), but it decides how often a warp runs the divergent park/insert code: with 32 NEARBY receivers per warp
+  // a candidate is either interesting to many lanes at once or to none.  So receivers are binned into an 8 x 8 grid
+  // over the two widest axes of the sample's bounding box and handed out in Morton order of the cells (counting
+  // sort with shared-memory atomics; the order inside a cell is arbitrary and irrelevant).
+  {
+    float lo[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+    float hi[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const float4 p = pos[i];
+      lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+      hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+        hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+      }
+    float* wl = cutd;            // scratch (cutd .. sel are written later): [warps][3] minima, then [warps][3] maxima
+    const int nw = (int)(blockDim.x >> 5);
+    if ((threadIdx.x & 31) == 0)
+      for (int a = 0; a < 3; ++a) { wl[(threadIdx.x >> 5) * 3 + a] = lo[a]; wl[(nw + (threadIdx.x >> 5)) * 3 + a] = hi[a]; }
+    if (threadIdx.x < 65) cell_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      float l = wl[threadIdx.x], h = wl[nw * 3 + threadIdx.x];
+      for (int w = 1; w < nw; ++w) { l = fminf(l, wl[w * 3 + threadIdx.x]); h = fmaxf(h, wl[(nw + w) * 3 + threadIdx.x]); }
+      box[threadIdx.x] = l;
+      box[3 + threadIdx.x] = h - l;
+    }
+    __syncthreads();
+    // the two widest axes
+    const float ex = box[3], ey = box[4], ez = box[5];
+    const int drop = (ex <= ey && ex <= ez) ? 0 : ((ey <= ez) ? 1 : 2);
+    const int a0 = drop == 0 ? 1 : 0, a1 = drop == 2 ? 1 : 2;
+    const float s0 = box[3 + a0] > 0.f ? 8.f / box[3 + a0] : 0.f, s1 = box[3 + a1] > 0.f ? 8.f / box[3 + a1] : 0.f;
+    auto cell_of = [&](int i) {
+      const float4 p = pos[i];
+      const float c[3] = {p.x, p.y, p.z};
+      const unsigned q0 = (unsigned)min(7, max(0, (int)((c[a0] - box[a0]) * s0)));
+      const unsigned q1 = (unsigned)min(7, max(0, (int)((c[a1] - box[a1]) * s1)));
+      return (int)((q0 & 1u) | ((q1 & 1u) << 1) | ((q0 & 2u) << 1) | ((q1 & 2u) << 2) | ((q0 & 4u) << 2) | ((q1 & 4u) << 3));
+    };
+    for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&cell_cnt[cell_of(i)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int run = 0;
+      for (int cidx = 0; cidx < 64; ++cidx) { const int n = cell_cnt[cidx]; cell_cnt[cidx] = run; run += n; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) perm[atomicAdd(&cell_cnt[cell_of(i)], 1)] = i;
+    __syncthreads();
+  }
+
   // pass 1: per receiver (one thread each), the (up to) 10 nearest in-radius senders, then sort them by index.
   // The sorted insertion is ~45 instructions and diverges (almost every j makes SOME lane of the warp insert),
   // so candidates are parked in a 3-deep per-lane FIFO and the warp runs the insertion code only when a lane's
   // FIFO is full: ~5x fewer executions on a 300-particle pile.  The pre-filter then uses a slightly stale
   // 10th-best distance, which only lets a few extra candidates through; the insertion itself re-checks.
   for (int base_i = 0; base_i < N; base_i += blockDim.x) {     // every thread takes part in the warp votes
-    const int i = base_i + threadIdx.x;
-    const bool active = i < N;
+    const bool active = base_i + (int)threadIdx.x < N;
+    const int i = active ? perm[base_i + threadIdx.x] : N;
     float bd[KMAX];
     int id[KMAX];
 #pragma unroll
@@ -460,7 +519,7 @@ int launch_gen_s_delta(const float* s_cur, long long s_stride, const float* acti
   return 0;
 }
 
-size_t nbr_smem_bytes(int N) { return sizeof(float) * (size_t)(4 * N + N) + sizeof(int) * (size_t)(N + N + N + 1 + N * KMAX); }
+size_t nbr_smem_bytes(int N) { return sizeof(float) * (size_t)(4 * N + N) + sizeof(int) * (size_t)(N + N + N + 1 + N * KMAX + N); }
 
 int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_delta_in, const float* action,
                       int act_stride, const PushCam& cam, float* s_delta_out, const int* particle_nums, int B,
