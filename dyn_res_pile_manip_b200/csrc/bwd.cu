@@ -237,7 +237,6 @@ k_bwd_prop(const float* __restrict__ wpack, const float* __restrict__ gpr_in, co
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c0 = warp * 8;
   const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
-  const int mb = l16 >> 1, msh = (l16 & 1) * 4;
   const long long R = (long long)B * N;
   const int ntiles = (int)((R + TILE - 1) / TILE);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {

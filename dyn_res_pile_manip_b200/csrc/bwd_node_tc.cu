@@ -16,8 +16,7 @@ namespace pile {
 constexpr uint32_t BN_W64 = 2 * b_bytes(64, 64);      // 16 KB  [hi | lo] of a transposed 64x64 weight
 constexpr uint32_t BN_W16 = 2 * b_bytes(16, 64);      //  4 KB  rows 0..2 = PE0[:, j] (the three s_delta inputs)
 // slot order: W_a^T | W_r^T | W_s^T | W_p^T | PE1^T | PE0sel ; p >= 1 loads the first three, p == 0 all but the first
-constexpr uint32_t BN_OFF_A = 0, BN_OFF_R = BN_W64, BN_OFF_S = 2 * BN_W64, BN_OFF_P = 3 * BN_W64, BN_OFF_PE1 = 4 * BN_W64,
-                   BN_OFF_PE0 = 5 * BN_W64, TC_BWD_NODE_BYTES = 5 * BN_W64 + BN_W16;
+constexpr uint32_t BN_OFF_A = 0, BN_OFF_R = BN_W64, TC_BWD_NODE_BYTES = 5 * BN_W64 + BN_W16;
 static_assert(TC_BWD_NODE_BYTES == 4 * TC_BWD_NODE_FLOATS, "TC_BWD_NODE slot size (common.cuh) out of sync");
 
 template <bool FIRST>
