@@ -303,16 +303,36 @@ k_fps(const float* __restrict__ pts, long long set_stride, int n, int dim, int c
     }
     float best = -1.f;
     int arg = 0x7fffffff;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      float s = 0.f;
-      for (int k = 0; k < dim; ++k) {
-        const float d = __fsub_rn(pts[(size_t)i * dim + k], c[k]);
-        s = k == 0 ? __fmul_rn(d, d) : __fadd_rn(s, __fmul_rn(d, d));
+    // four points per round, all loads first: the gap array is read and written in place every pick, and a
+    // load -> store -> load chain through L2 (the compiler keeps that order) costs ~1000 cycles per point
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * blockDim.x) {
+      float p[4][3], old[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        old[u] = 0.f;
+        p[u][0] = p[u][1] = p[u][2] = 0.f;
+        if (i < n) {
+          p[u][0] = pts[(size_t)i * dim];
+          if (dim > 1) p[u][1] = pts[(size_t)i * dim + 1];
+          if (dim > 2) p[u][2] = pts[(size_t)i * dim + 2];
+          if (it > 0) old[u] = gap_ws[i];
+        }
       }
-      float g = squared ? s : __fsqrt_rn(s);       // dgl's sampler compares squared distances, fps_np norms
-      if (it > 0) g = fminf(gap_ws[i], g);
-      gap_ws[i] = g;
-      if (g > best) { best = g; arg = i; }       // ascending i per thread: first index wins inside a thread
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < n) {
+          float d = __fsub_rn(p[u][0], c[0]);
+          float s = __fmul_rn(d, d);
+          if (dim > 1) { d = __fsub_rn(p[u][1], c[1]); s = __fadd_rn(s, __fmul_rn(d, d)); }
+          if (dim > 2) { d = __fsub_rn(p[u][2], c[2]); s = __fadd_rn(s, __fmul_rn(d, d)); }
+          float g = squared ? s : __fsqrt_rn(s);       // dgl's sampler compares squared distances, fps_np norms
+          if (it > 0) g = fminf(old[u], g);
+          gap_ws[i] = g;
+          if (g > best) { best = g; arg = i; }       // ascending i per thread: first index wins inside a thread
+        }
+      }
     }
     // block arg-max, lowest index on ties
 #pragma unroll

@@ -13,3 +13,13 @@ for count in (500, 1500):
     torch.cuda.synchronize()
     ref, r = synthetic.fps_np(coords, count, 0)
     print("n", len(coords), "count", count, "ms", (time.perf_counter() - t) / 3 * 1e3, "match", np.array_equal(picked.cpu().numpy(), ref), float(rad), float(r))
+# per-pick latency as a function of the cloud size (one set)
+rng = np.random.RandomState(0)
+for n in (512, 2048, 8192, 28800):
+    p = torch.as_tensor(rng.uniform(0, 700, size=(n, 2)).astype(np.float32), device="cuda")
+    ops.fps(p, 256, 0); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.fps(p, 256, 0)
+    e1.record(); torch.cuda.synchronize()
+    print("n", n, "us per pick %.2f" % (e0.elapsed_time(e1) * 1e3 / 256))
