@@ -81,7 +81,8 @@ __device__ __forceinline__ void tile_epilogue(Smem& S) {
 // a time through the staging tile (the A tile: its last MMA has completed).  Ends with the group barrier that
 // frees the tile for the next A operand.
 __device__ __forceinline__ void store_pr_ps(const GroupCtx& c, uint8_t* stage, int t, int r, int half,
-                                            float* __restrict__ Pr, float* __restrict__ Ps, long long row0, long long R) {
+                                            float* __restrict__ Pr, float* __restrict__ Ps, long long row0, long long R,
+                                            int packed_ps) {
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
 #pragma unroll
@@ -92,7 +93,10 @@ __device__ __forceinline__ void store_pr_ps(const GroupCtx& c, uint8_t* stage, i
       stage_put16(stage, r, half * 32 + q * 16, v);
     }
     group_barrier(c.g);
-    stage_flush(stage, t, which == 0 ? Pr : Ps, row0, R);
+    // P_s rows are gathered once per relation by k_edge_agg (through L2, next to the C_e stream): with the tensor
+    // engine's packed C_e they are stored in the same 24-bit row format
+    if (which == 1 && packed_ps) stage_flush_packed(stage, t, reinterpret_cast<uint8_t*>(Ps), row0, R);
+    else stage_flush(stage, t, which == 0 ? Pr : Ps, row0, R);
     group_barrier(c.g);
   }
 }
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr, const float* __restrict__ dens,
                  const float* __restrict__ s_delta, uint8_t* __restrict__ m_pe0, uint8_t* __restrict__ m_pe1,
                  float* __restrict__ Cp, float* __restrict__ eff, float* __restrict__ Pr, float* __restrict__ Ps,
-                 int B, int N) {
+                 int B, int N, int packed_ps) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   NodeEncSmemTc& S = *reinterpret_cast<NodeEncSmemTc*>(smem_raw);
   GroupCtx c = tile_prologue(S, wpack, OFF_PE0, OFF_WA);
@@ -172,7 +176,7 @@ k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr
     run_gemm(c, [&](uint32_t el) {
       issue_gemm<128, 4, false>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w + OFF_WRS, w + OFF_WRS + NB_WRS / 2);
     });
-    store_pr_ps(c, a_hi, t, r, half, Pr, Ps, (long long)tile * TILE, R);
+    store_pr_ps(c, a_hi, t, r, half, Pr, Ps, (long long)tile * TILE, R, packed_ps);
   }
   tile_epilogue(S);
 }
@@ -182,9 +186,11 @@ k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr
 // ------------------------------------------------------------------------------------------------
 constexpr int AGG_THREADS = 256;
 template <bool PACKED>
-__host__ __device__ constexpr int agg_edge_bytes() { return (PACKED ? CE_PACKED_ROW : H * 4) + H * 4; }      // C_e row + P_s row
+__host__ __device__ constexpr int agg_edge_bytes(bool packed_ps) {      // C_e row + P_s row
+  return (PACKED ? CE_PACKED_ROW : H * 4) + (packed_ps ? CE_PACKED_ROW : H * 4);
+}
 template <bool PACKED>
-__host__ __device__ constexpr int agg_smem_bytes() { return (AGG_THREADS / 16) * KMAX * agg_edge_bytes<PACKED>(); }
+__host__ __device__ constexpr int agg_smem_bytes(bool packed_ps) { return (AGG_THREADS / 16) * KMAX * agg_edge_bytes<PACKED>(packed_ps); }
 
 template <bool RECORD, bool PACKED>
 __global__ void __launch_bounds__(AGG_THREADS)
@@ -201,8 +207,12 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
   // All loop bounds are warp-uniform so that the two half-warps stay converged.
   extern __shared__ __align__(128) unsigned char agg_smem[];
   __shared__ uint64_t bars[AGG_THREADS / 16];
+  // P_s rows are packed like C_e when no tape is recorded; with a tape (gradient runs) they stay fp32, because the
+  // extra rounding in front of the ReLU flips sign bits and triples the gradient noise (5.9e-3 vs 2e-3 relative)
+  constexpr bool PS_PACKED = PACKED && !RECORD;
   constexpr int CE_ROW = PACKED ? CE_PACKED_ROW : H * 4;
-  constexpr int EDGE_BYTES = agg_edge_bytes<PACKED>();
+  constexpr int PS_ROW = PS_PACKED ? CE_PACKED_ROW : H * 4;
+  constexpr int EDGE_BYTES = agg_edge_bytes<PACKED>(PS_PACKED);
   const int hw = threadIdx.x >> 4;
   unsigned char* slab_ce = agg_smem + hw * (KMAX * EDGE_BYTES);
   unsigned char* slab_ps = slab_ce + KMAX * CE_ROW;
@@ -245,7 +255,9 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
       if (cnt > 0) tc::bulk_g2s(slab_ce, reinterpret_cast<const unsigned char*>(Ce) + slot * CE_ROW, (uint32_t)(cnt * CE_ROW), bar);
     }
     __syncwarp();
-    if (l16 < cnt) tc::bulk_g2s(slab_ps + l16 * (H * 4), Ps + ((long long)cur.b * N + mycol) * H, H * 4, bar);
+    if (l16 < cnt)
+      tc::bulk_g2s(slab_ps + l16 * PS_ROW, reinterpret_cast<const unsigned char*>(Ps) + ((long long)cur.b * N + mycol) * PS_ROW,
+                   PS_ROW, bar);
     // prefetch for the next two receivers of this half-warp while the rows are on their way
     const int n1 = node + nhw;
     int mycol1 = 0;
@@ -271,7 +283,12 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
           ce = unpack24(*reinterpret_cast<const uint2*>(e + l16 * 8), *reinterpret_cast<const uint32_t*>(e + 128 + l16 * 4));
         else
           ce = *reinterpret_cast<const float4*>(e + l16 * 16);
-        const float4 ps = *reinterpret_cast<const float4*>(slab_ps + k * (H * 4) + l16 * 16);
+        const unsigned char* pe = slab_ps + k * PS_ROW;
+        float4 ps;
+        if (PS_PACKED)
+          ps = unpack24(*reinterpret_cast<const uint2*>(pe + l16 * 8), *reinterpret_cast<const uint32_t*>(pe + 128 + l16 * 4));
+        else
+          ps = *reinterpret_cast<const float4*>(pe + l16 * 16);
         v = make_float4(ce.x + pr.x + ps.x, ce.y + pr.y + ps.y, ce.z + pr.z + ps.z, ce.w + pr.w + ps.w);
         sum.x += fmaxf(v.x, 0.f); sum.y += fmaxf(v.y, 0.f); sum.z += fmaxf(v.z, 0.f); sum.w += fmaxf(v.w, 0.f);
       }
@@ -299,7 +316,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg, const float* __restrict__ Cp,
                  float* __restrict__ eff, float* __restrict__ PrOut, float* __restrict__ PsOut,
                  uint8_t* __restrict__ m_eff, uint8_t* __restrict__ m_q, const float* __restrict__ s_cur,
-                 long long s_stride, float* __restrict__ s_out, long long o_stride, int B, int N) {
+                 long long s_stride, float* __restrict__ s_out, long long o_stride, int B, int N, int packed_ps) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   NodeUpdSmemTc& S = *reinterpret_cast<NodeUpdSmemTc*>(smem_raw);
   const long long t_entry = clock64();
@@ -380,7 +397,7 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
         issue_gemm<128, 4, false>(el, c.tmem_d, c.a_hi, c.a_lo, c.aux_hi, c.aux_lo, c.zero, w_rs, w_rs + NB_WRS / 2);
       });
       PILE_TRACE(5);
-      store_pr_ps(c, a_hi, t, r, half, PrOut, PsOut, (long long)tile * TILE, R);
+      store_pr_ps(c, a_hi, t, r, half, PrOut, PsOut, (long long)tile * TILE, R, packed_ps);
     } else {
       // predictor: q = ReLU(V0 eff + c0);  s_pred = s_cur + V1 q + c1
       run_gemm(c, [&](uint32_t el) {
@@ -440,19 +457,19 @@ int launch_node_encode_tc(const float* wpack, const float* attr, const float* de
     if ((e = set_smem_tc(k_node_update_tc<false, true>, sizeof(NodeUpdSmemTc)))) return e;
     if ((e = set_smem_tc(k_node_update_tc<true, false>, sizeof(NodeUpdSmemTc)))) return e;
     if ((e = set_smem_tc(k_node_update_tc<true, true>, sizeof(NodeUpdSmemTc)))) return e;
-    if ((e = set_smem_tc(k_edge_agg<false, false>, agg_smem_bytes<false>()))) return e;
-    if ((e = set_smem_tc(k_edge_agg<true, false>, agg_smem_bytes<false>()))) return e;
-    if ((e = set_smem_tc(k_edge_agg<false, true>, agg_smem_bytes<true>()))) return e;
-    if ((e = set_smem_tc(k_edge_agg<true, true>, agg_smem_bytes<true>()))) return e;
+    if ((e = set_smem_tc(k_edge_agg<false, false>, agg_smem_bytes<false>(false)))) return e;
+    if ((e = set_smem_tc(k_edge_agg<true, false>, agg_smem_bytes<false>(false)))) return e;
+    if ((e = set_smem_tc(k_edge_agg<false, true>, agg_smem_bytes<true>(true)))) return e;
+    if ((e = set_smem_tc(k_edge_agg<true, true>, agg_smem_bytes<true>(false)))) return e;
     configured = true;
   }
   const long long ntiles = ((long long)B * N + TILE - 1) / TILE;
   if (mk)
     k_node_encode_tc<true><<<tc_grid(ntiles), TC_THREADS, sizeof(NodeEncSmemTc), st>>>(
-        wpack, attr, dens, s_delta, mk->pe0, mk->pe1, ws.Cp, ws.eff, ws.Pr[0], ws.Ps[0], B, N);
+        wpack, attr, dens, s_delta, mk->pe0, mk->pe1, ws.Cp, ws.eff, ws.Pr[0], ws.Ps[0], B, N, g_use_tensor_cores == 2 && mk == nullptr);
   else
     k_node_encode_tc<false><<<tc_grid(ntiles), TC_THREADS, sizeof(NodeEncSmemTc), st>>>(
-        wpack, attr, dens, s_delta, nullptr, nullptr, ws.Cp, ws.eff, ws.Pr[0], ws.Ps[0], B, N);
+        wpack, attr, dens, s_delta, nullptr, nullptr, ws.Cp, ws.eff, ws.Pr[0], ws.Ps[0], B, N, g_use_tensor_cores == 2 && mk == nullptr);
   PILE_CHECK_LAUNCH();
   return 0;
 }
@@ -469,7 +486,7 @@ int launch_propagate_tc(const float* wpack, const Csr& csr, const StepScratch& w
   uint8_t* me = mk ? mk->edge[p] : nullptr;
   auto agg_kernel = mk ? (packed ? k_edge_agg<true, true> : k_edge_agg<true, false>)
                        : (packed ? k_edge_agg<false, true> : k_edge_agg<false, false>);
-  const int agg_smem = packed ? agg_smem_bytes<true>() : agg_smem_bytes<false>();
+  const int agg_smem = packed ? agg_smem_bytes<true>(mk == nullptr) : agg_smem_bytes<false>(false);
   agg_kernel<<<agg_blocks, AGG_THREADS, agg_smem, st>>>(csr.rowptr, csr.col, ws.Ce, ws.Pr[in], ws.Ps[in], me, ws.agg, B, N);
   PILE_CHECK_LAUNCH();
   const int grid = tc_grid(ntiles);
@@ -477,17 +494,17 @@ int launch_propagate_tc(const float* wpack, const Csr& csr, const StepScratch& w
   if (p < PSTEP - 1) {
     if (mk)
       k_node_update_tc<false, true><<<grid, TC_THREADS, sm, st>>>(wpack, ws.agg, ws.Cp, ws.eff, ws.Pr[out], ws.Ps[out],
-                                                                  mk->eff[p], nullptr, s_cur, s_stride, s_out, o_stride, B, N);
+                                                                  mk->eff[p], nullptr, s_cur, s_stride, s_out, o_stride, B, N, packed && mk == nullptr);
     else
       k_node_update_tc<false, false><<<grid, TC_THREADS, sm, st>>>(wpack, ws.agg, ws.Cp, ws.eff, ws.Pr[out], ws.Ps[out],
-                                                                   nullptr, nullptr, s_cur, s_stride, s_out, o_stride, B, N);
+                                                                   nullptr, nullptr, s_cur, s_stride, s_out, o_stride, B, N, packed && mk == nullptr);
   } else {
     if (mk)
       k_node_update_tc<true, true><<<grid, TC_THREADS, sm, st>>>(wpack, ws.agg, ws.Cp, ws.eff, nullptr, nullptr, mk->eff[p],
-                                                                 mk->q, s_cur, s_stride, s_out, o_stride, B, N);
+                                                                 mk->q, s_cur, s_stride, s_out, o_stride, B, N, packed && mk == nullptr);
     else
       k_node_update_tc<true, false><<<grid, TC_THREADS, sm, st>>>(wpack, ws.agg, ws.Cp, ws.eff, nullptr, nullptr, nullptr,
-                                                                  nullptr, s_cur, s_stride, s_out, o_stride, B, N);
+                                                                  nullptr, s_cur, s_stride, s_out, o_stride, B, N, packed && mk == nullptr);
   }
   PILE_CHECK_LAUNCH();
   return 0;
