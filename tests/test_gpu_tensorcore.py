@@ -19,7 +19,7 @@ def model():
 
 
 @pytest.mark.parametrize("mode", [1, 2])
-@pytest.mark.parametrize("N,B", [(7, 5), (50, 9), (100, 64), (300, 40), (13, 700)])
+@pytest.mark.parametrize("N,B", [(1, 4), (7, 5), (50, 9), (100, 64), (300, 40), (13, 700), (1000, 3)])
 def test_tc_step_matches_fp32_step(model, N, B, mode):
     rng = np.random.RandomState(N)
     if N >= 10:
