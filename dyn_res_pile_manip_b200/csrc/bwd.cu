@@ -445,9 +445,14 @@ int launch_step_backward(const float* wpack, const Csr& csr, const Masks& mk, co
   const int g1 = node_tiles < NSM ? node_tiles : NSM;
   const int ge = edge_tiles < 2 * NSM ? (int)edge_tiles : 2 * NSM;
 
-  k_bwd_head<<<g2, NT, sizeof(BwdHeadSmem), st>>>(wpack, g_pred, g_stride, mk.q, mk.eff[2], s.gz, s.gcp, s.gagg[2],
-                                                  B, N);
-  PILE_CHECK_LAUNCH();
+  if (g_use_tensor_cores) {
+    const int e = launch_bwd_head_tc(wpack, g_pred, g_stride, mk.q, mk.eff[2], s.gz, s.gcp, s.gagg[2], B, N, st);
+    if (e) return e;
+  } else {
+    k_bwd_head<<<g2, NT, sizeof(BwdHeadSmem), st>>>(wpack, g_pred, g_stride, mk.q, mk.eff[2], s.gz, s.gcp, s.gagg[2],
+                                                    B, N);
+    PILE_CHECK_LAUNCH();
+  }
   const int gg = (int)((R + 15) / 16 < 16 * NSM ? (R + 15) / 16 : 16 * NSM);
   for (int p = PSTEP - 1; p >= 0; --p) {
     k_bwd_gather<<<gg, 256, 0, st>>>(csr.rowptr, csr.trowptr, csr.trecv, csr.tedge, mk.edge[p], s.gagg[p], s.gpr, s.gps,

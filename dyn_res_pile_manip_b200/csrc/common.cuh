@@ -22,7 +22,7 @@ constexpr int NT = 256;        // threads per GEMM CTA: 8 warps x (4 rows/lane x
 constexpr int NSM = 148;
 constexpr int TC_EDGE2_FLOATS = 13312;  // 52 KB, layout in edge_tmem.cu
 constexpr int TC_BWD_EDGE_FLOATS = 13312;  // 52 KB, layout in bwd_tc.cu
-constexpr int TC_BWD_NODE_FLOATS = 21504;  // 84 KB, layout in bwd_node_tc.cu
+constexpr int TC_BWD_NODE_FLOATS = 26624;  // 104 KB, layout in bwd_node_tc.cu
 constexpr int TC_NODE_FLOATS = 29952;   // 117 KB of bf16 hi/lo weight images, layout in node_tc.cu
 
 // ---- packed weight buffer (floats). Forward blocks are transposed [K][H]; backward blocks keep the
@@ -56,7 +56,7 @@ enum WSlot {
   // relation-encoder backward on tcgen05 (bwd_tc.cu): W_e^T, RE2^T, RE1^T [64 x 64], RE0[:, 2:5]^T padded to [16 x 64]
   TC_BWD_EDGE,
   // particle-side backward on tcgen05 (bwd_node_tc.cu): W_a^T, W_r^T, W_s^T, W_p^T, PE1^T [64 x 64], PE0[:, 0:3]^T
-  // padded to [16 x 64]
+  // padded to [16 x 64], V0^T [64 x 64], V1^T padded to [64 x 16]
   TC_BWD_NODE,
   W_NUM
 };

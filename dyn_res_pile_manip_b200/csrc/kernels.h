@@ -70,6 +70,8 @@ int launch_edge_encode_tmem(const float* wpack, const float* efeat, const Csr& c
                             int B, int N, cudaStream_t st);
 int launch_bwd_edge_tc(const float* wpack, const Csr& csr, const Masks& mk, const float* ga0, const float* ga1,
                        const float* ga2, float* gx, int B, int N, cudaStream_t st);
+int launch_bwd_head_tc(const float* wpack, const float* g_pred, long long g_stride, const uint8_t* m_q,
+                       const uint8_t* m_eff2, float* gz, float* gcp, float* gagg2, int B, int N, cudaStream_t st);
 int launch_bwd_prop_tc(const float* wpack, bool first, const float* gpr, const float* gps, const uint8_t* m_next,
                        const uint8_t* m_pe0, float* gz, float* gcp, float* gagg_out, float* g_s_delta, int B, int N,
                        cudaStream_t st);

@@ -129,11 +129,12 @@ def pack_weights(state, device):
         "TC_BWD_EDGE": torch.cat([tc_operand(rp[:, 0:H].t().contiguous()), tc_operand(re2.t().contiguous()),
                                   tc_operand(re1.t().contiguous()),
                                   tc_operand(_pad_rows(re0[:, 2:5].t().contiguous(), 16))]),
-        # particle-side dgrad on tcgen05 (csrc/bwd_node_tc.cu): W_a^T, W_r^T, W_s^T, W_p^T, PE1^T, PE0[:, 0:3]^T
+        # particle-side dgrad on tcgen05 (csrc/bwd_node_tc.cu): W_a^T, W_r^T, W_s^T, W_p^T, PE1^T, PE0[:, 0:3]^T, V0^T, V1^T
         "TC_BWD_NODE": torch.cat([tc_operand(pp[:, H:2 * H].t().contiguous()), tc_operand(rp[:, H:2 * H].t().contiguous()),
                                   tc_operand(rp[:, 2 * H:3 * H].t().contiguous()), tc_operand(pp[:, 0:H].t().contiguous()),
                                   tc_operand(pe1.t().contiguous()),
-                                  tc_operand(_pad_rows(pe0[:, 0:3].t().contiguous(), 16))]),
+                                  tc_operand(_pad_rows(pe0[:, 0:3].t().contiguous(), 16)),
+                                  tc_operand(v0.t().contiguous()), tc_operand(_pad_cols(v1.t().contiguous(), 16))]),
     }
     if lib.pile_wpack_num_slots() != len(WSLOTS):
         raise _lib.PileLibraryError("weight-slot table out of sync with libpilegnn")
