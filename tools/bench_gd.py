@@ -20,7 +20,9 @@ acts = torch.tensor(synthetic.random_actions(S, T, seed=1), device="cuda", requi
 opt = torch.optim.Adam([acts], lr=0.05)
 ev = lambda: torch.cuda.Event(enable_timing=True)
 res = {}
-for engine in ("tensor", "tensor_smem", "fp32"):
+# the first engine measured pays one-time costs (allocator growth for the tape, kernel attribute setup) well past the
+# warm-up iterations, so the tensor engine is measured again at the end and that figure is reported
+for engine in ("tensor", "tensor_smem", "fp32", "tensor"):
     ops.set_tensor_cores({"tensor": 2, "tensor_smem": 1, "fp32": 0}[engine])
     f, b, tot = [], [], []
     for it in range(8):
