@@ -262,7 +262,7 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
         lim = fminf(thr, bd[KMAX - 1]);
       }
     };
-#pragma unroll 2
+#pragma unroll 4
     for (int j = 0; j < N; ++j) {
       const float4 pj = pos[j];
       const float d = sqdist_rn(xi, yi, zi, pj.x, pj.y, pj.z);
