@@ -133,3 +133,27 @@ def test_synthetic_pile_statistics():
     adj = O.adjacency(torch.from_numpy(s)[None], torch.zeros(1, 100, 3), 0.08)
     deg = adj[0].sum(1)
     assert deg.max() <= 10 and deg.min() >= 1 and adj[0].diagonal().all()
+
+
+def test_warm_start_shift_is_the_reference_expression():
+    """flex_env.py:1112-1113: a length-1 initial sequence comes back unchanged; for longer ones the reference
+    concatenates action_full[1:] ([traj-1, 4]) with a [steps, traj, 4] array, which numpy rejects - kept as is."""
+    from dyn_res_pile_manip_b200.observation import shift_warm_start
+    one = np.zeros((1, 6, 4))
+    assert shift_warm_start(one, np.ones((6, 4), np.float32), 1) is one
+    with pytest.raises(ValueError):
+        shift_warm_start(np.zeros((3, 6, 4)), np.ones((6, 4), np.float32), 1)
+
+
+def test_synthetic_observation_layout():
+    """render_observation produces what FlexEnv.obs2ptcl_fixed_num_batch asserts on (flex_env.py:934-940)."""
+    from dyn_res_pile_manip_b200 import synthetic
+    env = synthetic.FakeEnv()
+    st, _ = synthetic.make_pile_batch(1, 40, seed=2)
+    obs = synthetic.render_observation(st[0], env)
+    assert obs.shape == (env.screenHeight, env.screenWidth, 5) and obs.dtype == np.float32
+    assert obs[..., :3].max() <= 255.0 and obs[..., :3].min() >= 0.0 and obs[..., :3].max() >= 1.0
+    assert 0.7 * env.global_scale <= obs[..., -1].max() <= 0.8 * env.global_scale
+    depth = obs[..., -1] / env.global_scale
+    fg = depth < 0.599 / 0.8
+    assert 0 < fg.sum() < fg.size // 4           # a pile in the middle of an empty table
