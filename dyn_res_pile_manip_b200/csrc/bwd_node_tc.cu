@@ -107,7 +107,9 @@ k_bwd_prop_tc(const float* __restrict__ wpack, const float* __restrict__ gpr, co
   const int ntiles = (int)((R + TILE - 1) / TILE);
   tc::mbar_wait(&S.w_bar, 0);
 
-  for (int tile = (int)blockIdx.x * TC_GROUPS + g; tile < ntiles; tile += (int)gridDim.x * TC_GROUPS) {
+  // group g of CTA c takes tiles g * gridDim + c, + 4 * gridDim, ...: a small workload spreads over all SMs (one
+  // tile chain per SM) before any SM runs four chains side by side
+  for (int tile = g * (int)gridDim.x + (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x * TC_GROUPS) {
     const long long row0 = (long long)tile * TILE;
     const long long row = row0 + r;
     const bool valid = row < R;
@@ -238,7 +240,9 @@ k_bwd_head_tc(const float* __restrict__ wpack, const float* __restrict__ g_pred,
   const int ntiles = (int)((R + TILE - 1) / TILE);
   tc::mbar_wait(&S.w_bar, 0);
 
-  for (int tile = (int)blockIdx.x * TC_GROUPS + g; tile < ntiles; tile += (int)gridDim.x * TC_GROUPS) {
+  // group g of CTA c takes tiles g * gridDim + c, + 4 * gridDim, ...: a small workload spreads over all SMs (one
+  // tile chain per SM) before any SM runs four chains side by side
+  for (int tile = g * (int)gridDim.x + (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x * TC_GROUPS) {
     const long long row0 = (long long)tile * TILE;
     const long long row = row0 + r;
     const bool valid = row < R;
@@ -300,8 +304,7 @@ int launch_bwd_head_tc(const float* wpack, const float* g_pred, long long g_stri
     configured = true;
   }
   const long long ntiles = ((long long)B * N + TILE - 1) / TILE;
-  const long long want = (ntiles + TC_GROUPS - 1) / TC_GROUPS;
-  const int grid = (int)(want < 1 ? 1 : (want < NSM ? want : NSM));
+  const int grid = (int)(ntiles < 1 ? 1 : (ntiles < NSM ? ntiles : NSM));
   k_bwd_head_tc<<<grid, TC_THREADS, sizeof(BwdHeadTcSmem), st>>>(wpack, g_pred, g_stride, m_q, m_eff2, gz, gcp, gagg2, B, N);
   PILE_CHECK_LAUNCH();
   return 0;
@@ -321,8 +324,7 @@ int launch_bwd_prop_tc(const float* wpack, bool first, const float* gpr, const f
     configured = true;
   }
   const long long ntiles = ((long long)B * N + TILE - 1) / TILE;
-  const long long want = (ntiles + TC_GROUPS - 1) / TC_GROUPS;
-  const int grid = (int)(want < 1 ? 1 : (want < NSM ? want : NSM));
+  const int grid = (int)(ntiles < 1 ? 1 : (ntiles < NSM ? ntiles : NSM));
   if (first)
     k_bwd_prop_tc<true><<<grid, TC_THREADS, sizeof(BwdNodeTcSmem<true>), st>>>(wpack, gpr, gps, m_next, m_pe0, gz, gcp,
                                                                               gagg_out, g_s_delta, B, N);

@@ -123,7 +123,9 @@ k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr
   const int ntiles = (R + TILE - 1) / TILE;
   tc::mbar_wait(&S.w_bar, 0);
 
-  for (int tile = (int)blockIdx.x * TC_GROUPS + g; tile < ntiles; tile += (int)gridDim.x * TC_GROUPS) {
+  // group g of CTA c takes tiles g * gridDim + c, + 4 * gridDim, ...: a small workload spreads over all SMs (one
+  // tile chain per SM) before any SM runs four chains side by side
+  for (int tile = g * (int)gridDim.x + (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x * TC_GROUPS) {
     const int row = tile * TILE + r;
     const bool valid = row < R;
     float d = 0.f;
@@ -343,7 +345,9 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
   tc::mbar_wait(&S.w_bar, 0);
   PILE_TRACE(9);
 
-  for (int tile = (int)blockIdx.x * TC_GROUPS + g; tile < ntiles; tile += (int)gridDim.x * TC_GROUPS) {
+  // group g of CTA c takes tiles g * gridDim + c, + 4 * gridDim, ...: a small workload spreads over all SMs (one
+  // tile chain per SM) before any SM runs four chains side by side
+  for (int tile = g * (int)gridDim.x + (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x * TC_GROUPS) {
     const int row = tile * TILE + r;
     const bool valid = row < R;
     PILE_TRACE(1);
@@ -442,8 +446,7 @@ static int set_smem_tc(Kern k, size_t bytes) {
 }
 
 static int tc_grid(long long ntiles) {
-  const long long want = (ntiles + TC_GROUPS - 1) / TC_GROUPS;
-  return (int)(want < 1 ? 1 : (want < NSM ? want : NSM));
+  return (int)(ntiles < 1 ? 1 : (ntiles < NSM ? ntiles : NSM));
 }
 
 int launch_node_encode_tc(const float* wpack, const float* attr, const float* dens, const float* s_delta,
