@@ -483,7 +483,7 @@ int launch_propagate_tc(const float* wpack, const Csr& csr, const StepScratch& w
   const int in = p & 1, out = in ^ 1;
   const long long R = (long long)B * N;
   const long long ntiles = (R + TILE - 1) / TILE;
-  const int agg_blocks = (int)((R + 15) / 16 < 8 * NSM ? (R + 15) / 16 : 8 * NSM);
+  const int agg_blocks = (int)((R + 15) / 16 < 3 * NSM ? (R + 15) / 16 : 3 * NSM);      // 3 resident blocks per SM: one wave
   // tensor engine 2 (edge_tmem.cu) writes packed C_e rows, engine 1 (edge_tc.cu) plain fp32 rows
   const bool packed = g_use_tensor_cores == 2;
   uint8_t* me = mk ? mk->edge[p] : nullptr;
