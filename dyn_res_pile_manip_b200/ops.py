@@ -204,6 +204,11 @@ class Relations:
         counts = torch.zeros(B, N + 1, dtype=torch.int64, device=dev)
         counts.scatter_add_(1, torch.where(live, recv + 1, torch.zeros_like(recv)), live.long())
         counts[:, 0] = 0
+        # the kernels keep one receiver's relations in a KMAX-row shared-memory slab (the reference's own builder
+        # never emits more: topk(k=10), gnn_dyn.py:231); reject anything else instead of computing garbage
+        if n_rel > 0 and int(counts.max()) > KMAX:
+            raise ValueError("a particle receives %d relations; at most %d per receiver are supported" %
+                             (int(counts.max()), KMAX))
         return Relations(counts.cumsum(1).int().contiguous(), col, row)
 
 

@@ -68,7 +68,8 @@ int pile_predict_step(const float* wpack, const float* attr, const float* dens, 
                       const float* s_cur, const float* s_delta, float adj_thresh, int B, int N, void* scratch,
                       void* tape, float* s_pred, void* stream);
 /* forward on caller-provided relation lists -- the "Rr/Rs-equivalent" entry of PropModuleDiffDen.forward
- * (model/gnn_dyn.py:147): relations of a sample must be grouped by receiver (CSR). */
+ * (model/gnn_dyn.py:147): relations of a sample must be grouped by receiver (CSR), at most pile_max_relations()
+ * per receiver (what the reference's own builder emits, gnn_dyn.py:231); the caller checks this. */
 int pile_forward_relations(const float* wpack, const float* attr, const float* dens, const float* s_cur,
                            const float* s_delta, const int* rowptr, const int* col, const int* row, int B, int N,
                            void* scratch, void* tape, float* s_pred, void* stream);

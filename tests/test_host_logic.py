@@ -157,3 +157,17 @@ def test_synthetic_observation_layout():
     depth = obs[..., -1] / env.global_scale
     fg = depth < 0.599 / 0.8
     assert 0 < fg.sum() < fg.size // 4           # a pile in the middle of an empty table
+
+
+def test_from_dense_rejects_more_than_ten_relations_per_receiver():
+    N = 14
+    rr = torch.zeros(1, 12, N)
+    rs = torch.zeros(1, 12, N)
+    rr[0, :, 3] = 1.0                                  # twelve relations into particle 3
+    rs[0, torch.arange(12), torch.arange(12)] = 1.0
+    with pytest.raises(ValueError):
+        ops.Relations.from_dense(rr, rs)
+    rr[0, 10:, 3] = 0.0
+    rr[0, 10:, 4] = 1.0                                # ten into particle 3, two into particle 4: fine
+    rel = ops.Relations.from_dense(rr, rs)
+    assert rel.rowptr[0, 4].item() - rel.rowptr[0, 3].item() == 10
