@@ -177,6 +177,33 @@ def gen_s_delta(cam_extrinsic, global_scale, s_cur, action):
     return to_end[..., None] * u[:, None, :] * hard[..., None] * soft[..., None]
 
 
+IRL_PUSHER_W = 0.048     # planners.py:279
+IRL_HEIGHT = 0.88        # planners.py:276
+
+
+def gen_s_delta_irl(s_cur, action, wkspc_center_x, wkspc_center_y, s2r_scale):
+    """Real-robot pusher parametrisation (planners.py:259-300, behind env.is_real): the push end points come from
+    the action scaled by s2r_scale at a fixed height, the particles are shifted by the workspace centre.
+    s_cur [B,N,3], action [B,4]=(sx,sy,ex,ey) -> s_delta [B,N,3]."""
+    shift = torch.tensor([wkspc_center_x, wkspc_center_y, 0.0], dtype=s_cur.dtype, device=s_cur.device)
+    p = s_cur - shift
+    h = torch.full((action.shape[0], 1), IRL_HEIGHT, dtype=action.dtype, device=action.device)
+    start = torch.cat([action[:, 0:1] / s2r_scale, -action[:, 1:2] / s2r_scale, h], dim=1)
+    end = torch.cat([action[:, 2:3] / s2r_scale, -action[:, 3:4] / s2r_scale, h], dim=1)
+    push = end - start
+    length = torch.linalg.norm(push, dim=1)
+    u = push / torch.linalg.norm(push, dim=1, keepdim=True)
+    v = torch.cat([-u[:, 1:2], u[:, 0:1], torch.zeros_like(u[:, 0:1])], dim=1)
+    rel = p - start[:, None, :]
+    across = (rel * v[:, None, :]).sum(-1)
+    along = (rel * u[:, None, :]).sum(-1)
+    hard = ((along < length[:, None]) & (along > 0.0)).float()
+    excess = torch.maximum(torch.clamp(-IRL_PUSHER_W - across, min=0.), torch.clamp(across - IRL_PUSHER_W, min=0.))
+    soft = torch.exp(-excess / WIDTH_DECAY)
+    to_end = ((end[:, None, :] - p) * u[:, None, :]).sum(-1)
+    return to_end[..., None] * u[:, None, :] * hard[..., None] * soft[..., None]
+
+
 # --------------------------------------------------------------------------------------
 # rollout (planners.py:302-370)
 # --------------------------------------------------------------------------------------

@@ -75,3 +75,18 @@ def test_fps_matches_reference_goal_coords(golden):
     coords = torch.flip((goal < 0.5).nonzero(), dims=(1,)).float().numpy()
     mine, _ = synthetic.fps_np(coords, min(300, coords.shape[0]), 0)
     assert np.array_equal(mine.astype(np.float32), golden["D/goal_coor"])
+
+
+def test_gen_s_delta_irl_vs_reference():
+    """Real-robot pusher variant (planners.py:259-300): oracle restatement against the reference's
+    own output and autograd gradients (tests/golden/make_golden_irl.py).  The CUDA path does not implement it yet
+    (PlannerGD raises for env.is_real); this pins the oracle for when it does."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_irl_v1.npz"))
+    s = torch.tensor(g["s_cur"], requires_grad=True)
+    a = torch.tensor(g["action"], requires_grad=True)
+    out = O.gen_s_delta_irl(s, a, float(g["wkspc_center_x"]), float(g["wkspc_center_y"]), float(g["s2r_scale"]))
+    np.testing.assert_allclose(out.detach().numpy(), g["s_delta"], rtol=0, atol=2e-7)
+    (out * torch.tensor(g["weight"])).sum().backward()
+    np.testing.assert_allclose(s.grad.numpy(), g["g_s_cur"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(a.grad.numpy(), g["g_action"], rtol=1e-4, atol=1e-5)
