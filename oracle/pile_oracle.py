@@ -142,6 +142,21 @@ def predict_one_step(W, adj_thresh, a_cur, s_cur, s_delta, particle_dens, partic
     return (out, adj) if return_adj else out
 
 
+def training_loss(W, adj_thresh, states, states_delta, attrs, particle_dens, particle_nums):
+    """train/train_gnn_dyn.py:150-192: roll the model over states_delta [B, n_roll, N, 3] from states[:, 0], per
+    sample MSE against states[:, t+1] over the first particle_nums[b] particles, mean over n_roll * B."""
+    B, n_roll = states_delta.shape[0], states_delta.shape[1]
+    s_cur, a_cur = states[:, 0], attrs[:, 0]
+    loss = 0.
+    for t in range(n_roll):
+        s_pred = predict_one_step(W, adj_thresh, a_cur, s_cur, states_delta[:, t], particle_dens, particle_nums)
+        for b in range(B):
+            n = int(particle_nums[b])
+            loss = loss + torch.mean((s_pred[b, :n] - states[b, t + 1, :n]) ** 2)
+        s_cur = s_pred
+    return loss / (n_roll * B)
+
+
 # --------------------------------------------------------------------------------------
 # pusher model (planners.py:192-257)
 # --------------------------------------------------------------------------------------
