@@ -108,3 +108,32 @@ def test_training_objective_and_weight_gradients_vs_reference(golden_weights):
         ref = g["g/" + k]
         err = np.abs(w.grad.numpy() - ref).max()
         assert err <= 2e-6 + 1e-4 * np.abs(ref).max(), (k, err)
+
+
+def test_three_pass_bf16_split_meets_the_position_bar(golden, golden_weights, monkeypatch):
+    """Numerical design check of the tensor engine, on the CPU: every linear layer evaluated as the three bf16 passes
+    hi*hi' + lo*hi' + hi*lo' with fp32 accumulation (csrc/tc.cuh) keeps one-step positions within
+    1e-5 of the fp32 oracle on the golden case (bar: 1e-4 relative); a single bf16 pass does not."""
+    def split(t):
+        hi = t.to(torch.bfloat16).float()
+        return hi, (t - hi).to(torch.bfloat16).float()
+
+    def lin_split(W, prefix, x):
+        w, b = W[prefix + ".weight"], W[prefix + ".bias"]
+        (xh, xl), (wh, wl) = split(x), split(w)
+        return xh @ wh.T + xl @ wh.T + xh @ wl.T + b
+
+    def lin_bf16(W, prefix, x):
+        return x.to(torch.bfloat16).float() @ W[prefix + ".weight"].to(torch.bfloat16).float().T + W[prefix + ".bias"]
+
+    args = [torch.from_numpy(golden["A/" + k]) for k in ("s_cur", "s_delta", "dens")]
+    a = torch.zeros(args[0].shape[:2])
+    ref = O.predict_one_step(golden_weights, 0.08, a, args[0], args[1], args[2])
+    scale = float(ref.norm())
+    monkeypatch.setattr(O, "_lin", lin_split)
+    out = O.predict_one_step(golden_weights, 0.08, a, args[0], args[1], args[2])
+    assert float((out - ref).norm()) / scale < 1e-5
+    assert float((out - ref).abs().max()) < 2e-5
+    monkeypatch.setattr(O, "_lin", lin_bf16)
+    single = O.predict_one_step(golden_weights, 0.08, a, args[0], args[1], args[2])
+    assert float((single - ref).abs().max()) > 10 * float((out - ref).abs().max())
