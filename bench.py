@@ -272,8 +272,8 @@ def main():
         s_out = torch.empty(samples, N, 3, device=dev)
         wpack = model.model.packed_weights(dev)
         _lib.check(lib.pile_profile_step(_lib.ptr(wpack), _lib.ptr(eng.attr), _lib.ptr(eng.dens), _lib.ptr(eng.s0),
-                                         _lib.ptr(pool_dev[0]), T * 4, _lib.host_floats(planner.cam12),
-                                         float(planner.global_scale), 0.08, samples, N, _lib.ptr(eng.scratch),
+                                         _lib.ptr(pool_dev[0]), T * 4, planner.pusher.ref(), 0.08, samples, N,
+                                         _lib.ptr(eng.scratch),
                                          _lib.ptr(s_out), 5, ms6, ops._stream()), "pile_profile_step")
         names = ["nbr_search", "node_encode", "edge_encode", "propagate0", "propagate1", "propagate2_predict"]
         kms = dict(zip(names, [float(v) for v in ms6]))

@@ -18,6 +18,15 @@ _F = C.c_float
 _LL = C.c_longlong
 _D = C.c_double
 
+
+class PusherStruct(C.Structure):
+    """`pile_pusher` of include/pile_gnn.h (HOST struct describing the frame of the push)."""
+    _fields_ = [("kind", C.c_int), ("cam_m12", C.c_float * 12), ("global_scale", C.c_float),
+                ("s2r_scale", C.c_float), ("wkspc_center_x", C.c_float), ("wkspc_center_y", C.c_float)]
+
+
+_PU = C.POINTER(PusherStruct)
+
 # name -> (restype, argtypes); mirrors include/pile_gnn.h one to one
 SIGNATURES = {
     "pile_abi_version": (_I, []),
@@ -31,22 +40,25 @@ SIGNATURES = {
     "pile_wpack_slot_offset": (_LL, [_I]),
     "pile_wpack_slot_size": (_LL, [_I]),
     "pile_wpack_total": (_LL, []),
-    "pile_gen_s_delta": (_I, [_P, _P, _I, _P, _F, _I, _I, _P, _P]),
-    "pile_gen_s_delta_backward": (_I, [_P, _P, _I, _P, _F, _I, _I, _P, _P, _P, _I, _P]),
+    "pile_gen_s_delta": (_I, [_P, _P, _I, _PU, _I, _I, _P, _P]),
+    "pile_gen_s_delta_backward": (_I, [_P, _P, _I, _PU, _I, _I, _P, _P, _P, _I, _P]),
     "pile_build_relations": (_I, [_P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "pile_step_scratch_bytes": (_LL, [_I, _I]),
     "pile_tape_step_bytes": (_LL, [_I, _I]),
     "pile_predict_step": (_I, [_P, _P, _P, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P]),
     "pile_forward_relations": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "pile_relations_view": (_I, [_P, _I, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
-    "pile_rollout_forward": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P, _P]),
-    "pile_profile_step": (_I, [_P, _P, _P, _P, _P, _I, _P, _F, _F, _I, _I, _P, _P, _I, _P, _P]),
+    "pile_rollout_forward": (_I, [_P, _P, _P, _P, _P, _PU, _F, _I, _I, _I, _P, _P, _P, _P]),
+    "pile_profile_step": (_I, [_P, _P, _P, _P, _P, _I, _PU, _F, _I, _I, _P, _P, _I, _P, _P]),
     "pile_bwd_scratch_bytes": (_LL, [_I, _I]),
     "pile_step_backward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
-    "pile_rollout_backward": (_I, [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "pile_rollout_backward": (_I, [_P, _P, _P, _P, _PU, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "pile_reward": (_I, [_P, _LL, _LL, _I, _P, _I, _I, _P, _I, _P, _F, _F, _I, _P, _P, _P]),
     "pile_reward_backward": (_I, [_P, _LL, _LL, _I, _P, _I, _I, _P, _I, _P, _F, _F, _I, _P, _P, _P, _LL, _I, _P]),
     "pile_adam_clamp": (_I, [_P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _P, _P, _P]),
+    "pile_adam_clamp_dev": (_I, [_P, _P, _P, _P, _LL, _P, _F, _F, _F, _F, _P, _P, _P]),
+    "pile_counter_add": (_I, [_P, _I, _P]),
+    "pile_gd_track": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "pile_fps": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "pile_fps_sets": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P]),
     "pile_depth_counts_len": (_I, [_I, _I]),
@@ -60,6 +72,7 @@ SIGNATURES = {
     "pile_mppi_combine": (_I, [_P, _I, _I, _P, _P]),
 }
 
+ABI_VERSION = 2          # PILE_ABI_VERSION of include/pile_gnn.h
 _lib = None
 
 
@@ -91,7 +104,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.pile_abi_version() != 1:
+    if lib.pile_abi_version() != ABI_VERSION:
         raise PileLibraryError("libpilegnn ABI version mismatch")
     _lib = lib
     return lib

@@ -85,13 +85,32 @@ TapeView carve_tape(void* p, int B, int N) {
   return v;
 }
 
-PushCam make_cam(const float* m12, float gs) {
-  PushCam c;
-  for (int i = 0; i < 12; ++i) c.m[i] = m12[i];
-  c.global_scale = gs;
-  c.pusher_w = 0.8f / 24.0f;   // planners.py:225
-  c.decay = 0.01f;             // planners.py:251
+PushCam make_cam(const pile_pusher* p) {
+  PushCam c{};
+  for (int i = 0; i < 12; ++i) c.m[i] = p->cam_m12[i];
+  c.global_scale = p->global_scale;
+  c.decay = 0.01f;             // planners.py:251 / :294
+  c.kind = p->kind;
+  if (p->kind == PILE_PUSHER_REAL) {
+    c.pusher_w = 0.048f;       // planners.py:279
+    c.s2r_scale = p->s2r_scale;
+    c.shift_x = p->wkspc_center_x;   // planners.py:271-272
+    c.shift_y = p->wkspc_center_y;
+    c.height = 0.88f;          // planners.py:276
+  } else {
+    c.pusher_w = 0.8f / 24.0f; // planners.py:225
+    c.s2r_scale = 1.f;
+    c.shift_x = c.shift_y = 0.f;
+    c.height = 0.f;
+  }
   return c;
+}
+
+inline bool bad_pusher(const pile_pusher* p) {
+  if (!p) return true;
+  if (p->kind == PILE_PUSHER_SIM) return !(p->global_scale != 0.f);
+  if (p->kind == PILE_PUSHER_REAL) return !(p->s2r_scale != 0.f);
+  return true;
 }
 
 inline bool bad_dims(int B, int N) { return B <= 0 || N <= 0 || nbr_smem_bytes(N) > 200 * 1024; }
@@ -106,11 +125,9 @@ int pile_max_relations(void) { return KMAX; }
 const char* pile_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
 
 int pile_set_tensor_cores(int enable) {
-  const int old = g_use_tensor_cores;
-  g_use_tensor_cores = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
-  return old;
+  return g_use_tensor_cores.exchange(enable < 0 ? 0 : (enable > 2 ? 2 : enable));
 }
-int pile_get_tensor_cores(void) { return g_use_tensor_cores; }
+int pile_get_tensor_cores(void) { return g_use_tensor_cores.load(); }
 
 int pile_debug_set_trace(long long* device_buf, int capacity, int which) {
   if (which == 2) return set_edge_tmem_trace(device_buf, capacity);
@@ -122,11 +139,11 @@ long long pile_wpack_slot_offset(int slot) { return (slot < 0 || slot > W_NUM) ?
 long long pile_wpack_slot_size(int slot) { return (slot < 0 || slot >= W_NUM) ? -1 : wslot_size(slot); }
 long long pile_wpack_total(void) { return wslot_offset(W_NUM); }
 
-int pile_gen_s_delta(const float* s_cur, const float* action, int act_stride, const float* cam_m12,
-                     float global_scale, int B, int N, float* s_delta, void* stream) {
-  if (B <= 0 || N <= 0 || !s_cur || !action || !cam_m12 || !s_delta) return (int)cudaErrorInvalidValue;
-  return launch_gen_s_delta(s_cur, (long long)N * 3, action, act_stride, make_cam(cam_m12, global_scale), B, N,
-                            s_delta, (cudaStream_t)stream);
+int pile_gen_s_delta(const float* s_cur, const float* action, int act_stride, const pile_pusher* pusher, int B,
+                     int N, float* s_delta, void* stream) {
+  if (B <= 0 || N <= 0 || !s_cur || !action || bad_pusher(pusher) || !s_delta) return (int)cudaErrorInvalidValue;
+  return launch_gen_s_delta(s_cur, (long long)N * 3, action, act_stride, make_cam(pusher), B, N, s_delta,
+                            (cudaStream_t)stream);
 }
 
 int pile_build_relations(const float* s_cur, const float* s_delta, const int* particle_nums, int B, int N,
@@ -177,13 +194,14 @@ int pile_predict_step(const float* wpack, const float* attr, const float* dens, 
 }
 
 int pile_rollout_forward(const float* wpack, const float* attr, const float* dens, const float* s0,
-                         const float* actions, const float* cam_m12, float global_scale, float adj_thresh,
-                         int B, int N, int T, void* scratch, void* tape, float* states, void* stream) {
-  if (bad_dims(B, N) || T <= 0 || !wpack || !attr || !dens || !s0 || !actions || !cam_m12 || !scratch || !states)
+                         const float* actions, const pile_pusher* pusher, float adj_thresh, int B, int N, int T,
+                         void* scratch, void* tape, float* states, void* stream) {
+  if (bad_dims(B, N) || T <= 0 || !wpack || !attr || !dens || !s0 || !actions || bad_pusher(pusher) || !scratch ||
+      !states)
     return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   ScratchView sv = carve_scratch(scratch, B, N);
-  const PushCam cam = make_cam(cam_m12, global_scale);
+  const PushCam cam = make_cam(pusher);
   const size_t tape_step = carve_tape(nullptr, B, N).bytes;
   const long long sstride = (long long)T * N * 3;
   const bool tc = g_use_tensor_cores != 0;      // the tensor engine takes its relation rows from the search kernel
@@ -229,12 +247,12 @@ int pile_forward_relations(const float* wpack, const float* attr, const float* d
                         s_pred, (long long)N * 3, B, N, st);
 }
 
-int pile_gen_s_delta_backward(const float* s_cur, const float* action, int act_stride, const float* cam_m12,
-                              float global_scale, int B, int N, const float* g_s_delta, float* g_s_cur,
-                              float* g_action, int g_act_stride, void* stream) {
-  if (B <= 0 || N <= 0 || !s_cur || !action || !cam_m12 || !g_s_delta || !g_s_cur || !g_action)
+int pile_gen_s_delta_backward(const float* s_cur, const float* action, int act_stride, const pile_pusher* pusher,
+                              int B, int N, const float* g_s_delta, float* g_s_cur, float* g_action,
+                              int g_act_stride, void* stream) {
+  if (B <= 0 || N <= 0 || !s_cur || !action || bad_pusher(pusher) || !g_s_delta || !g_s_cur || !g_action)
     return (int)cudaErrorInvalidValue;
-  return launch_gen_s_delta_bwd(s_cur, (long long)N * 3, action, act_stride, make_cam(cam_m12, global_scale), B, N,
+  return launch_gen_s_delta_bwd(s_cur, (long long)N * 3, action, act_stride, make_cam(pusher), B, N,
                                 g_s_delta, g_s_cur, (long long)N * 3, g_action, g_act_stride, (cudaStream_t)stream);
 }
 
@@ -257,15 +275,14 @@ BwdView carve_bwd_view(void* p, int B, int N) {
 }  // namespace
 
 int pile_profile_step(const float* wpack, const float* attr, const float* dens, const float* s_cur,
-                      const float* action, int act_stride, const float* cam_m12, float global_scale,
-                      float adj_thresh, int B, int N, void* scratch, float* s_out, int reps, float* ms_out,
-                      void* stream) {
-  if (bad_dims(B, N) || reps <= 0 || !wpack || !attr || !dens || !s_cur || !action || !cam_m12 || !scratch ||
-      !s_out || !ms_out)
+                      const float* action, int act_stride, const pile_pusher* pusher, float adj_thresh, int B,
+                      int N, void* scratch, float* s_out, int reps, float* ms_out, void* stream) {
+  if (bad_dims(B, N) || reps <= 0 || !wpack || !attr || !dens || !s_cur || !action || bad_pusher(pusher) ||
+      !scratch || !s_out || !ms_out)
     return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   ScratchView sv = carve_scratch(scratch, B, N);
-  const PushCam cam = make_cam(cam_m12, global_scale);
+  const PushCam cam = make_cam(pusher);
   constexpr int NK = 3 + PSTEP;   // nbr, node_encode, edge_encode, propagate x3
   cudaEvent_t ev[NK + 1];
   for (auto& e : ev) cudaEventCreate(&e);
@@ -308,15 +325,14 @@ int pile_step_backward(const float* wpack, const float* dens, const void* tape, 
 }
 
 int pile_rollout_backward(const float* wpack, const float* dens, const float* s0, const float* actions,
-                          const float* cam_m12, float global_scale, int B, int N, int T, const void* tape,
-                          const float* states, float* g_states, void* bwd_scratch, float* g_actions,
-                          void* stream) {
+                          const pile_pusher* pusher, int B, int N, int T, const void* tape, const float* states,
+                          float* g_states, void* bwd_scratch, float* g_actions, void* stream) {
   (void)dens;
-  if (bad_dims(B, N) || T <= 0 || !wpack || !s0 || !actions || !cam_m12 || !tape || !states || !g_states ||
+  if (bad_dims(B, N) || T <= 0 || !wpack || !s0 || !actions || bad_pusher(pusher) || !tape || !states || !g_states ||
       !bwd_scratch || !g_actions)
     return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
-  const PushCam cam = make_cam(cam_m12, global_scale);
+  const PushCam cam = make_cam(pusher);
   const size_t tape_step = carve_tape(nullptr, B, N).bytes;
   const long long sstride = (long long)T * N * 3;
   BwdView bv = carve_bwd_view(bwd_scratch, B, N);
@@ -409,6 +425,30 @@ int pile_adam_clamp(float* actions, const float* grad, float* exp_avg, float* ex
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   return launch_adam_clamp(actions, grad, exp_avg, exp_avg_sq, n, beta1, beta2, (float)((double)lr / bc1),
                            (float)sqrt(bc2), eps, lo4, hi4, (cudaStream_t)stream);
+}
+
+int pile_adam_clamp_dev(float* actions, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                        const int* iter_dev, float lr, float beta1, float beta2, float eps, const float* lo4,
+                        const float* hi4, void* stream) {
+  if (!actions || !grad || !exp_avg || !exp_avg_sq || n <= 0 || (n & 3) || !iter_dev || !lo4 || !hi4)
+    return (int)cudaErrorInvalidValue;
+  return launch_adam_clamp_dev(actions, grad, exp_avg, exp_avg_sq, n, iter_dev, lr, beta1, beta2, eps, lo4, hi4,
+                               (cudaStream_t)stream);
+}
+
+int pile_counter_add(int* counter_dev, int delta, void* stream) {
+  if (!counter_dev) return (int)cudaErrorInvalidValue;
+  return launch_counter_add(counter_dev, delta, (cudaStream_t)stream);
+}
+
+int pile_gd_track(const float* reward, const float* actions, int n_sample, int n_batch, int T, float* max_reward,
+                  int* max_idx, float* best_actions, float* rew_mean, float* rew_std, const int* iter_dev,
+                  void* stream) {
+  if (!reward || !actions || n_sample <= 0 || n_batch <= 0 || T <= 0 || !max_reward || !max_idx || !best_actions ||
+      !rew_mean || !rew_std || !iter_dev)
+    return (int)cudaErrorInvalidValue;
+  return launch_gd_track(reward, actions, n_sample, n_batch, T, max_reward, max_idx, best_actions, rew_mean, rew_std,
+                         iter_dev, (cudaStream_t)stream);
 }
 
 int pile_mppi_num_chunks(int S) { return mppi_num_chunks(S); }

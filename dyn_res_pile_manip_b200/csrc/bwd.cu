@@ -427,14 +427,15 @@ static int set_smem_b(Kern k, size_t bytes) {
 int launch_step_backward(const float* wpack, const Csr& csr, const Masks& mk, const float* g_pred,
                          long long g_stride, float* g_s_cur, float* g_s_delta, void* scratch, int B, int N,
                          cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  const int once_dev = once.pending();
+  if (once_dev >= 0) {
     int e;
     if ((e = set_smem_b(k_bwd_head, sizeof(BwdHeadSmem)))) return e;
     if ((e = set_smem_b(k_bwd_prop<false>, sizeof(BwdPropSmem)))) return e;
     if ((e = set_smem_b(k_bwd_prop<true>, sizeof(BwdPropSmem)))) return e;
     if ((e = set_smem_b(k_bwd_edge, sizeof(BwdEdgeSmem)))) return e;
-    configured = true;
+    once.done(once_dev);
   }
   if (!csr.trowptr) return (int)cudaErrorInvalidValue;
   BwdScratch s = carve_bwd(scratch, B, N);

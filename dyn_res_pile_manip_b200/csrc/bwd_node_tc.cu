@@ -297,11 +297,12 @@ k_bwd_head_tc(const float* __restrict__ wpack, const float* __restrict__ g_pred,
 
 int launch_bwd_head_tc(const float* wpack, const float* g_pred, long long g_stride, const uint8_t* m_q,
                        const uint8_t* m_eff2, float* gz, float* gcp, float* gagg2, int B, int N, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  const int once_dev = once.pending();
+  if (once_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(k_bwd_head_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdHeadTcSmem));
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    once.done(once_dev);
   }
   const long long ntiles = ((long long)B * N + TILE - 1) / TILE;
   const int grid = (int)(ntiles < 1 ? 1 : (ntiles < NSM ? ntiles : NSM));
@@ -313,15 +314,16 @@ int launch_bwd_head_tc(const float* wpack, const float* g_pred, long long g_stri
 int launch_bwd_prop_tc(const float* wpack, bool first, const float* gpr, const float* gps, const uint8_t* m_next,
                        const uint8_t* m_pe0, float* gz, float* gcp, float* gagg_out, float* g_s_delta, int B, int N,
                        cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  const int once_dev = once.pending();
+  if (once_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(k_bwd_prop_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(BwdNodeTcSmem<false>));
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_bwd_prop_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(BwdNodeTcSmem<true>));
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    once.done(once_dev);
   }
   const long long ntiles = ((long long)B * N + TILE - 1) / TILE;
   const int grid = (int)(ntiles < 1 ? 1 : (ntiles < NSM ? ntiles : NSM));

@@ -146,12 +146,13 @@ k_bwd_edge_tc(const float* __restrict__ wpack, const int* __restrict__ rowptr, c
 
 int launch_bwd_edge_tc(const float* wpack, const Csr& csr, const Masks& mk, const float* ga0, const float* ga1,
                        const float* ga2, float* gx, int B, int N, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  const int once_dev = once.pending();
+  if (once_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(k_bwd_edge_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(BwdEdgeTcSmem));
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    once.done(once_dev);
   }
   const long long ntiles = (long long)B * ((KMAX * N + TILE - 1) / TILE);
   const long long want = (ntiles + TC_GROUPS - 1) / TC_GROUPS;

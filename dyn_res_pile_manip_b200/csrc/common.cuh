@@ -9,6 +9,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 
 namespace pile {
 
@@ -82,12 +83,32 @@ __host__ __device__ inline int wslot_offset(int s) {
   return o;
 }
 
-// camera / pusher constants handed to the s_delta kernels (planners.py:192-257)
+// pusher frame handed to the s_delta kernels: simulator (planners.py:192-257) or real robot (planners.py:259-300)
 struct PushCam {
-  float m[12];        // rows 0..2 of the 4x4 world->camera(OpenCV) matrix
-  float global_scale;
-  float pusher_w;     // 0.8/24
+  float m[12];        // kind 0: rows 0..2 of the 4x4 world->camera(OpenCV) matrix
+  float global_scale; // kind 0
+  float pusher_w;     // half width of the pusher: 0.8/24 (sim, planners.py:225) or 0.048 (real, planners.py:279)
   float decay;        // 0.01
+  int kind;           // 0 = simulator frame, 1 = real-robot frame
+  float s2r_scale;    // kind 1: action -> metres
+  float shift_x, shift_y;   // kind 1: workspace centre subtracted from the particles (0 for kind 0)
+  float height;       // kind 1: pusher height 0.88
+};
+
+// One-time kernel attribute setup (cudaFuncSetAttribute) is per DEVICE: every translation unit remembers which
+// devices it has configured.  Racing threads may configure a device twice, which is harmless.
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  // current device index if it still has to be configured, -1 otherwise
+  int pending() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+    if (d >= 0 && d < 64 && ((mask.load(std::memory_order_acquire) >> d) & 1ull)) return -1;
+    return d;
+  }
+  void done(int d) {
+    if (d >= 0 && d < 64) mask.fetch_or(1ull << d, std::memory_order_release);
+  }
 };
 
 #define PILE_CHECK_LAUNCH() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)

@@ -257,15 +257,16 @@ PILE_TRACE_SETTER(set_edge_trace)
 int launch_edge_encode_tc(const float* wpack, const float* attr, const float* dens, const float* s_cur,
                           long long s_stride, const Csr& csr, const Masks* mk, float* efeat, float* Ce, int B, int N,
                           cudaStream_t st, bool efeat_ready) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  const int once_dev = once.pending();
+  if (once_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(k_edge_encode_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(EdgeTcSmem));
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_edge_encode_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(EdgeTcSmem));
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    once.done(once_dev);
   }
   if (!efeat_ready) {          // relations that did not come from launch_nbr_search (which writes the rows itself)
     const dim3 fgrid((KMAX * N + 255) / 256, B);

@@ -306,15 +306,16 @@ PILE_TRACE_SETTER(set_edge_tmem_trace)
 
 int launch_edge_encode_tmem(const float* wpack, const float* efeat, const Csr& csr, const Masks* mk, float* Ce,
                             int B, int N, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  const int once_dev = once.pending();
+  if (once_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(k_edge_encode_tmem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(EdgeTmemSmem));
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_edge_encode_tmem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(EdgeTmemSmem));
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    once.done(once_dev);
   }
   const long long ntiles = (long long)B * ((KMAX * N + TILE - 1) / TILE);
   const long long want = (ntiles + TC_GROUPS - 1) / TC_GROUPS;

@@ -361,7 +361,7 @@ k_propagate(const float* __restrict__ wpack, const int* __restrict__ rowptr, con
   }
 }
 
-int g_use_tensor_cores = 2;   // default: tcgen05 tiles, relation encoder with A in tensor memory
+std::atomic<int> g_use_tensor_cores{2};   // default: tcgen05 tiles, relation encoder with A in tensor memory
 
 template <typename Kern>
 static int set_smem(Kern k, size_t bytes) {
@@ -372,14 +372,15 @@ int launch_forward(const float* wpack, const float* attr, const float* dens, con
                    long long s_cur_stride, const float* s_delta, const Csr& csr, const StepScratch& ws,
                    const Masks* mk, float* s_out, long long s_out_stride, int B, int N, cudaStream_t st,
                    cudaEvent_t* ev, bool efeat_ready) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  const int once_dev = once.pending();
+  if (once_dev >= 0) {
     int e;
     if ((e = set_smem(k_node_encode, sizeof(NodeEncSmem)))) return e;
     if ((e = set_smem(k_edge_encode, sizeof(EdgeEncSmem)))) return e;
     if ((e = set_smem(k_propagate<false>, sizeof(PropSmem)))) return e;
     if ((e = set_smem(k_propagate<true>, sizeof(PropSmem)))) return e;
-    configured = true;
+    once.done(once_dev);
   }
   const long long R = (long long)B * N;
   const int node_tiles = (int)((R + TILE - 1) / TILE);

@@ -61,7 +61,7 @@ int launch_forward(const float* wpack, const float* attr, const float* dens, con
 
 // process-wide switch: 0 = FP32 CUDA-core tiles, 1 = tcgen05 tiles with shared-memory activations,
 // 2 = 1 + relation encoder with the activation operand in tensor memory
-extern int g_use_tensor_cores;
+extern std::atomic<int> g_use_tensor_cores;
 int launch_edge_encode_tc(const float* wpack, const float* attr, const float* dens, const float* s_cur,
                           long long s_stride, const Csr& csr, const Masks* mk, float* efeat, float* Ce, int B, int N,
                           cudaStream_t st, bool efeat_ready = false);
@@ -109,6 +109,12 @@ int launch_recenter(const double* pcd, int m, const float* picks, int S, int N, 
 
 int launch_adam_clamp(float* p, const float* g, float* m, float* v, long long n, float b1, float b2, float step_size,
                       float bc2_sqrt, float eps, const float* lo4, const float* hi4, cudaStream_t st);
+int launch_adam_clamp_dev(float* p, const float* g, float* m, float* v, long long n, const int* iter_dev, float lr,
+                          float b1, float b2, float eps, const float* lo4, const float* hi4, cudaStream_t st);
+int launch_counter_add(int* counter, int delta, cudaStream_t st);
+int launch_gd_track(const float* reward, const float* acts, int n_sample, int n_batch, int T, float* max_reward,
+                    int* max_idx, float* best_actions, float* rew_mean, float* rew_std, const int* iter_dev,
+                    cudaStream_t st);
 int mppi_num_chunks(int S);
 int launch_mppi_partials(const float* reward, const float* acts, int S, int T, float weight, float* part,
                          cudaStream_t st);

@@ -22,11 +22,21 @@ __device__ __forceinline__ void cam_point(const PushCam& c, float wx, float wy, 
   z = __fdiv_rn(c.m[8] * wx + c.m[9] * wy + c.m[10] * wz + c.m[11], c.global_scale);
 }
 
-// planners.py:218-240: action (sx,sy,ex,ey) -> start/end in the camera frame, unit push direction
+// planners.py:218-240 (simulator) / :274-285 (real robot): action (sx,sy,ex,ey) -> start/end of the push in the
+// frame the particles live in, unit push direction
 __device__ __forceinline__ PushFrame make_push_frame(const PushCam& c, const float* __restrict__ act) {
   PushFrame f;
-  cam_point(c, act[0], 0.f, -act[1], f.sx, f.sy, f.sz);
-  cam_point(c, act[2], 0.f, -act[3], f.ex, f.ey, f.ez);
+  if (c.kind == 0) {
+    cam_point(c, act[0], 0.f, -act[1], f.sx, f.sy, f.sz);
+    cam_point(c, act[2], 0.f, -act[3], f.ex, f.ey, f.ez);
+  } else {
+    f.sx = __fdiv_rn(act[0], c.s2r_scale);
+    f.sy = -__fdiv_rn(act[1], c.s2r_scale);
+    f.ex = __fdiv_rn(act[2], c.s2r_scale);
+    f.ey = -__fdiv_rn(act[3], c.s2r_scale);
+    f.sz = c.height;
+    f.ez = c.height;
+  }
   const float dx = __fsub_rn(f.ex, f.sx), dy = __fsub_rn(f.ey, f.sy), dz = __fsub_rn(f.ez, f.sz);
   f.len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
   f.ux = __fdiv_rn(dx, f.len);
@@ -39,9 +49,12 @@ __device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx,
   return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
 }
 
-// planners.py:241-254 for one particle
+// planners.py:241-254 (:286-297 for the real robot, whose particles are first shifted by the workspace centre;
+// shift = 0 in the simulator frame and x - 0 is exact) for one particle
 __device__ __forceinline__ void push_delta(const PushCam& c, const PushFrame& f, float x, float y, float z,
                                            float& ox, float& oy, float& oz) {
+  x = __fsub_rn(x, c.shift_x);
+  y = __fsub_rn(y, c.shift_y);
   const float rx = __fsub_rn(x, f.sx), ry = __fsub_rn(y, f.sy), rz = __fsub_rn(z, f.sz);
   const float across = dot3_rn(rx, ry, rz, -f.uy, f.ux, 0.f);
   const float along = dot3_rn(rx, ry, rz, f.ux, f.uy, f.uz);
@@ -387,7 +400,7 @@ k_gen_s_delta_bwd(const float* __restrict__ s_cur, long long s_stride, const flo
   float gu[3] = {0.f, 0.f, 0.f}, ge[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f};
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const float* p = s_cur + (long long)b * s_stride + i * 3;
-    const float x = p[0], y = p[1], z = p[2];
+    const float x = p[0] - cam.shift_x, y = p[1] - cam.shift_y, z = p[2];
     const float* g = g_sd + ((size_t)b * N + i) * 3;
     const float g0 = g[0], g1 = g[1], g2 = g[2];
     const float rx = x - f.sx, ry = y - f.sy, rz = z - f.sz;
@@ -440,13 +453,22 @@ k_gen_s_delta_bwd(const float* __restrict__ s_cur, long long s_stride, const flo
     const float gp[3] = {(t[0] - f.ux * udg) / f.len, (t[1] - f.uy * udg) / f.len, (t[2] - f.uz * udg) / f.len};
     const float gE[3] = {t[3] + gp[0], t[4] + gp[1], t[5] + gp[2]};
     const float gS[3] = {t[6] - gp[0], t[7] - gp[1], t[8] - gp[2]};
-    // start = (M[:,0] a0 - M[:,2] a1 + M[:,3]) / gs ; end likewise with a2, a3
-    const float inv = 1.f / cam.global_scale;
     float* ga = g_action + (size_t)b * g_act_stride;
-    ga[0] = (gS[0] * cam.m[0] + gS[1] * cam.m[4] + gS[2] * cam.m[8]) * inv;
-    ga[1] = -(gS[0] * cam.m[2] + gS[1] * cam.m[6] + gS[2] * cam.m[10]) * inv;
-    ga[2] = (gE[0] * cam.m[0] + gE[1] * cam.m[4] + gE[2] * cam.m[8]) * inv;
-    ga[3] = -(gE[0] * cam.m[2] + gE[1] * cam.m[6] + gE[2] * cam.m[10]) * inv;
+    if (cam.kind == 0) {
+      // start = (M[:,0] a0 - M[:,2] a1 + M[:,3]) / gs ; end likewise with a2, a3
+      const float inv = 1.f / cam.global_scale;
+      ga[0] = (gS[0] * cam.m[0] + gS[1] * cam.m[4] + gS[2] * cam.m[8]) * inv;
+      ga[1] = -(gS[0] * cam.m[2] + gS[1] * cam.m[6] + gS[2] * cam.m[10]) * inv;
+      ga[2] = (gE[0] * cam.m[0] + gE[1] * cam.m[4] + gE[2] * cam.m[8]) * inv;
+      ga[3] = -(gE[0] * cam.m[2] + gE[1] * cam.m[6] + gE[2] * cam.m[10]) * inv;
+    } else {
+      // start = (a0 / s2r, -a1 / s2r, h) ; end likewise with a2, a3
+      const float inv = 1.f / cam.s2r_scale;
+      ga[0] = gS[0] * inv;
+      ga[1] = -gS[1] * inv;
+      ga[2] = gE[0] * inv;
+      ga[3] = -gE[1] * inv;
+    }
   }
 }
 
@@ -527,11 +549,12 @@ int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_del
                       float* efeat) {
   const size_t smem = nbr_smem_bytes(N);
   if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  const int dev = once.pending();
+  if (dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(k_nbr_search, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    once.done(dev);
   }
   int threads = (N + 31) / 32 * 32;
   threads = threads < 64 ? 64 : (threads > NBR_THREADS ? NBR_THREADS : threads);

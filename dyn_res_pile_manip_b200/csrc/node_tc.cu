@@ -451,8 +451,9 @@ static int tc_grid(long long ntiles) {
 
 int launch_node_encode_tc(const float* wpack, const float* attr, const float* dens, const float* s_delta,
                           const Masks* mk, const StepScratch& ws, int B, int N, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  const int once_dev = once.pending();
+  if (once_dev >= 0) {
     int e;
     if ((e = set_smem_tc(k_node_encode_tc<false>, sizeof(NodeEncSmemTc)))) return e;
     if ((e = set_smem_tc(k_node_encode_tc<true>, sizeof(NodeEncSmemTc)))) return e;
@@ -464,7 +465,7 @@ int launch_node_encode_tc(const float* wpack, const float* attr, const float* de
     if ((e = set_smem_tc(k_edge_agg<true, false>, agg_smem_bytes<false>(false)))) return e;
     if ((e = set_smem_tc(k_edge_agg<false, true>, agg_smem_bytes<true>(true)))) return e;
     if ((e = set_smem_tc(k_edge_agg<true, true>, agg_smem_bytes<true>(false)))) return e;
-    configured = true;
+    once.done(once_dev);
   }
   const long long ntiles = ((long long)B * N + TILE - 1) / TILE;
   if (mk)

@@ -266,11 +266,12 @@ k_recenter(const double* __restrict__ pcd, int m, const float* __restrict__ pick
 
 int launch_cover_radius(const double* pcd, int m, const float* picks, int S, int N, double* radius, cudaStream_t st) {
   if (m <= 0 || S <= 0 || N <= 0 || (size_t)N * 24 > 96 * 1024) return (int)cudaErrorInvalidValue;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce once;
+  const int once_dev = once.pending();
+  if (once_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(k_cover_radius, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr = true;
+    once.done(once_dev);
   }
   k_cover_radius<<<S, OBS_BLOCK, (size_t)N * 24, st>>>(pcd, m, picks, N, radius);
   PILE_CHECK_LAUNCH();

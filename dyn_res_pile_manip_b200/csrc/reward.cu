@@ -98,10 +98,31 @@ k_reward(const float* __restrict__ states, long long state_stride, int N, const 
   if (threadIdx.x == 0) reward[s] = -(normalize ? total / (float)N : total);
 }
 
+// Both kernels keep the projected particles (and the backward the arg-min table, M = 5N ints) in dynamic shared
+// memory: 28 N bytes for the backward, so the default 48 KB would stop at N = 1755 although the relation search
+// accepts N up to ~2690; raise the limit once per device.
+constexpr size_t RW_MAX_SMEM = 160 * 1024;
+__global__ void k_reward_bwd(const float*, long long, int, const float*, int, int, const float*, int, float, float, float,
+                             float, float, float, int, const float*, const int*, float*, long long, int);
+static int reward_configure() {
+  static DeviceOnce once;
+  const int dev = once.pending();
+  if (dev < 0) return 0;
+  cudaError_t e = cudaFuncSetAttribute(k_reward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RW_MAX_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_reward_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RW_MAX_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  once.done(dev);
+  return 0;
+}
+
 int launch_reward(const float* states, long long n_states, long long state_stride, int N, const float* goal_img,
                   int Hh, int Ww, const float* goal_coor, int M, float fx, float fy, float cx, float cy,
                   float off_x, float off_y, int normalize, float* reward, int* argmin_out, cudaStream_t st) {
   if (n_states <= 0) return 0;
+  int e = reward_configure();
+  if (e) return e;
+  if (2 * (size_t)N * sizeof(float) > RW_MAX_SMEM) return (int)cudaErrorInvalidValue;
   k_reward<<<(unsigned)n_states, RW_THREADS, 2 * N * sizeof(float), st>>>(
       states, state_stride, N, goal_img, Hh, Ww, goal_coor, M, fx, fy, cx, cy, off_x, off_y, normalize, reward,
       argmin_out);
@@ -178,7 +199,9 @@ int launch_reward_bwd(const float* states, long long n_states, long long state_s
                       float* g_states, long long g_stride, int accumulate, cudaStream_t st) {
   if (n_states <= 0) return 0;
   const size_t smem = 2 * N * sizeof(float) + M * sizeof(int);
-  if (smem > 48 * 1024) return (int)cudaErrorInvalidValue;
+  if (smem > RW_MAX_SMEM) return (int)cudaErrorInvalidValue;
+  int e = reward_configure();
+  if (e) return e;
   k_reward_bwd<<<(unsigned)n_states, RW_THREADS, smem, st>>>(
       states, state_stride, N, goal_img, Hh, Ww, goal_coor, M, fx, fy, cx, cy, off_x, off_y, normalize, g_reward,
       argmin_in, g_states, g_stride, accumulate);

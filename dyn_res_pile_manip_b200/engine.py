@@ -43,6 +43,7 @@ class RolloutEngine:
             self.set_goal(goal, goal_coor)
         self._graph = None
         self._wpack = None
+        self._mode = None
 
     # ---- inputs ---------------------------------------------------------------------------------
     def set_goal(self, goal, goal_coor=None):
@@ -74,15 +75,16 @@ class RolloutEngine:
 
     def _enqueue(self):
         p = self.planner
-        ops.rollout_forward_raw(self._wpack, self.attr, self.dens, self.s0, self.actions, p.cam12, p.global_scale,
+        ops.rollout_forward_raw(self._wpack, self.attr, self.dens, self.s0, self.actions, p.pusher,
                                 self.model_dy.adj_thresh, self.scratch, None, out=self.states)
         if self.goal_img is not None:
             N, T = self.N, self.T
             last = self.states[:, T - 1]
             lib = _lib.load()
+            off = p.reward_offset()
             _lib.check(lib.pile_reward(_lib.ptr(last), self.rows, T * N * 3, N, _lib.ptr(self.goal_img),
                                        self.goal_img.shape[0], self.goal_img.shape[1], _lib.ptr(self.goal_coor),
-                                       self.goal_coor.shape[0], _lib.host_floats(p.cam_params), 0.0, 0.0, 1,
+                                       self.goal_coor.shape[0], _lib.host_floats(p.cam_params), off[0], off[1], 1,
                                        _lib.ptr(self.reward), None, ops._stream()), "pile_reward")
             _lib.check(lib.pile_mppi_partials(_lib.ptr(self.reward), _lib.ptr(self.actions), self.rows, T,
                                               float(self.reward_weight), _lib.ptr(self._parts), ops._stream()),
@@ -93,8 +95,10 @@ class RolloutEngine:
     def evaluate(self):
         """Roll `self.actions` out from `self.s0`; fills states, reward (last step) and the MPPI record."""
         wpack = self.model_dy.model.packed_weights(self.device)
-        if self._wpack is None or self._wpack.data_ptr() != wpack.data_ptr():
-            self._wpack, self._graph = wpack, None
+        mode = _lib.load().pile_get_tensor_cores()
+        # a captured graph keeps the weights buffer and the GEMM engine it was captured with
+        if self._wpack is None or self._wpack.data_ptr() != wpack.data_ptr() or mode != self._mode:
+            self._wpack, self._graph, self._mode = wpack, None, mode
         if not self.use_graph:
             self._enqueue()
             return

@@ -155,6 +155,41 @@ def cam_matrix12(cam_extrinsic):
     return [float(np.float32(v)) for v in m[:3].reshape(-1)]
 
 
+class Pusher:
+    """Frame of the push handed to the pusher-model kernels (`pile_pusher`, include/pile_gnn.h).
+
+    `Pusher.sim(cam_extrinsic, global_scale)`: the simulator's camera frame (planners.py:192-257);
+    `Pusher.real(s2r_scale, wkspc_center_x, wkspc_center_y)`: the real robot (gen_s_delta_irl, planners.py:259-300)."""
+
+    def __init__(self, kind, cam12=None, global_scale=1.0, s2r_scale=1.0, center=(0.0, 0.0)):
+        self.kind = int(kind)
+        self.cam12 = [0.0] * 12 if cam12 is None else [float(v) for v in cam12]
+        self.global_scale = float(global_scale)
+        self.s2r_scale = float(s2r_scale)
+        self.center = (float(center[0]), float(center[1]))
+        st = _lib.PusherStruct()
+        st.kind = self.kind
+        for i, v in enumerate(self.cam12):
+            st.cam_m12[i] = v
+        st.global_scale, st.s2r_scale = self.global_scale, self.s2r_scale
+        st.wkspc_center_x, st.wkspc_center_y = self.center
+        self.struct = st
+
+    @staticmethod
+    def sim(cam_extrinsic, global_scale):
+        return Pusher(0, cam_matrix12(cam_extrinsic), global_scale)
+
+    @staticmethod
+    def real(s2r_scale, wkspc_center_x, wkspc_center_y):
+        return Pusher(1, None, 1.0, s2r_scale, (wkspc_center_x, wkspc_center_y))
+
+    def ref(self):
+        return C.byref(self.struct)
+
+    def signature(self):
+        return (self.kind, tuple(self.cam12), self.global_scale, self.s2r_scale, self.center)
+
+
 @dataclass
 class Relations:
     """Compact relation lists of a batch: the Rr/Rs-equivalent (SURVEY.md §8b 'Forward')."""
@@ -213,71 +248,78 @@ class Relations:
 
 
 class Workspace:
-    """Per-(B,N) device scratch reused across calls (the library never allocates)."""
+    """Device scratch reused across calls (the library never allocates).  The dynamic-resolution MPC loop changes
+    the particle count every step, so only the few most recently used (B, N) sizes are kept: anything older is
+    dropped (a holder such as RolloutEngine or a captured planner loop keeps its own reference alive)."""
+    KEEP = 3
 
     def __init__(self):
         self._scratch = {}
         self._bwd = {}
 
-    def scratch(self, B, N, device):
-        key = (B, N, str(device))
-        if key not in self._scratch:
-            n = _lib.load().pile_step_scratch_bytes(B, N)
+    def _get(self, cache, key, nbytes_fn):
+        hit = cache.pop(key, None)
+        if hit is None:
+            n = nbytes_fn(key[0], key[1])
             if n < 0:
-                raise _lib.PileLibraryError("unsupported sizes B=%d N=%d" % (B, N))
-            self._scratch[key] = torch.empty(n, dtype=torch.uint8, device=device)
-        return self._scratch[key]
+                raise _lib.PileLibraryError("unsupported sizes B=%d N=%d" % (key[0], key[1]))
+            while len(cache) >= self.KEEP:
+                cache.pop(next(iter(cache)))            # least recently used first (dict keeps insertion order)
+            hit = torch.empty(n, dtype=torch.uint8, device=key[2])
+        cache[key] = hit
+        return hit
+
+    def scratch(self, B, N, device):
+        return self._get(self._scratch, (int(B), int(N), str(device)), _lib.load().pile_step_scratch_bytes)
 
     def bwd(self, B, N, device):
-        key = (B, N, str(device))
-        if key not in self._bwd:
-            n = _lib.load().pile_bwd_scratch_bytes(B, N)
-            self._bwd[key] = torch.empty(n, dtype=torch.uint8, device=device)
-        return self._bwd[key]
+        return self._get(self._bwd, (int(B), int(N), str(device)), _lib.load().pile_bwd_scratch_bytes)
 
 
 def new_tape(B, N, T, device):
     n = _lib.load().pile_tape_step_bytes(B, N)
+    if n < 0:
+        raise _lib.PileLibraryError("unsupported sizes B=%d N=%d" % (B, N))
     return torch.empty(n * T, dtype=torch.uint8, device=device)
 
 
-def gen_s_delta_raw(s_cur, action, cam12, global_scale):
+def gen_s_delta_raw(s_cur, action, pusher):
     _require_cuda(s_cur, "s_cur")
     B, N, _ = s_cur.shape
     out = torch.empty_like(s_cur)
-    _lib.check(_lib.load().pile_gen_s_delta(_lib.ptr(s_cur), _lib.ptr(action), action.stride(0), _lib.host_floats(cam12),
-                                            float(global_scale), B, N, _lib.ptr(out), _stream()), "pile_gen_s_delta")
+    _lib.check(_lib.load().pile_gen_s_delta(_lib.ptr(s_cur), _lib.ptr(action), action.stride(0), pusher.ref(), B, N,
+                                            _lib.ptr(out), _stream()), "pile_gen_s_delta")
     return out
 
 
-def gen_s_delta_backward_raw(s_cur, action, cam12, global_scale, g_sd):
+def gen_s_delta_backward_raw(s_cur, action, pusher, g_sd):
     B, N, _ = s_cur.shape
     g_s = torch.zeros_like(s_cur)
     g_a = torch.empty(B, 4, dtype=torch.float32, device=s_cur.device)
     _lib.check(_lib.load().pile_gen_s_delta_backward(
-        _lib.ptr(s_cur), _lib.ptr(action), action.stride(0), _lib.host_floats(cam12), float(global_scale), B, N,
-        _lib.ptr(g_sd), _lib.ptr(g_s), _lib.ptr(g_a), 4, _stream()), "pile_gen_s_delta_backward")
+        _lib.ptr(s_cur), _lib.ptr(action), action.stride(0), pusher.ref(), B, N, _lib.ptr(g_sd), _lib.ptr(g_s),
+        _lib.ptr(g_a), 4, _stream()), "pile_gen_s_delta_backward")
     return g_s, g_a
 
 
 class _GenSDelta(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, s_cur, action, cam12, global_scale):
+    def forward(ctx, s_cur, action, pusher):
         s_cur, action = _f32(s_cur), _f32(action)
         ctx.save_for_backward(s_cur, action)
-        ctx.cam12, ctx.gs = cam12, global_scale
-        return gen_s_delta_raw(s_cur, action, cam12, global_scale)
+        ctx.pusher = pusher
+        return gen_s_delta_raw(s_cur, action, pusher)
 
     @staticmethod
     def backward(ctx, g):
         s_cur, action = ctx.saved_tensors
-        g_s, g_a = gen_s_delta_backward_raw(s_cur, action, ctx.cam12, ctx.gs, _f32(g))
-        return g_s, g_a, None, None
+        g_s, g_a = gen_s_delta_backward_raw(s_cur, action, ctx.pusher, _f32(g))
+        return g_s, g_a, None
 
 
-def gen_s_delta(s_cur, action, cam12, global_scale):
-    """Differentiable pusher model (planners.py:211-257)."""
-    return _GenSDelta.apply(s_cur, action, cam12, global_scale)
+def gen_s_delta(s_cur, action, pusher):
+    """Differentiable pusher model (planners.py:211-257; :259-300 for a real-robot `pusher`)."""
+    return _GenSDelta.apply(s_cur, action, pusher)
 
 
 def build_relations(s_cur, s_delta, adj_thresh, particle_nums=None):
@@ -338,33 +380,35 @@ def step_backward_raw(wpack, dens, tape, B, N, g_pred, bwd_scratch):
     return g_s, g_sd
 
 
-def rollout_forward_raw(wpack, attr, dens, s0, actions, cam12, global_scale, adj_thresh, scratch, tape, out=None):
+def rollout_forward_raw(wpack, attr, dens, s0, actions, pusher, adj_thresh, scratch, tape, out=None):
     B, N, _ = s0.shape
     T = actions.shape[1]
     if out is None:
         out = torch.empty(B, T, N, 3, dtype=torch.float32, device=s0.device)
     _lib.check(_lib.load().pile_rollout_forward(
-        _lib.ptr(wpack), _lib.ptr(attr), _lib.ptr(dens), _lib.ptr(s0), _lib.ptr(actions), _lib.host_floats(cam12),
-        float(global_scale), float(adj_thresh), B, N, T, _lib.ptr(scratch), _lib.ptr(tape), _lib.ptr(out), _stream()),
+        _lib.ptr(wpack), _lib.ptr(attr), _lib.ptr(dens), _lib.ptr(s0), _lib.ptr(actions), pusher.ref(),
+        float(adj_thresh), B, N, T, _lib.ptr(scratch), _lib.ptr(tape), _lib.ptr(out), _stream()),
         "pile_rollout_forward")
     return out
 
 
-def rollout_backward_raw(wpack, dens, s0, actions, cam12, global_scale, tape, states, g_states, bwd_scratch):
+def rollout_backward_raw(wpack, dens, s0, actions, pusher, tape, states, g_states, bwd_scratch, out=None):
     B, T, N, _ = states.shape
-    g_act = torch.empty(B, T, 4, dtype=torch.float32, device=states.device)
+    g_act = out if out is not None else torch.empty(B, T, 4, dtype=torch.float32, device=states.device)
     _lib.check(_lib.load().pile_rollout_backward(
-        _lib.ptr(wpack), _lib.ptr(dens), _lib.ptr(s0), _lib.ptr(actions), _lib.host_floats(cam12), float(global_scale),
-        B, N, T, _lib.ptr(tape), _lib.ptr(states), _lib.ptr(g_states), _lib.ptr(bwd_scratch), _lib.ptr(g_act),
+        _lib.ptr(wpack), _lib.ptr(dens), _lib.ptr(s0), _lib.ptr(actions), pusher.ref(), B, N, T, _lib.ptr(tape), _lib.ptr(states), _lib.ptr(g_states), _lib.ptr(bwd_scratch), _lib.ptr(g_act),
         _stream()), "pile_rollout_backward")
     return g_act
 
 
-def reward_raw(states, n_states, state_stride, N, goal_img, goal_coor, cam_params, offset, normalize, want_argmin=False):
+def reward_raw(states, n_states, state_stride, N, goal_img, goal_coor, cam_params, offset, normalize, want_argmin=False,
+               out=None, arg=None):
     M = goal_coor.shape[0]
     Hh, Ww = goal_img.shape
-    out = torch.empty(n_states, dtype=torch.float32, device=goal_img.device)
-    arg = torch.empty(n_states, M, dtype=torch.int32, device=goal_img.device) if want_argmin else None
+    if out is None:
+        out = torch.empty(n_states, dtype=torch.float32, device=goal_img.device)
+    if arg is None and want_argmin:
+        arg = torch.empty(n_states, M, dtype=torch.int32, device=goal_img.device)
     _lib.check(_lib.load().pile_reward(_lib.ptr(states), n_states, state_stride, N, _lib.ptr(goal_img), Hh, Ww,
                                        _lib.ptr(goal_coor), M, _lib.host_floats(cam_params), float(offset[0]),
                                        float(offset[1]), int(bool(normalize)), _lib.ptr(out), _lib.ptr(arg), _stream()),
@@ -426,3 +470,23 @@ def adam_clamp(actions, grad, exp_avg, exp_avg_sq, step, lr, lo4, hi4, betas=(0.
                                            actions.numel(), int(step), float(lr), float(betas[0]), float(betas[1]),
                                            float(eps), _lib.host_floats(lo4), _lib.host_floats(hi4), _stream()),
                "pile_adam_clamp")
+
+
+def adam_clamp_dev(actions, grad, exp_avg, exp_avg_sq, iter_dev, lr, lo4, hi4, betas=(0.9, 0.999), eps=1e-8):
+    """adam_clamp with the step number (= iter_dev[0] + 1) read on the device: graph-replayable."""
+    _lib.check(_lib.load().pile_adam_clamp_dev(_lib.ptr(actions), _lib.ptr(grad), _lib.ptr(exp_avg),
+                                               _lib.ptr(exp_avg_sq), actions.numel(), _lib.ptr(iter_dev), float(lr),
+                                               float(betas[0]), float(betas[1]), float(eps), _lib.host_floats(lo4),
+                                               _lib.host_floats(hi4), _stream()), "pile_adam_clamp_dev")
+
+
+def counter_add(counter, delta=1):
+    _lib.check(_lib.load().pile_counter_add(_lib.ptr(counter), int(delta), _stream()), "pile_counter_add")
+
+
+def gd_track(reward, actions, n_sample, n_batch, T, max_reward, max_idx, best_actions, rew_mean, rew_std, iter_dev):
+    """Per-iteration best tracking + reward statistics of the GD planner on the device (planners.py:721-740)."""
+    _lib.check(_lib.load().pile_gd_track(_lib.ptr(reward), _lib.ptr(actions), int(n_sample), int(n_batch), int(T),
+                                         _lib.ptr(max_reward), _lib.ptr(max_idx), _lib.ptr(best_actions),
+                                         _lib.ptr(rew_mean), _lib.ptr(rew_std), _lib.ptr(iter_dev), _stream()),
+               "pile_gd_track")

@@ -8,6 +8,7 @@ ships in pieces but never wires up).  All tensor work runs
 libpilegnn; torch provides memory, streams, autograd glue and the process group.
 """
 import time
+from collections import OrderedDict
 
 import numpy as np
 import torch
@@ -40,21 +41,115 @@ class _RolloutFn(torch.autograd.Function):
         wpack = net.packed_weights(dev)
         scratch = net.workspace.scratch(Bt, N, dev)
         tape = ops.new_tape(Bt, N, T, dev) if need_grad else None
-        states = ops.rollout_forward_raw(wpack, attr, dens, s0, acts, planner.cam12, planner.global_scale,
-                                         model_dy.adj_thresh, scratch, tape)
-        ctx.saved = (wpack, dens, s0, acts, tape, states, planner, net)
+        states = ops.rollout_forward_raw(wpack, attr, dens, s0, acts, planner.pusher, model_dy.adj_thresh, scratch, tape)
+        # tensors go through save_for_backward (the output too: keeping it on ctx would be an output -> grad_fn ->
+        # ctx reference cycle that only the garbage collector frees, with the tape hanging off it)
+        if need_grad:
+            ctx.save_for_backward(wpack, dens, s0, acts, tape, states)
+        ctx.has_tape = need_grad
+        ctx.planner, ctx.net = planner, net
         return states
 
     @staticmethod
     def backward(ctx, g_states):
-        wpack, dens, s0, acts, tape, states, planner, net = ctx.saved
-        if tape is None:
+        if not ctx.has_tape:
             raise RuntimeError("rollout was recorded without a tape (actions did not require grad)")
+        wpack, dens, s0, acts, tape, states = ctx.saved_tensors
         Bt, T, N, _ = states.shape
         g = ops._f32(g_states).clone()          # consumed by the backward sweep
-        g_act = ops.rollout_backward_raw(wpack, dens, s0, acts, planner.cam12, planner.global_scale, tape, states, g,
-                                         net.workspace.bwd(Bt, N, states.device))
+        g_act = ops.rollout_backward_raw(wpack, dens, s0, acts, ctx.planner.pusher, tape, states, g,
+                                         ctx.net.workspace.bwd(Bt, N, states.device))
         return g_act, None, None, None, None, None
+
+
+class _GDLoop:
+    """Static device state of the GD planner's optimisation loop for one problem size.
+
+    Every buffer an iteration touches is allocated once, so the two halves of an iteration --
+    (rollout + last-step reward + best tracking) and (reward/rollout backward + Adam/clamp + counter) -- are
+    fixed launch sequences without a host-side value in them: they are captured as two CUDA graphs and replayed
+    n_iter times (two graphs so that the reference's rollout_time / optim_time split survives as event pairs
+    around the replays)."""
+    REW_CAP = 1024
+
+    def __init__(self, key, net, device):
+        rows, n_batch, N, T, M, Hh, Ww = key[:7]
+        self.key = key
+        self.rows, self.n_batch, self.N, self.T, self.M = rows, n_batch, N, T, M
+        f = dict(dtype=torch.float32, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
+        self.acts = torch.zeros(rows, T, 4, **f)
+        self.s0 = torch.zeros(rows, N, 3, **f)
+        self.dens = torch.ones(rows, **f)
+        self.attr = torch.zeros(rows, N, **f)
+        self.states = torch.zeros(rows, T, N, 3, **f)
+        self.g_states = torch.zeros(rows, T, N, 3, **f)
+        self.reward = torch.zeros(rows, **f)
+        self.argmin = torch.zeros(rows, M, **i32)
+        self.g_reward = torch.full((rows,), -1.0, **f)            # d(sum(-reward)) / d reward
+        self.g_act = torch.zeros(rows, T, 4, **f)
+        self.exp_avg = torch.zeros(rows, T, 4, **f)
+        self.exp_avg_sq = torch.zeros(rows, T, 4, **f)
+        self.goal_img = torch.zeros(Hh, Ww, **f)
+        self.goal_coor = torch.zeros(M, 2, **f)
+        self.max_reward = torch.zeros(n_batch, **f)
+        self.max_idx = torch.zeros(n_batch, **i32)
+        self.best_actions = torch.zeros(n_batch, T, 4, **f)
+        self.rew_mean = torch.zeros(self.REW_CAP, **f)
+        self.rew_std = torch.zeros(self.REW_CAP, **f)
+        self.iter = torch.zeros(1, **i32)
+        self.scratch = net.workspace.scratch(rows, N, device)
+        self.bwd_scratch = net.workspace.bwd(rows, N, device)
+        self.tape = ops.new_tape(rows, N, T, device)
+        self.sig = None
+        self.g_fwd = self.g_bwd = None
+
+    def reset(self, s0, dens, attr, acts, goal_img, goal_coor):
+        self.s0.copy_(s0); self.dens.copy_(dens); self.attr.copy_(attr); self.acts.copy_(acts)
+        self.goal_img.copy_(goal_img); self.goal_coor.copy_(goal_coor)
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.iter.zero_()
+        self.max_reward.fill_(-float('inf')); self.max_idx.zero_(); self.best_actions.zero_()
+
+    def _enqueue_fwd(self, c):
+        N, T = self.N, self.T
+        last = self.states[:, T - 1]                              # view: last-step states, stride T*N*3
+        ops.rollout_forward_raw(c['wpack'], self.attr, self.dens, self.s0, self.acts, c['pusher'], c['adj_thresh'],
+                                self.scratch, self.tape, out=self.states)
+        # the loss only looks at the last step (reward_seqs = next_r[:, -1], planners.py:438)
+        ops.reward_raw(last, self.rows, T * N * 3, N, self.goal_img, self.goal_coor, c['cam'], c['offset'], True,
+                       want_argmin=True, out=self.reward, arg=self.argmin)
+        # per state variant: keep the best trajectory seen so far (planners.py:721-727) + rew_mean / rew_std
+        ops.gd_track(self.reward, self.acts, self.rows // self.n_batch, self.n_batch, T, self.max_reward, self.max_idx,
+                     self.best_actions, self.rew_mean, self.rew_std, self.iter)
+
+    def _enqueue_bwd(self, c):
+        N, T = self.N, self.T
+        last = self.states[:, T - 1]
+        # loss = sum(-reward): only the last step has an upstream gradient; earlier slices accumulate the
+        # state gradients of the sweep and must start at zero
+        if T > 1:
+            self.g_states[:, :T - 1].zero_()
+        ops.reward_backward_raw(last, self.rows, T * N * 3, N, self.goal_img, self.goal_coor, c['cam'], c['offset'],
+                                True, self.g_reward, self.argmin, self.g_states[:, T - 1], T * N * 3, False)
+        ops.rollout_backward_raw(c['wpack'], self.dens, self.s0, self.acts, c['pusher'], self.tape, self.states,
+                                 self.g_states, self.bwd_scratch, out=self.g_act)
+        ops.adam_clamp_dev(self.acts, self.g_act, self.exp_avg, self.exp_avg_sq, self.iter, c['lr'], c['lo'], c['hi'])
+        ops.counter_add(self.iter, 1)
+
+    def ensure_captured(self, sig, c):
+        """(Re)capture when anything baked into the launches changed (weights buffer, engine, pusher, camera, box)."""
+        if self.sig == sig and self.g_fwd is not None:
+            return False
+        self._enqueue_fwd(c)                    # eager warm-up (one-time kernel attribute setup)
+        self._enqueue_bwd(c)
+        torch.cuda.synchronize()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            self._enqueue_fwd(c)
+        with torch.cuda.graph(g2):
+            self._enqueue_bwd(c)
+        self.g_fwd, self.g_bwd, self.sig = g1, g2, sig
+        return True
 
 
 class Planner(object):
@@ -84,12 +179,23 @@ class PlannerGD(Planner):
     def __init__(self, config, env):
         super(PlannerGD, self).__init__(config, env)
         if self.is_real:
-            raise NotImplementedError("real-robot pusher model (gen_s_delta_irl) is a SURVEY.md §8f 'next' row")
-        self.cam12 = ops.cam_matrix12(self.cam_extrinsic)
+            # real robot: the pusher model is gen_s_delta_irl (planners.py:259-300, dispatch :345-348)
+            self.pusher = ops.Pusher.real(self.env.s2r_scale, self.env.wkspc_center_x, self.env.wkspc_center_y)
+        else:
+            self.cam12 = ops.cam_matrix12(self.cam_extrinsic)
+            self.pusher = ops.Pusher.sim(self.cam_extrinsic, self.global_scale)
         self.goals = GoalCache()
         self.dist_group = None      # torch.distributed process group for sample-sharded planning
         self.device = torch.device('cuda')
         self._goal_coor_cache = {}
+        self._gd_loops = OrderedDict()      # captured optimisation loops, most recently used last
+        self.use_graph = True               # False: launch every iteration's kernels one by one (debugging)
+
+    def reward_offset(self):
+        """Pixel offset of the reward projection (planners.py:409-412): the real camera image is cropped."""
+        if self.env.is_real:
+            return (float(-self.env.crop_w_lower + self.env.crop_w_off), float(-self.env.crop_h_lower + self.env.crop_h_off))
+        return (0., 0.)
 
     # ---- workspace box (planners.py:150-155, 756-760) ---------------------------------------------
     def action_box(self, cvx_l=0):
@@ -156,7 +262,19 @@ class PlannerGD(Planner):
         assert s_cur.shape[1:] == (self.particle_num, 3)
         assert s_cur.shape[0] == action.shape[0]
         assert type(action) == torch.Tensor
-        return ops.gen_s_delta(s_cur, action, self.cam12, self.global_scale)
+        if self.is_real:
+            raise _lib.PileLibraryError("gen_s_delta needs the simulator camera; this planner was built for env.is_real")
+        return ops.gen_s_delta(s_cur, action, self.pusher)
+
+    def gen_s_delta_irl(self, s_cur: torch.Tensor, action: torch.Tensor):
+        """Real-robot pusher model (planners.py:259-300): reads env.wkspc_center_x/y and env.s2r_scale."""
+        assert type(s_cur) == torch.Tensor
+        assert s_cur.shape[1:] == (self.particle_num, 3)
+        assert s_cur.shape[0] == action.shape[0]
+        assert type(action) == torch.Tensor
+        pusher = self.pusher if self.is_real else ops.Pusher.real(self.env.s2r_scale, self.env.wkspc_center_x,
+                                                                  self.env.wkspc_center_y)
+        return ops.gen_s_delta(s_cur, action, pusher)
 
     # ---- rollout (planners.py:302-370) ---------------------------------------------------------------
     def ptcl_model_rollout(self, s_cur_tensor, s_param_tensor, a_cur_tensor, model_dy, act_seqs, enable_grad=True):
@@ -182,8 +300,8 @@ class PlannerGD(Planner):
         start.record()
         states = _RolloutFn.apply(act_seqs, self, model_dy, s0, dens, attr)
         end.record()
-        self._rollout_events = (start, end)
-        return {'model_rollout': {'state_pred': states}, 'rollout_time': _LazyMs(start, end)}
+        end.synchronize()          # the reference synchronises after every step (planners.py:357); here once
+        return {'model_rollout': {'state_pred': states}, 'rollout_time': start.elapsed_time(end)}
 
     # ---- reward (planners.py:372-452) -------------------------------------------------------------------
     def ptcl_evaluate_traj(self, obs_seqs, obs_goal, obs_goal_coor_tensor, debug=False, funnel_dist=None,
@@ -201,7 +319,7 @@ class PlannerGD(Planner):
         n_sample, n_look_ahead, cvx_num, _, _ = obs_seqs.shape
         obs_future = obs_seqs.reshape(n_sample * n_look_ahead * cvx_num, self.particle_num, 3)
         next_r = config_reward_ptcl(obs_future, obs_goal, cam_params=self.cam_params, goal_coor=obs_goal_coor_tensor,
-                                    normalize=normalize_rew, offset=(0, 0), cache=self.goals)
+                                    normalize=normalize_rew, offset=self.reward_offset(), cache=self.goals)
         next_r = next_r.reshape(n_sample, n_look_ahead, cvx_num)
         reward_seqs = next_r[:, -1]
         assert reward_seqs.shape == (n_sample, cvx_num)
@@ -244,89 +362,79 @@ class PlannerGD(Planner):
 
         n_iter = min(n_update_iter, int(time_lim * 1000.0 / particle_num_to_iter_time(self.particle_num))) \
             if time_lim != float('inf') else n_update_iter
+        n_iter = min(n_iter, _GDLoop.REW_CAP)
         rew_mean = np.zeros((1, n_update_iter * gd_loop), dtype=np.float32)
         rew_std = np.zeros((1, n_update_iter * gd_loop), dtype=np.float32)
-        rew_mean_d = torch.zeros(max(n_iter, 1), device=device)
-        rew_std_d = torch.zeros(max(n_iter, 1), device=device)
 
-        # ---- static device state of the optimisation (no autograd graph, no host sync inside the loop) --------
+        # ---- static device state of the optimisation: no autograd graph, no host-side value and no host sync
+        # inside an iteration, so each half of it is one CUDA-graph replay ------------------------------------
         N, T = self.particle_num, n_act
         rows = traj_num * n_batch                       # flat row = traj * n_batch + b  (planners.py:661-663)
         act_seqs = np.repeat(act_seq.transpose(1, 0, 2)[:, :, np.newaxis, :], n_batch, axis=0)
         act_seqs_tensor = torch.tensor(act_seqs, device=device, dtype=torch.float)     # [rows, T, 1, 4]
-        acts = act_seqs_tensor.view(rows, T, 4)
         net = model_dy.model
-        wpack = net.packed_weights(device)
-        scratch = net.workspace.scratch(rows, N, device)
-        bwd_scratch = net.workspace.bwd(rows, N, device)
-        tape = ops.new_tape(rows, N, T, device)
-        s0 = state_cur_tensor.repeat(traj_num, 1, 1).contiguous()
-        dens = state_param_tensor.repeat(traj_num).contiguous()
-        attr = attr_cur_tensor.repeat(traj_num, 1).contiguous()
-        states = torch.empty(rows, T, N, 3, device=device, dtype=torch.float)
-        g_states = torch.zeros(rows, T, N, 3, device=device, dtype=torch.float)
-        g_reward = torch.full((rows,), -1.0, device=device)        # d(sum(-reward)) / d reward
-        exp_avg = torch.zeros_like(acts)
-        exp_avg_sq = torch.zeros_like(acts)
-        goal_img = self.goals.shaped(obs_goal_tensor)
-        cam = [float(v) for v in self.cam_params]
-        lr = self.config['mpc']['gd']['lr']
-        reward_seqs_tensor = torch.ones((rows, 1), device=device, dtype=torch.float)
-        start = time.time()
-        max_reward = -float('inf') * torch.ones(n_batch, device=device, dtype=torch.float)
-        max_reward_traj_idx = torch.zeros(n_batch, device=device, dtype=torch.long)
-        best_actions_of_samples = torch.zeros((n_batch, n_act, self.action_dim), device=device, dtype=torch.float)
         lo, hi = self.action_box(0)
+        ctx = {'wpack': net.packed_weights(device), 'pusher': self.pusher, 'adj_thresh': model_dy.adj_thresh,
+               'cam': [float(v) for v in self.cam_params], 'offset': self.reward_offset(),
+               'lr': self.config['mpc']['gd']['lr'], 'lo': [float(v) for v in lo], 'hi': [float(v) for v in hi]}
+        sig = (ctx['wpack'].data_ptr(), _lib.load().pile_get_tensor_cores(), self.pusher.signature(),
+               float(model_dy.adj_thresh), tuple(ctx['cam']), ctx['offset'], float(ctx['lr']), tuple(ctx['lo']),
+               tuple(ctx['hi']))
+        start = time.time()
         timed = []
-        batch_ids = torch.arange(n_batch, device=device)
-        last = states[:, T - 1]                          # view: last-step states, stride T*N*3
-
-        i = -1
-        for i in range(n_iter):
-            e0, e1, e2, e3 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            e0.record()
-            try:
-                ops.rollout_forward_raw(wpack, attr, dens, s0, acts, self.cam12, self.global_scale,
-                                        model_dy.adj_thresh, scratch, tape, out=states)
-            except (_lib.PileLibraryError, torch.cuda.OutOfMemoryError):
-                print('OOM error')
-                break
-            e1.record()
-            # the loss only looks at the last step (reward_seqs = next_r[:, -1], planners.py:438)
-            reward, argmin = ops.reward_raw(last, rows, T * N * 3, N, goal_img, obs_goal_coor_tensor, cam, (0., 0.),
-                                            True, want_argmin=True)
-            reward_seqs_tensor = reward.view(n_sample, n_batch)
-            # per state variant: keep the best trajectory seen so far (planners.py:721-727), on device
-            cur_max, idx_best = torch.max(reward_seqs_tensor, dim=0)
-            better = cur_max > max_reward
-            max_reward = torch.where(better, cur_max, max_reward)
-            max_reward_traj_idx = torch.where(better, idx_best, max_reward_traj_idx)
-            picked = acts[idx_best * n_batch + batch_ids]
-            best_actions_of_samples = torch.where(better[:, None, None], picked, best_actions_of_samples)
-            rew_mean_d[i] = reward_seqs_tensor[:, 0].mean()
-            rew_std_d[i] = reward_seqs_tensor[:, 0].std()
-            e2.record()
-            try:
-                # loss = sum(-reward); backward through reward, T model steps and the pusher model; Adam; clamp
-                g_states.zero_()
-                ops.reward_backward_raw(last, rows, T * N * 3, N, goal_img, obs_goal_coor_tensor, cam, (0., 0.), True,
-                                        g_reward, argmin, g_states[:, T - 1], T * N * 3, False)
-                g_act = ops.rollout_backward_raw(wpack, dens, s0, acts, self.cam12, self.global_scale, tape, states,
-                                                 g_states, bwd_scratch)
-                ops.adam_clamp(acts, g_act, exp_avg, exp_avg_sq, i + 1, lr, lo, hi)
-            except (_lib.PileLibraryError, torch.cuda.OutOfMemoryError):
-                print('OOM error')
-                break
-            e3.record()
-            timed.append((e0, e1, e2, e3))
-
+        done = 0
+        loop = None
+        try:
+            M = int(obs_goal_coor_tensor.shape[0])
+            key = (rows, n_batch, N, T, M, int(obs_goal_tensor.shape[0]), int(obs_goal_tensor.shape[1]), str(device))
+            loop = self._gd_loops.pop(key, None)
+            if loop is None:
+                while len(self._gd_loops) >= 2:          # each loop owns a tape: keep the two most recent sizes
+                    self._gd_loops.popitem(last=False)
+                loop = _GDLoop(key, net, device)
+            self._gd_loops[key] = loop
+            goal_img = self.goals.shaped_np(obs_goal, obs_goal_tensor)
+            inputs = (state_cur_tensor.repeat(traj_num, 1, 1), state_param_tensor.repeat(traj_num),
+                      attr_cur_tensor.repeat(traj_num, 1), act_seqs_tensor.view(rows, T, 4), goal_img,
+                      obs_goal_coor_tensor)
+            loop.reset(*inputs)
+            if n_iter > 0 and self.use_graph and loop.ensure_captured(sig, ctx):
+                loop.reset(*inputs)                      # the capture's warm-up iteration moved the actions
+            for i in range(n_iter):
+                e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                e0.record()
+                if self.use_graph:
+                    loop.g_fwd.replay()
+                else:
+                    loop._enqueue_fwd(ctx)
+                e1.record()
+                if self.use_graph:
+                    loop.g_bwd.replay()
+                else:
+                    loop._enqueue_bwd(ctx)
+                e2.record()
+                timed.append((e0, e1, e2))
+                done = i + 1
+        except torch.cuda.OutOfMemoryError:
+            # the reference's loop prints this and keeps what it has (planners.py:694-696, 748-750); every other
+            # failure (bad sizes, launch errors) propagates as PileLibraryError
+            print('OOM error')
         torch.cuda.synchronize()
-        rollout_time = float(sum(a.elapsed_time(b) for a, b, _, _ in timed))
-        optim_time = float(sum(c.elapsed_time(d) for _, _, c, d in timed))
-        done = i + 1 if n_iter > 0 else 0
-        rew_mean[0, :done] = rew_mean_d[:done].cpu().numpy()
-        rew_std[0, :done] = rew_std_d[:done].cpu().numpy()
-        reward_seqs_tensor = reward_seqs_tensor.reshape(n_sample, n_batch)
+        i = done - 1
+        rollout_time = float(sum(a.elapsed_time(b) for a, b, _ in timed))
+        optim_time = float(sum(b.elapsed_time(c) for _, b, c in timed))
+        if loop is not None and done > 0:
+            rew_mean[0, :done] = loop.rew_mean[:done].cpu().numpy()
+            rew_std[0, :done] = loop.rew_std[:done].cpu().numpy()
+            reward_seqs_tensor = loop.reward.reshape(n_sample, n_batch)
+            act_seqs_tensor = loop.acts.view(rows, T, 1, 4)
+            max_reward, max_reward_traj_idx = loop.max_reward.clone(), loop.max_idx.long()
+            best_actions_of_samples = loop.best_actions.clone()
+        else:
+            reward_seqs_tensor = torch.ones((n_sample, n_batch), device=device, dtype=torch.float)
+            max_reward = -float('inf') * torch.ones(n_batch, device=device, dtype=torch.float)
+            max_reward_traj_idx = torch.zeros(n_batch, device=device, dtype=torch.long)
+            best_actions_of_samples = torch.zeros((n_batch, n_act, self.action_dim), device=device, dtype=torch.float)
 
         reward_seqs = reward_seqs_tensor.data.cpu().numpy()
         act_seqs = act_seqs_tensor.data.cpu().numpy()
@@ -478,28 +586,3 @@ def shard_bounds(n_sample, rank, world):
     """Contiguous slice of the sample dimension owned by `rank` (SURVEY.md §8e partitioning)."""
     per = shard_size(n_sample, world)
     return rank * per, (rank + 1) * per
-
-
-class _LazyMs(float):
-    """rollout_time in ms, resolved from CUDA events on first use (no host sync inside the hot loop)."""
-
-    def __new__(cls, start, end):
-        obj = float.__new__(cls, 0.0)
-        obj._ev = (start, end)
-        return obj
-
-    def _value(self):
-        s, e = self._ev
-        e.synchronize()
-        return s.elapsed_time(e)
-
-    def __float__(self):
-        return self._value()
-
-    def __add__(self, other):
-        return self._value() + float(other)
-
-    __radd__ = __add__
-
-    def __repr__(self):
-        return repr(self._value())

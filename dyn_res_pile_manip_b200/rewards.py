@@ -12,17 +12,42 @@ from . import ops
 
 
 class GoalCache:
-    """shaped goal image on the device, keyed by the goal tensor's storage + version."""
+    """Shaped goal image on the device, keyed by the goal's CONTENT.
+
+    A key made of (data_ptr, _version) is not enough: the planner builds a fresh goal tensor per call and the
+    caching allocator hands the next same-size goal the same address, so a different goal would hit the stale
+    entry.  The cache therefore keeps its own copy of the keyed goal; a lookup is a hit when it is handed the very
+    same tensor object at the same version (no sync), or a tensor that compares equal to the kept copy."""
 
     def __init__(self):
-        self._key = None
+        self._ref = None        # the tensor object the entry was built from (kept alive: its address cannot be reused)
+        self._version = None
+        self._copy = None       # private copy of its contents at that time
         self._img = None
+        self._np_key = None
 
     def shaped(self, goal):
-        key = (goal.data_ptr(), goal._version, tuple(goal.shape), str(goal.device))
-        if key != self._key:
-            self._img = shape_goal_image(goal)
-            self._key = key
+        if self._img is not None and self._copy is not None:
+            if goal is self._ref and goal._version == self._version:
+                return self._img
+            if goal.shape == self._copy.shape and goal.device == self._copy.device and goal.dtype == self._copy.dtype \
+                    and torch.equal(goal, self._copy):
+                self._ref, self._version = goal, goal._version
+                return self._img
+        self._img = shape_goal_image(goal)
+        self._ref, self._version, self._copy = goal, goal._version, goal.detach().clone()
+        self._np_key = None
+        return self._img
+
+    def shaped_np(self, goal_np, goal_tensor):
+        """Planner entry: the goal arrives as a numpy array, so the key is a hash of its bytes (as
+        PlannerGD.goal_coordinates does); `goal_tensor` is the same image already on the device."""
+        g = np.ascontiguousarray(goal_np)
+        key = (g.shape, str(g.dtype), str(goal_tensor.device), hash(g.tobytes()))
+        if self._img is None or key != self._np_key:
+            self._img = shape_goal_image(goal_tensor)
+            self._np_key = key
+            self._ref, self._version, self._copy = goal_tensor, goal_tensor._version, goal_tensor.detach().clone()
         return self._img
 
 

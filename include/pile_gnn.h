@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PILE_ABI_VERSION 1
+#define PILE_ABI_VERSION 2
 
 int pile_abi_version(void);
 int pile_nf_effect(void);        /* hidden width compiled in (config train.particle.nf_effect = 64) */
@@ -45,11 +45,24 @@ long long pile_wpack_slot_offset(int slot);   /* in floats */
 long long pile_wpack_slot_size(int slot);
 long long pile_wpack_total(void);
 
-/* ---- pusher model: replaces PlannerGD.world2cam + gen_s_delta (planners.py:192-257) -------------
- * action[b] = (sx, sy, ex, ey) at action + b*act_stride; cam_m12 = rows 0..2 of the 4x4 world->camera
- * matrix (HOST pointer, 12 floats). */
-int pile_gen_s_delta(const float* s_cur, const float* action, int act_stride, const float* cam_m12,
-                     float global_scale, int B, int N, float* s_delta, void* stream);
+/* ---- pusher model: replaces PlannerGD.world2cam + gen_s_delta (planners.py:192-257) and, for the real robot
+ * (env.is_real), gen_s_delta_irl (planners.py:259-300; dispatch at :345-348) -----------------------------------
+ * action[b] = (sx, sy, ex, ey) at action + b*act_stride.  The frame of the push is described by a HOST struct:
+ *   kind 0 (simulator): end points = cam_m12 * (a_x, 0, -a_y, 1) / global_scale with cam_m12 = rows 0..2 of the
+ *          4x4 world->camera matrix the reference rebuilds per call (planners.py:197-203); half width 0.8/24;
+ *   kind 1 (real robot): end points = (a_x / s2r_scale, -a_y / s2r_scale, 0.88), particles shifted by the
+ *          workspace centre (wkspc_center_x, wkspc_center_y, 0) before the projection; half width 0.048. */
+#define PILE_PUSHER_SIM 0
+#define PILE_PUSHER_REAL 1
+typedef struct pile_pusher {
+  int kind;
+  float cam_m12[12];
+  float global_scale;
+  float s2r_scale;
+  float wkspc_center_x, wkspc_center_y;
+} pile_pusher;
+int pile_gen_s_delta(const float* s_cur, const float* action, int act_stride, const pile_pusher* pusher /*HOST*/,
+                     int B, int N, float* s_delta, void* stream);
 
 /* ---- relation construction: replaces model/gnn_dyn.py:221-251 ------------------------------------
  * rowptr [B, N+1] (offsets local to the sample), col/row [B, 10*N] sender / receiver index; relations of
@@ -77,9 +90,9 @@ int pile_forward_relations(const float* wpack, const float* attr, const float* d
 int pile_step_backward(const float* wpack, const float* dens, const void* tape, int B, int N, const float* g_pred,
                        float* g_s_cur, float* g_s_delta, void* bwd_scratch, void* stream);
 /* backward of pile_gen_s_delta: g_s_cur += d/ds_cur, g_action[b] (at g_action + b*g_act_stride) = d/daction */
-int pile_gen_s_delta_backward(const float* s_cur, const float* action, int act_stride, const float* cam_m12,
-                              float global_scale, int B, int N, const float* g_s_delta, float* g_s_cur,
-                              float* g_action, int g_act_stride, void* stream);
+int pile_gen_s_delta_backward(const float* s_cur, const float* action, int act_stride, const pile_pusher* pusher,
+                              int B, int N, const float* g_s_delta, float* g_s_cur, float* g_action,
+                              int g_act_stride, void* stream);
 /* read the relation lists of a step back out of scratch (tape == NULL run) or tape */
 int pile_relations_view(void* scratch_or_tape, int is_tape, int B, int N, int** rowptr, int** col, int** row);
 
@@ -87,25 +100,23 @@ int pile_relations_view(void* scratch_or_tape, int is_tape, int B, int N, int** 
  * attr [B,N], dens [B], s0 [B,N,3], actions [B,T,4] -> states [B,T,N,3]; B is the already tiled
  * sample*state-variant batch (flat index = sample*n_batch + b).  tape (nullable): T * tape_step_bytes. */
 int pile_rollout_forward(const float* wpack, const float* attr, const float* dens, const float* s0,
-                         const float* actions, const float* cam_m12, float global_scale, float adj_thresh,
-                         int B, int N, int T, void* scratch, void* tape, float* states, void* stream);
+                         const float* actions, const pile_pusher* pusher, float adj_thresh, int B, int N, int T,
+                         void* scratch, void* tape, float* states, void* stream);
 
 /* measurement hook for bench.py's roofline line: runs one rollout step `reps` times with CUDA events
  * around each of its 6 kernels (relation search, node encode, relation encode, 3 x propagate) on `stream`,
  * SYNCHRONISES, and writes the mean milliseconds per kernel to ms_out (HOST, 6 floats). */
 int pile_profile_step(const float* wpack, const float* attr, const float* dens, const float* s_cur,
-                      const float* action, int act_stride, const float* cam_m12, float global_scale,
-                      float adj_thresh, int B, int N, void* scratch, float* s_out, int reps, float* ms_out,
-                      void* stream);
+                      const float* action, int act_stride, const pile_pusher* pusher, float adj_thresh, int B,
+                      int N, void* scratch, float* s_out, int reps, float* ms_out, void* stream);
 
 /* backward of the rollout w.r.t. the actions (dgrad only; relation sets and the hard along-push mask
  * carry no gradient, as in autograd: planners.py:742-745).  g_states [B,T,N,3] = dL/dstates (consumed,
  * overwritten), g_actions [B,T,4] out.  bwd_scratch: pile_bwd_scratch_bytes(B,N). */
 long long pile_bwd_scratch_bytes(int B, int N);
 int pile_rollout_backward(const float* wpack, const float* dens, const float* s0, const float* actions,
-                          const float* cam_m12, float global_scale, int B, int N, int T, const void* tape,
-                          const float* states, float* g_states, void* bwd_scratch, float* g_actions,
-                          void* stream);
+                          const pile_pusher* pusher, int B, int N, int T, const void* tape, const float* states,
+                          float* g_states, void* bwd_scratch, float* g_actions, void* stream);
 
 /* ---- reward: replaces config_reward_ptcl via ptcl_evaluate_traj (env/flex_rewards.py:156-214) ----
  * states: n_states blocks of [N,3], state_stride floats apart; goal_img [Hh,Ww] is the SHAPED image
@@ -125,6 +136,21 @@ int pile_reward_backward(const float* states, long long n_states, long long stat
  * update for 1-based `step`, then clamp component c to [lo4[c], hi4[c]] (HOST pointers). */
 int pile_adam_clamp(float* actions, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, int step,
                     float lr, float beta1, float beta2, float eps, const float* lo4, const float* hi4, void* stream);
+/* Same update with the 1-based step number read from DEVICE memory (step = *iter_dev + 1), so that one captured
+ * CUDA graph of a planner iteration can be replayed n_iter times; pile_counter_add advances the counter on the
+ * stream (planners.py:682 `for i in range(n_iter)`). */
+int pile_adam_clamp_dev(float* actions, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                        const int* iter_dev, float lr, float beta1, float beta2, float eps, const float* lo4,
+                        const float* hi4, void* stream);
+int pile_counter_add(int* counter_dev, int delta, void* stream);
+/* Per-iteration bookkeeping of the GD planner on the device (planners.py:721-740): reward [n_sample*n_batch] with
+ * row = sample*n_batch + b, actions [rows, T, 4] BEFORE the update.  For every state variant b: the best sample of
+ * this iteration (lowest index on ties); if it beats max_reward[b] (strictly) it replaces max_reward[b],
+ * max_idx[b] and best_actions[b, T, 4].  rew_mean[it] / rew_std[it] (it = *iter_dev) receive the mean and the
+ * unbiased standard deviation of reward[:, 0] over the samples. */
+int pile_gd_track(const float* reward, const float* actions, int n_sample, int n_batch, int T, float* max_reward,
+                  int* max_idx, float* best_actions, float* rew_mean, float* rew_std, const int* iter_dev,
+                  void* stream);
 
 /* ---- farthest-point sampling: replaces utils.fps_np (utils.py:451-466) as used for the goal pixels
  * (planners.py:620-624).  pts [n_sets, n, dim] (dim <= 3); per set: start at init_idx, take the farthest

@@ -23,7 +23,6 @@ ms6 = (_lib.C.c_float * 6)()
 s_out = torch.empty(B, N, 3, device="cuda")
 wpack = model.model.packed_weights(torch.device("cuda"))
 _lib.check(lib.pile_profile_step(_lib.ptr(wpack), _lib.ptr(eng.attr), _lib.ptr(eng.dens), _lib.ptr(eng.s0),
-                                 _lib.ptr(eng.actions), 4, _lib.host_floats(planner.cam12),
-                                 float(planner.global_scale), 0.08, B, N, _lib.ptr(eng.scratch),
+                                 _lib.ptr(eng.actions), 4, planner.pusher.ref(), 0.08, B, N, _lib.ptr(eng.scratch),
                                  _lib.ptr(s_out), 10, ms6, ops._stream()), "pile_profile_step")
 print(os.path.basename(os.environ.get("PILE_GNN_LIB", "default")), " ".join("%.1f" % (1e3 * v) for v in ms6), "us  sum %.1f" % (1e3 * sum(ms6)))
