@@ -4,12 +4,16 @@
 One "step" = one MPPI planner evaluation of the hot path on one batch of synthetic input:
 T-step particle-GNN rollout of `samples` sampled action sequences (relation search + propagation
 network per horizon step), target-shape reward of the final state, MPPI weighting record, and
--- for N > 1 -- ONE all-gather of the (2+4T)-float record per evaluation.  Work per GPU is fixed
-(weak scaling: every rank evaluates its own `samples` sequences), value = all ranks' particle-steps
-/ max-over-ranks device time.
+-- for N > 1 -- ONE all-gather of the (2+4T)-float record per evaluation.
+
+Two splits are measured in the same run (BASELINE config 3 reads "1024 samples ... sharded over 1/2/4/8"):
+  * weak   (headline `value`, "scaling": "weak"): every rank evaluates its own 1024 sequences;
+  * strong (`strong` object): 1024 sequences in total, 1024/N per rank.  At N = 1 the same object carries the
+    single-GPU times of the 512/256/128-sample shards (what each rank of a 2/4/8-GPU strong split runs; the
+    collective is 82 floats) with the per-kernel times that say which kernel stops the scaling.
 
   python bench.py                       # N=1, BASELINE config 3 @ 300 particles: 1024 x 300 x T=20
-  torchrun ... bench.py --gpus 8        # same per-GPU batch on 8 ranks + NCCL record exchange
+  torchrun ... bench.py --gpus 8        # weak + strong split on 8 ranks, NCCL record exchange, + config 5
   python bench.py --impl reference      # the reference algorithm's CPU path (oracle port) on host cores
 """
 import argparse
@@ -39,6 +43,8 @@ WORKLOADS = {   # name -> (samples per GPU, particles, horizon)   (BASELINE.json
     "cfg5": (2048, 300, 30),
     "cfg1": (1, 100, 1),          # the reference's own CPU-runnable case (reference arm / parity only)
 }
+KERNELS = ["nbr_search", "node_encode", "edge_encode", "edge_agg0", "node_update0", "edge_agg1", "node_update1",
+           "edge_agg2", "node_update2_predict"]
 
 
 def peaks():
@@ -151,6 +157,36 @@ def run_reference(args, samples, N, T):
     print(json.dumps(line))
 
 
+def kernel_rooflines(kms, E, R, B, N, engine_mode, hbm_gbs, bf16_tf):
+    """Per-kernel roofline entries from the live per-kernel times (ms) of one model step.
+    Algorithmic bytes / flops per launch as stated in DESIGN.md section 5."""
+    ce_row = 192 if engine_mode == 2 else H * 4          # tensor engine 2 stores C_e (and P_s) rows as 24-bit words
+    ps_row = ce_row
+    out = {}
+
+    def hbm(name, nbytes):
+        if kms[name] <= 0:
+            return
+        ach = nbytes / (kms[name] * 1e-3) / 1e9
+        out[name] = {"bound": "hbm", "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs,
+                     "algorithmic_bytes": nbytes, "ms": kms[name]}
+
+    def tensor(name, flops):
+        ach = flops / (kms[name] * 1e-3) / 1e12
+        out[name] = {"bound": "tensor", "achieved": ach, "peak": bf16_tf, "unit": "TFLOP/s", "frac": ach / bf16_tf,
+                     "algorithmic_flops": flops, "ms": kms[name]}
+
+    hbm("nbr_search", R * 24 + 4 * B * (N + 1) + 8 * E + 32 * E)
+    hbm("node_encode", R * 16 + R * (3 * H * 4 + ps_row))
+    tensor("edge_encode", E * 2 * (6 * H + 3 * H * H))
+    for p in range(3):
+        hbm("edge_agg%d" % p, E * (ce_row + 4) + R * (H * 4 + ps_row + H * 4) + 4 * (R + B))
+    for name in ("node_update0", "node_update1"):
+        hbm(name, R * (3 * H * 4) + R * (2 * H * 4 + ps_row))
+    hbm("node_update2_predict", R * (3 * H * 4) + R * 24)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,6 +196,7 @@ def main():
     ap.add_argument("--workload", default="cfg3_n300", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip plan latency / GD / parity legs (quick kernel runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     samples, N, T = WORKLOADS[args.workload]
@@ -190,38 +227,25 @@ def main():
     model = PropNetDiffDenModel(cfg, True).to(dev)
     planner = PlannerGD(cfg, env)
     goal = synthetic.make_goal("bar")
-    eng = RolloutEngine(model, planner, samples, N, T, device=dev, goal=goal, use_graph=not args.no_graph)
-    st, dn = synthetic.make_pile_batch(1, N, seed=0)
-    eng.load_state(st, dn)
-
+    lib = _lib.load()
     K, Wm = args.steps, args.warmup
-    pool = [torch.from_numpy(synthetic.random_actions(samples, T, seed=1000 * rank + i)) for i in range(K + Wm)]
-    pool_dev = [p.to(dev) for p in pool]
-    pool_host = [p.pin_memory() for p in pool]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
-    rec_all = torch.zeros(world * (2 + 4 * T), device=dev)
-    rec_out = torch.zeros(2 + 4 * T, device=dev)
-
-    def exchange():
-        if world > 1:
-            dist.all_gather_into_tensor(rec_all, eng.record)
-            lib = _lib.load()
-            _lib.check(lib.pile_mppi_combine(_lib.ptr(rec_all), world, T, _lib.ptr(rec_out), ops._stream()), "combine")
+    st, dn = synthetic.make_pile_batch(1, N, seed=0)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed_loop(step_fn):
+    def timed_loop(step_fn, steps):
         evs = []
         barrier()
         t0 = time.time()
-        for i in range(K):
+        for i in range(steps):
             flush.fill_(i & 0xff)                      # evict L2 between timed steps
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            step_fn(Wm + i)
+            step_fn(i)
             b.record()
             evs.append((a, b))
         barrier()
@@ -231,189 +255,350 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), t0, t1
 
-    # ---- device-resident arm ------------------------------------------------------------------------------
-    def step_device(i):
-        eng.actions.copy_(pool_dev[i])
-        eng.evaluate()
-        exchange()
+    class Arm:
+        """One engine + its action pool + the record exchange of an evaluation."""
 
+        def __init__(self, n_samples, n_particles, horizon, seed0, steps, state):
+            self.S, self.N, self.T = n_samples, n_particles, horizon
+            self.eng = RolloutEngine(model, planner, n_samples, n_particles, horizon, device=dev, goal=goal,
+                                     use_graph=not args.no_graph)
+            self.eng.load_state(*state)
+            pool = [torch.from_numpy(synthetic.random_actions(n_samples, horizon, seed=seed0 + i)) for i in range(steps)]
+            self.pool_dev = [p.to(dev) for p in pool]
+            self.pool_host = [p.pin_memory() for p in pool]
+            self.rec_all = torch.zeros(world * (2 + 4 * horizon), device=dev)
+            self.rec_out = torch.zeros(2 + 4 * horizon, device=dev)
+            self.r_host = torch.empty(n_samples, dtype=torch.float32).pin_memory()
+            self.rec_host = torch.empty(2 + 4 * horizon, dtype=torch.float32).pin_memory()
+
+        def exchange(self):
+            if world > 1:
+                dist.all_gather_into_tensor(self.rec_all, self.eng.record)
+                _lib.check(lib.pile_mppi_combine(_lib.ptr(self.rec_all), world, self.T, _lib.ptr(self.rec_out),
+                                                 ops._stream()), "combine")
+
+        def step_device(self, i):
+            self.eng.actions.copy_(self.pool_dev[i % len(self.pool_dev)])
+            self.eng.evaluate()
+            self.exchange()
+
+        def step_host(self, i):
+            self.eng.evaluate_host(self.pool_host[i % len(self.pool_host)], self.r_host, self.rec_host)
+            self.exchange()
+
+        def launches_per_step(self):
+            return self.eng.launches_per_eval() + (1 if world > 1 else 0)
+
+    # ---- weak split (headline): every rank evaluates `samples` sequences ------------------------------------------
+    arm = Arm(samples, N, T, 1000 * rank, K + Wm, (st, dn))
     for i in range(Wm):
-        step_device(i)
+        arm.step_device(i)
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    total_ms, t0, t1 = timed_loop(step_device)
-
-    # ---- end-to-end arm: host buffers in, host results out, through the engine's public call ----------
-    r_host = torch.empty(samples, dtype=torch.float32).pin_memory()
-    rec_host = torch.empty(2 + 4 * T, dtype=torch.float32).pin_memory()
-
-    def step_host(i):
-        eng.evaluate_host(pool_host[i], r_host, rec_host)
-        exchange()
-
+    total_ms, t0, t1 = timed_loop(lambda i: arm.step_device(Wm + i), K)
     for i in range(Wm):
-        step_host(i)
-    e2e_ms, _, t2 = timed_loop(step_host)
+        arm.step_host(i)
+    e2e_ms, _, t2 = timed_loop(lambda i: arm.step_host(Wm + i), K)
     time.sleep(0.2)
     sampler.stop()
     clocks = sampler.summary(t0, t2)
-
     units = world * samples * N * T
     value = units * K / (total_ms * 1e-3)
     e2e_value = units * K / (e2e_ms * 1e-3)
+    launches = 2 * K * arm.launches_per_step()
 
-    # ---- roofline of the dominant kernel, timed live with CUDA events (rank 0) --------------------------
+    def profile_kernels(a, reps=5):
+        ms = (_lib.C.c_float * len(KERNELS))()
+        s_out = torch.empty(a.S, a.N, 3, device=dev)
+        wpack = model.model.packed_weights(dev)
+        _lib.check(lib.pile_profile_step(_lib.ptr(wpack), _lib.ptr(a.eng.attr), _lib.ptr(a.eng.dens), _lib.ptr(a.eng.s0),
+                                         _lib.ptr(a.pool_dev[0]), a.T * 4, planner.pusher.ref(), 0.08, a.S, a.N,
+                                         _lib.ptr(a.eng.scratch), _lib.ptr(s_out), reps, ms, ops._stream()),
+                   "pile_profile_step")
+        return dict(zip(KERNELS, [float(v) for v in ms]))
+
+    # ---- strong split: 1024 sequences in total -------------------------------------------------------------------
+    strong = None
+    if args.workload.startswith("cfg3"):
+        weak_ms_per_step = total_ms / K
+        if world > 1 and samples % world == 0:
+            per = samples // world
+            sarm = Arm(per, N, T, 5000 + 1000 * rank, K + Wm, (st, dn))
+            for i in range(Wm):
+                sarm.step_device(i)
+            s_ms, _, _ = timed_loop(lambda i: sarm.step_device(Wm + i), K)
+            launches += K * sarm.launches_per_step()
+            strong = {"total_samples": samples, "samples_per_gpu": per, "n_gpus": world,
+                      "value": samples * N * T * K / (s_ms * 1e-3), "unit": UNIT, "ms_per_step": s_ms / K,
+                      "n1_ms_per_step": weak_ms_per_step,
+                      "efficiency_vs_n1": (weak_ms_per_step / world) / (s_ms / K),
+                      "note": "n1_ms_per_step = this run's %d-sample evaluation per GPU (the weak leg, max over ranks, "
+                              "incl. its record exchange)" % samples}
+            if rank == 0:
+                strong["kernel_ms"] = profile_kernels(sarm)
+            del sarm
+        elif world == 1:
+            shards = []
+            for g in (2, 4, 8):
+                per = samples // g
+                sarm = Arm(per, N, T, 5000 + g, K + Wm, (st, dn))
+                for i in range(Wm):
+                    sarm.step_device(i)
+                s_ms, _, _ = timed_loop(lambda i: sarm.step_device(Wm + i), K)
+                launches += K * sarm.launches_per_step()
+                shards.append({"n_gpus": g, "samples_per_gpu": per, "ms_per_step": s_ms / K,
+                               "projected_value": samples * N * T / (s_ms / K * 1e-3),
+                               "projected_efficiency": (weak_ms_per_step / g) / (s_ms / K),
+                               "kernel_ms": profile_kernels(sarm)})
+                del sarm
+            strong = {"total_samples": samples, "n_gpus": 1, "value": value, "unit": UNIT, "ms_per_step": weak_ms_per_step,
+                      "efficiency_vs_n1": 1.0, "single_gpu_shards": shards,
+                      "note": "single_gpu_shards: the per-rank work of a 2/4/8-GPU strong split timed on this one GPU "
+                              "(the collective of a multi-GPU run is 82 floats); projected_efficiency = (t_1024 / g) / t_shard"}
+
+    # ---- config 5 on the 8-rank run: 16384 x 300 x T=30 over 8 GPUs -------------------------------------------------
+    cfg5 = None
+    if world == 8 and args.workload == "cfg3_n300":
+        s5, n5, t5 = WORKLOADS["cfg5"]
+        k5 = max(3, min(K, 5))
+        a5 = Arm(s5, n5, t5, 9000 + 1000 * rank, k5 + Wm, (st, dn))
+        for i in range(Wm):
+            a5.step_device(i)
+        ms5, _, _ = timed_loop(lambda i: a5.step_device(Wm + i), k5)
+        launches += k5 * a5.launches_per_step()
+        cfg5 = {"workload": "cfg5: %d samples x %d particles x T=%d over 8 GPUs + NCCL MPPI record exchange" % (8 * s5, n5, t5),
+                "value": 8 * s5 * n5 * t5 * k5 / (ms5 * 1e-3), "unit": UNIT, "ms_per_step": ms5 / k5, "steps": k5}
+        del a5
+
+    # ---- rank 0: roofline, parity curve, plan latency, GD refinement, CPU baseline ------------------------------
     line = None
     if rank == 0:
         hbm_gbs, bf16_tf, _, peak_kind = peaks()
-        lib = _lib.load()
-        ms6 = (_lib.C.c_float * 6)()
-        s_out = torch.empty(samples, N, 3, device=dev)
-        wpack = model.model.packed_weights(dev)
-        _lib.check(lib.pile_profile_step(_lib.ptr(wpack), _lib.ptr(eng.attr), _lib.ptr(eng.dens), _lib.ptr(eng.s0),
-                                         _lib.ptr(pool_dev[0]), T * 4, planner.pusher.ref(), 0.08, samples, N,
-                                         _lib.ptr(eng.scratch),
-                                         _lib.ptr(s_out), 5, ms6, ops._stream()), "pile_profile_step")
-        names = ["nbr_search", "node_encode", "edge_encode", "propagate0", "propagate1", "propagate2_predict"]
-        kms = dict(zip(names, [float(v) for v in ms6]))
-        rel = ops.relations_from_buffer(eng.scratch, False, samples, N)
+        mode = lib.pile_get_tensor_cores()
+        kms = profile_kernels(arm)
+        rel = ops.relations_from_buffer(arm.eng.scratch, False, samples, N)
         E = int(rel.n_rel.sum().item())
         R = samples * N
-        flops = {"edge_encode": E * 2 * (6 * H + 3 * H * H),
-                 "node_encode": R * 2 * (5 * H + 4 * H * H),
-                 "propagate0": R * 2 * (3 * H * H) + E * 3 * H, "propagate1": R * 2 * (3 * H * H) + E * 3 * H,
-                 "propagate2_predict": R * 2 * (2 * H * H + 3 * H) + E * 3 * H}
-        ce_row = 192 if lib.pile_get_tensor_cores() == 2 else H * 4     # tensor engine 2 stores C_e as 24-bit words
-        hbm_bytes = {"nbr_search": R * 24 + 4 * (samples * (N + 1)) + 8 * E + 32 * E,
-                     "edge_encode": E * (32 + ce_row),
-                     "propagate0": E * (ce_row + 4) + R * H * 4 * 7}
-        dom = max(kms, key=kms.get)
+        per_kernel = kernel_rooflines(kms, E, R, samples, N, mode, hbm_gbs, bf16_tf)
         step_ms = sum(kms.values())
-        if dom in ("edge_encode", "node_encode"):
-            ach = flops[dom] / (kms[dom] * 1e-3) / 1e12
-            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": bf16_tf, "unit": "TFLOP/s",
-                    "frac": ach / bf16_tf, "traffic": None, "peak_source": peak_kind + " bf16 cuBLAS burst",
-                    "note": ("tcgen05 bf16 hi/lo split, 3 tensor passes per algorithmic MAC (tensor-pipe MACs = 3x achieved)"
-                             if lib.pile_get_tensor_cores() else "FP32 CUDA-core tile GEMM engine (parity anchor)")}
-        else:
-            by = hbm_bytes.get(dom, hbm_bytes["propagate0"])
-            ach = by / (kms[dom] * 1e-3) / 1e9
-            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_gbs, "unit": "GB/s",
-                    "frac": ach / hbm_gbs, "traffic": None, "peak_source": peak_kind + " copy"}
+        # dominant kernel = largest share of the model step summed over its launches (k_edge_agg and the particle
+        # update launch three times per step); `achieved` is per launch (average over the launches)
+        groups = {"nbr_search": ["nbr_search"], "node_encode": ["node_encode"], "edge_encode": ["edge_encode"],
+                  "edge_agg": ["edge_agg0", "edge_agg1", "edge_agg2"],
+                  "node_update": ["node_update0", "node_update1", "node_update2_predict"]}
+        share = {g: sum(kms[k] for k in ks) / step_ms for g, ks in groups.items()}
+        dom = max(share, key=share.get)
+        members = [k for k in groups[dom] if k in per_kernel]
+        first = per_kernel[members[0]]
+        avg_ms = sum(kms[k] for k in members) / len(members)
+        work = first.get("algorithmic_bytes", first.get("algorithmic_flops"))
+        ach = work / (avg_ms * 1e-3) / (1e9 if first["bound"] == "hbm" else 1e12)
+        roof = {"kernel": dom, "bound": first["bound"], "achieved": ach, "peak": first["peak"], "unit": first["unit"],
+                "frac": ach / first["peak"], "traffic": None, "launches_per_model_step": len(members),
+                "avg_launch_ms": avg_ms,
+                "peak_source": peak_kind + (" copy" if first["bound"] == "hbm" else " bf16 cuBLAS burst")}
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tr):
-            roof["traffic"] = json.load(open(tr)).get(dom)
+            tj = json.load(open(tr))
+            roof["traffic"] = tj.get(dom)
         roof["kernel_ms"] = kms
-        roof["kernel_share_of_model_step"] = {k: v / step_ms for k, v in kms.items()}
+        roof["kernel_share_of_model_step"] = share
+        roof["kernels"] = per_kernel
         roof["E_relations"] = E
         f_ref, f_alg = O.flops_per_sample_step(N, E / samples, H)
         roof["alg_tflops_whole_step"] = f_alg * samples / (step_ms * 1e-3) / 1e12
+        roof["note"] = ("tensor kernels: tcgen05 bf16 hi/lo split, 3 tensor passes per algorithmic MAC (tensor-pipe MACs = 3x achieved)"
+                        if mode else "FP32 CUDA-core tile GEMM engine (parity anchor)")
 
-        # MPC plan latency (BASELINE.json metric, second half): one MPPI planner evaluation of BASELINE config 2
-        # (256 samples x 100 particles x T=10) through the host-buffer call, >= 50 timed calls after 5 warm-ups
-        plan = None
-        if world == 1:
-            s2, n2, t2 = WORKLOADS["cfg2"]
-            eng2 = RolloutEngine(model, planner, s2, n2, t2, device=dev, goal=goal, use_graph=not args.no_graph)
-            st2, dn2 = synthetic.make_pile_batch(1, n2, seed=0)
-            eng2.load_state(st2, dn2)
-            acts2 = [torch.from_numpy(synthetic.random_actions(s2, t2, seed=50 + i)).pin_memory() for i in range(8)]
-            r2 = torch.empty(s2, dtype=torch.float32).pin_memory()
-            rec2 = torch.empty(2 + 4 * t2, dtype=torch.float32).pin_memory()
-            lat = []
-            for i in range(55):
-                t_a = time.perf_counter()
-                eng2.evaluate_host(acts2[i % 8], r2, rec2)
-                lat.append((time.perf_counter() - t_a) * 1e3)
-            lat = sorted(lat[5:])
-            plan = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "calls": len(lat),
-                    "workload": "cfg2: 256 samples x 100 particles x T=10, host actions in -> host reward + MPPI record out"}
-
-            # the reference's own MPC entry point with its shipped configuration (config/mpc/config.yaml:38-43,
-            # env/flex_env.py:1020): 50 trajectories x 30 state variants, 100 particles, horizon 1, time budget
-            # 2000 ms -> 27 Adam iterations (planners.py:679-682)
-            st3, dn3 = synthetic.make_pile_batch(30, 100, seed=0)
-            act3 = synthetic.random_actions(50, 1, seed=9).transpose(1, 0, 2).astype(np.float64)
-            gd = []
-            for i in range(8):
-                t_a = time.perf_counter()
-                res = planner.trajectory_optimization_ptcl_multi_traj(
-                    st3, dn3, np.zeros((30, 100), np.float32), goal, model, act3, np.zeros(1), 50, 1, 200, None, None,
-                    time_lim=2000)
-                gd.append((time.perf_counter() - t_a) * 1e3)
-            gd = sorted(gd[2:])
-            plan["gd_planner"] = {"p50_ms": gd[len(gd) // 2], "calls": len(gd), "iterations": int(res["iter_num"]) + 1,
-                                  "workload": "trajectory_optimization_ptcl_multi_traj: 50 traj x 30 variants x 100 particles, "
-                                              "T=1, numpy in -> result dict out (reference budget for this call: 2000 ms)"}
-
-            # the other planner-side piece of an MPC step: RGB-D observation -> 30 particle
-            # re-samplings (env/flex_env.py:933-951), host observation in -> host particles out
-            from dyn_res_pile_manip_b200 import observation as OBS
-            st4, _ = synthetic.make_pile_batch(1, 300, seed=0)
-            obs4 = synthetic.render_observation(st4[0], env)
-            ol = []
-            for i in range(12):
-                t_a = time.perf_counter()
-                OBS.obs2ptcl_fixed_num_batch(obs4, 100, 30, env.get_cam_params(), env.global_scale, seed=i)
-                ol.append((time.perf_counter() - t_a) * 1e3)
-            ol = sorted(ol[2:])
-            plan["obs_to_particles"] = {"p50_ms": ol[len(ol) // 2], "calls": len(ol),
-                                        "workload": "obs2ptcl_fixed_num_batch: 720x720 RGB-D -> 30 x 100 particles "
-                                                    "(depth2fgpcd, 1 cm voxel downsample, FPS, recenter), numpy in -> numpy out"}
-            if not args.no_cpu_baseline:
-                from oracle import obs_oracle as OO
-                t_a = time.perf_counter()
-                depth4 = obs4[..., -1] / env.global_scale
-                for i in range(2):      # the reference repeats all four stages for each of the 30 re-samplings
-                    fg4 = OO.voxel_down_sample(OO.depth2fgpcd(depth4, depth4 < 0.599 / 0.8, env.get_cam_params()), 0.01)
-                    pk4, r4 = OO.fps(fg4, 100, i)
-                    OO.recenter(fg4, pk4, r=min(0.02, 0.5 * r4))
-                plan["obs_to_particles"]["cpu_port_ms"] = (time.perf_counter() - t_a) * 1e3 / 2 * 30
-                plan["obs_to_particles"]["cpu_sample"] = "2 of 30 re-samplings timed (oracle/obs_oracle.py, numpy), scaled to 30"
-
+        extras = world == 1 and not args.no_extras
+        parity = parity_report(model, planner, dev) if extras else None
+        plan = plan_latency(model, planner, env, goal, dev, args) if extras else None
         cpu = None
         torch_cuda = None
         if world == 1 and not args.no_cpu_baseline:
-            chunk = 16 if N >= 200 else 32
-            # the reference algorithm with torch's own CUDA kernels on this B200 (dense one-hot bmm path)
+            # the reference algorithm with torch's own CUDA kernels on this B200 (dense one-hot bmm path), chunk sized
+            # so the dense [chunk, 10N, N] one-hot tensors use a few GB
+            gchunk = 256 if N >= 200 else 512
             try:
-                r_gpu, t_gpu, _ = cpu_reference_rate(N, T, chunk, 3.0, warmup=1, device="cuda")
+                r_gpu, t_gpu, _ = cpu_reference_rate(N, T, gchunk, 3.0, warmup=1, device="cuda")
                 torch_cuda = {"value": r_gpu, "unit": UNIT, "kind": "oracle port on torch-CUDA (cuBLAS/ATen), same B200",
-                              "sample": "%d passes of %d action sequences x %d particles x T=%d" % (len(t_gpu), chunk, N, T)}
+                              "sample": "%d passes of %d action sequences x %d particles x T=%d" % (len(t_gpu), gchunk, N, T)}
             except RuntimeError as err:      # e.g. out of memory for the dense [B, 10N, N] tensors
                 torch_cuda = {"value": None, "error": str(err)[:120]}
+            torch.cuda.empty_cache()
+            chunk = 16 if N >= 200 else 32
             rate, times, cores = cpu_reference_rate(N, T, chunk, 12.0)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d passes of %d of %d action sequences x %d particles x T=%d (oracle/pile_oracle.py, "
                              "torch CPU, dense one-hot form)" % (len(times), chunk, samples, N, T)}
 
-        launches = eng.launches_per_eval() + (1 if world > 1 else 0) + 1   # + D2D action copy is a memcpy, + flush fill
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "samples_per_gpu": samples, "particles": N, "horizon": T,
                            "nf_effect": H, "relations_per_particle": E / R, "cuda_graph": not args.no_graph,
+                           "gemm_engine": {0: "fp32 CUDA cores", 1: "tcgen05 (smem A)", 2: "tcgen05 (TMEM A)"}[mode],
                            "cache": "L2 flushed (256 MB fill) between timed steps; per-step intermediates (%.0f MB) exceed L2"
                                     % (E * H * 4 / 1e6),
                            "collective": "all_gather of %d floats per evaluation" % (2 + 4 * T) if world > 1 else "none"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / K,
                         "h2d_bytes_per_step": samples * T * 4 * 4,
                         "d2h_bytes_per_step": samples * 4 + (2 + 4 * T) * 4},
-                "gpu_launches": (eng.launches_per_eval() + (1 if world > 1 else 0)) * K,
+                "gpu_launches": launches,
                 "clocks": clocks, "roofline": roof}
+        if strong:
+            line["strong"] = strong
+        if cfg5:
+            line["cfg5"] = cfg5
+        if parity:
+            line["parity"] = parity
         if plan:
             line["mpc_plan_latency"] = plan
         if cpu:
             line["cpu_baseline"] = cpu
         if torch_cuda:
             line["torch_cuda_reference"] = torch_cuda
-        del launches
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line:
         print(json.dumps(line))
+
+
+def parity_report(model, planner, dev):
+    """Drift over the full horizon against vectors the real reference produced at BASELINE's sizes
+    (tests/golden/golden_big_v1.npz; SURVEY 8d 'Parity report'): per-step ||d||/||s|| and relation-set Jaccard."""
+    from dyn_res_pile_manip_b200 import ops
+    path = os.path.join(ROOT, "tests", "golden", "golden_big_v1.npz")
+    base = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
+    if not (os.path.isfile(path) and os.path.isfile(base)):
+        return None
+    g, b = np.load(path), np.load(base)
+    weights = {k[2:]: torch.from_numpy(v) for k, v in b.items() if k.startswith("w/")}
+    keep = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    def pair_set(c):
+        c = np.asarray(c).astype(np.int64)
+        return set((c[:, 0] << 40 | c[:, 1] << 20 | c[:, 2]).tolist())
+
+    def coo(rel):
+        return np.concatenate([np.concatenate([np.full((e.shape[0], 1), i), e], axis=1) for i, e in enumerate(rel.edge_sets())])
+
+    out = {"source": "tests/golden/golden_big_v1.npz (real reference, CPU, seed-0 weights)"}
+    try:
+        for tag, name in (("K", "n300_T20_tamed"), ("H", "n300_T20_random_init"), ("J", "n100_T10_tamed")):
+            nb, ns, N, T = [int(v) for v in g[tag + "/dims"]]
+            w = {k: v.clone() for k, v in weights.items()}
+            for k in ("model.particle_predictor.linear_1.weight", "model.particle_predictor.linear_1.bias"):
+                w[k] = w[k] * float(g[tag + "/tame"])
+            model.load_state_dict(w)
+            planner.particle_num = N
+            acts = torch.from_numpy(g[tag + "/acts"]).to(dev)
+            with torch.no_grad():
+                pred = planner.ptcl_model_rollout(torch.from_numpy(g[tag + "/s0"]).to(dev), torch.from_numpy(g[tag + "/dens"]).to(dev),
+                                                  torch.zeros(nb, N, device=dev), model, acts)["model_rollout"]["state_pred"]
+                ref = torch.from_numpy(g[tag + "/state_pred"]).to(dev)
+                drift = [float((pred[:, t] - ref[:, t]).double().norm() / ref[:, t].double().norm()) for t in range(T)]
+                jac = []
+                s = torch.from_numpy(g[tag + "/s0"]).to(dev).repeat(ns, 1, 1)
+                for t in range(T):
+                    sd = planner.gen_s_delta(s, acts[:, t].contiguous())
+                    mine, want = pair_set(coo(ops.build_relations(s, sd, 0.08))), pair_set(g[tag + "/rel%d" % t])
+                    jac.append(len(mine & want) / len(mine | want))
+                    s = pred[:, t].contiguous()
+            out[name] = {"one_step_rel": drift[0], "drift_T": drift, "jaccard_T": jac, "samples": nb * ns, "particles": N,
+                         "horizon": T, "predictor_scale": float(g[tag + "/tame"])}
+    finally:
+        model.load_state_dict(keep)
+    return out
+
+
+def plan_latency(model, planner, env, goal, dev, args):
+    """MPC plan latency (BASELINE.json metric, second half) and the GD refinement (config 4)."""
+    from dyn_res_pile_manip_b200 import synthetic
+    from dyn_res_pile_manip_b200.engine import RolloutEngine
+    # one MPPI planner evaluation of BASELINE config 2 (256 samples x 100 particles x T=10) through the host-buffer
+    # call, >= 50 timed calls after 5 warm-ups
+    s2, n2, t2 = WORKLOADS["cfg2"]
+    eng2 = RolloutEngine(model, planner, s2, n2, t2, device=dev, goal=goal, use_graph=not args.no_graph)
+    st2, dn2 = synthetic.make_pile_batch(1, n2, seed=0)
+    eng2.load_state(st2, dn2)
+    acts2 = [torch.from_numpy(synthetic.random_actions(s2, t2, seed=50 + i)).pin_memory() for i in range(8)]
+    r2 = torch.empty(s2, dtype=torch.float32).pin_memory()
+    rec2 = torch.empty(2 + 4 * t2, dtype=torch.float32).pin_memory()
+    lat = []
+    for i in range(55):
+        t_a = time.perf_counter()
+        eng2.evaluate_host(acts2[i % 8], r2, rec2)
+        lat.append((time.perf_counter() - t_a) * 1e3)
+    lat = sorted(lat[5:])
+    plan = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "calls": len(lat),
+            "workload": "cfg2: 256 samples x 100 particles x T=10, host actions in -> host reward + MPPI record out"}
+    del eng2
+
+    # the reference's own MPC entry point with its shipped configuration (config/mpc/config.yaml:38-43,
+    # env/flex_env.py:1020): 50 trajectories x 30 state variants, 100 particles, horizon 1, time budget
+    # 2000 ms -> 27 Adam iterations (planners.py:679-682)
+    st3, dn3 = synthetic.make_pile_batch(30, 100, seed=0)
+    act3 = synthetic.random_actions(50, 1, seed=9).transpose(1, 0, 2).astype(np.float64)
+    gd = []
+    for i in range(12):
+        t_a = time.perf_counter()
+        res = planner.trajectory_optimization_ptcl_multi_traj(
+            st3, dn3, np.zeros((30, 100), np.float32), goal, model, act3, np.zeros(1), 50, 1, 200, None, None,
+            time_lim=2000)
+        gd.append((time.perf_counter() - t_a) * 1e3)
+    gd = sorted(gd[2:])
+    plan["gd_planner"] = {"p50_ms": gd[len(gd) // 2], "calls": len(gd), "iterations": int(res["iter_num"]) + 1,
+                          "optim_loop_ms": res["times"]["rollout_time"] + res["times"]["optim_time"],
+                          "workload": "trajectory_optimization_ptcl_multi_traj: 50 traj x 30 variants x 100 particles, "
+                                      "T=1, numpy in -> result dict out (reference budget for this call: 2000 ms)"}
+
+    # BASELINE config 4: gradient-based refinement, forward + backward through T=20, 128 samples x 300 particles,
+    # one Adam iteration = rollout with tape + last-step reward | reward/rollout backward + Adam + clamp
+    st4, dn4 = synthetic.make_pile_batch(1, 300, seed=0)
+    act4 = synthetic.random_actions(128, 20, seed=4).transpose(1, 0, 2).astype(np.float64)
+    iters = 6
+    best = None
+    for rep in range(3):
+        res4 = planner.trajectory_optimization_ptcl_multi_traj(
+            st4, dn4, np.zeros((1, 300), np.float32), goal, model, act4, np.zeros(20), 128, 20, iters, None, None,
+            rollout_best_action_sequence=False)
+        cur = (res4["times"]["rollout_time"] / iters, res4["times"]["optim_time"] / iters)
+        if best is None or sum(cur) < sum(best):
+            best = cur
+    plan["cfg4_gd_refinement"] = {"fwd_ms": best[0], "bwd_ms": best[1], "iter_ms": best[0] + best[1],
+                                  "value": 128 * 300 * 20 / ((best[0] + best[1]) * 1e-3), "unit": UNIT,
+                                  "workload": "cfg4: 128 samples x 300 particles x T=20, one Adam iteration (captured graphs): "
+                                              "fwd = rollout with tape + reward + best tracking, bwd = reward/rollout backward + Adam/clamp"}
+    planner._gd_loops.clear()
+
+    # the other planner-side piece of an MPC step (SURVEY 8f rank 1): RGB-D observation -> 30 particle
+    # re-samplings (env/flex_env.py:933-951), host observation in -> host particles out
+    from dyn_res_pile_manip_b200 import observation as OBS
+    st5, _ = synthetic.make_pile_batch(1, 300, seed=0)
+    obs5 = synthetic.render_observation(st5[0], env)
+    ol = []
+    for i in range(12):
+        t_a = time.perf_counter()
+        OBS.obs2ptcl_fixed_num_batch(obs5, 100, 30, env.get_cam_params(), env.global_scale, seed=i)
+        ol.append((time.perf_counter() - t_a) * 1e3)
+    ol = sorted(ol[2:])
+    plan["obs_to_particles"] = {"p50_ms": ol[len(ol) // 2], "calls": len(ol),
+                                "workload": "obs2ptcl_fixed_num_batch: 720x720 RGB-D -> 30 x 100 particles "
+                                            "(depth2fgpcd, 1 cm voxel downsample, FPS, recenter), numpy in -> numpy out"}
+    if not args.no_cpu_baseline:
+        from oracle import obs_oracle as OO
+        t_a = time.perf_counter()
+        depth5 = obs5[..., -1] / env.global_scale
+        for i in range(2):      # the reference repeats all four stages for each of the 30 re-samplings
+            fg = OO.voxel_down_sample(OO.depth2fgpcd(depth5, depth5 < 0.599 / 0.8, env.get_cam_params()), 0.01)
+            pk, r_ = OO.fps(fg, 100, i)
+            OO.recenter(fg, pk, r=min(0.02, 0.5 * r_))
+        plan["obs_to_particles"]["cpu_port_ms"] = (time.perf_counter() - t_a) * 1e3 / 2 * 30
+        plan["obs_to_particles"]["cpu_sample"] = "2 of 30 re-samplings timed (oracle/obs_oracle.py, numpy), scaled to 30"
+    return plan
 
 
 if __name__ == "__main__":

@@ -283,7 +283,7 @@ int pile_profile_step(const float* wpack, const float* attr, const float* dens, 
   cudaStream_t st = (cudaStream_t)stream;
   ScratchView sv = carve_scratch(scratch, B, N);
   const PushCam cam = make_cam(pusher);
-  constexpr int NK = 3 + PSTEP;   // nbr, node_encode, edge_encode, propagate x3
+  constexpr int NK = PROFILE_SLOTS;   // nbr, node_encode, edge_encode, 3 x (segmented sum, particle update)
   cudaEvent_t ev[NK + 1];
   for (auto& e : ev) cudaEventCreate(&e);
   for (int k = 0; k < NK; ++k) ms_out[k] = 0.f;

@@ -398,10 +398,12 @@ int launch_forward(const float* wpack, const float* attr, const float* dens, con
     if (ev) cudaEventRecord(ev[1], st);
     if ((e = launch_edge_encode_tc(wpack, attr, dens, s_cur, s_cur_stride, csr, mk, ws.efeat, ws.Ce, B, N, st, efeat_ready))) return e;
     for (int p = 0; p < PSTEP; ++p) {
-      if (ev) cudaEventRecord(ev[2 + p], st);
-      if ((e = launch_propagate_tc(wpack, csr, ws, mk, p, s_cur, s_cur_stride, s_out, s_out_stride, B, N, st))) return e;
+      if (ev) cudaEventRecord(ev[2 + 2 * p], st);
+      if ((e = launch_propagate_tc(wpack, csr, ws, mk, p, s_cur, s_cur_stride, s_out, s_out_stride, B, N, st,
+                                   ev ? ev[3 + 2 * p] : nullptr)))
+        return e;
     }
-    if (ev) cudaEventRecord(ev[2 + PSTEP], st);
+    if (ev) cudaEventRecord(ev[2 + 2 * PSTEP], st);
     return 0;
   }
   if (ev) cudaEventRecord(ev[0], st);
@@ -416,7 +418,7 @@ int launch_forward(const float* wpack, const float* attr, const float* dens, con
   PILE_CHECK_LAUNCH();
   for (int p = 0; p < PSTEP; ++p) {
     const int in = p & 1, out = in ^ 1;
-    if (ev) cudaEventRecord(ev[2 + p], st);
+    if (ev) { cudaEventRecord(ev[2 + 2 * p], st); cudaEventRecord(ev[3 + 2 * p], st); }   // no separate segmented sum
     if (p < PSTEP - 1) {
       k_propagate<false><<<g_node, NT, sizeof(PropSmem), st>>>(
           wpack, csr.rowptr, csr.col, ws.Ce, ws.Cp, ws.eff, ws.Pr[in], ws.Ps[in], ws.Pr[out], ws.Ps[out],
@@ -430,7 +432,7 @@ int launch_forward(const float* wpack, const float* attr, const float* dens, con
     }
     PILE_CHECK_LAUNCH();
   }
-  if (ev) cudaEventRecord(ev[2 + PSTEP], st);
+  if (ev) cudaEventRecord(ev[2 + 2 * PSTEP], st);
   return 0;
 }
 

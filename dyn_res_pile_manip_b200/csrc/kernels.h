@@ -56,7 +56,9 @@ int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_del
 int launch_forward(const float* wpack, const float* attr, const float* dens, const float* s_cur,
                    long long s_cur_stride, const float* s_delta, const Csr& csr, const StepScratch& ws,
                    const Masks* masks, float* s_out, long long s_out_stride, int B, int N, cudaStream_t st,
-                   cudaEvent_t* ev = nullptr,    // ev: 6 events recorded before each kernel and after the last
+                   cudaEvent_t* ev = nullptr,    // ev: PROFILE_SLOTS + 1 events: before nbr-search's successors (node
+                                                 // encode, relation encode, then per propagation step the segmented
+                                                 // sum and the particle update) and after the last kernel
                    bool efeat_ready = false);    // ws.efeat already written by launch_nbr_search
 
 // process-wide switch: 0 = FP32 CUDA-core tiles, 1 = tcgen05 tiles with shared-memory activations,
@@ -83,7 +85,9 @@ int launch_node_encode_tc(const float* wpack, const float* attr, const float* de
 // propagation step p on the tensor-core path: k_edge_agg + k_node_update_tc (p == PSTEP-1: + predictor)
 int launch_propagate_tc(const float* wpack, const Csr& csr, const StepScratch& ws, const Masks* mk, int p,
                         const float* s_cur, long long s_stride, float* s_out, long long o_stride, int B, int N,
-                        cudaStream_t st);
+                        cudaStream_t st, cudaEvent_t mid = nullptr /* recorded between the two kernels */);
+// kernels timed by pile_profile_step: relation search, particle encoder, relation encoder, 3 x (k_edge_agg, particle update)
+constexpr int PROFILE_SLOTS = 3 + 2 * PSTEP;
 
 int launch_reward(const float* states, long long n_states, long long state_stride, int N, const float* goal_img,
                   int Hh, int Ww, const float* goal_coor, int M, float fx, float fy, float cx, float cy,

@@ -480,7 +480,7 @@ int launch_node_encode_tc(const float* wpack, const float* attr, const float* de
 
 int launch_propagate_tc(const float* wpack, const Csr& csr, const StepScratch& ws, const Masks* mk, int p,
                         const float* s_cur, long long s_stride, float* s_out, long long o_stride, int B, int N,
-                        cudaStream_t st) {
+                        cudaStream_t st, cudaEvent_t mid) {
   const int in = p & 1, out = in ^ 1;
   const long long R = (long long)B * N;
   const long long ntiles = (R + TILE - 1) / TILE;
@@ -493,6 +493,7 @@ int launch_propagate_tc(const float* wpack, const Csr& csr, const StepScratch& w
   const int agg_smem = packed ? agg_smem_bytes<true>(mk == nullptr) : agg_smem_bytes<false>(false);
   agg_kernel<<<agg_blocks, AGG_THREADS, agg_smem, st>>>(csr.rowptr, csr.col, ws.Ce, ws.Pr[in], ws.Ps[in], me, ws.agg, B, N);
   PILE_CHECK_LAUNCH();
+  if (mid) cudaEventRecord(mid, st);
   const int grid = tc_grid(ntiles);
   const size_t sm = sizeof(NodeUpdSmemTc);
   if (p < PSTEP - 1) {

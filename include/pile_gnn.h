@@ -104,8 +104,9 @@ int pile_rollout_forward(const float* wpack, const float* attr, const float* den
                          void* scratch, void* tape, float* states, void* stream);
 
 /* measurement hook for bench.py's roofline line: runs one rollout step `reps` times with CUDA events
- * around each of its 6 kernels (relation search, node encode, relation encode, 3 x propagate) on `stream`,
- * SYNCHRONISES, and writes the mean milliseconds per kernel to ms_out (HOST, 6 floats). */
+ * around each of its 9 kernels (relation search, particle encoder, relation encoder, then per propagation step the
+ * receiver-segmented sum k_edge_agg and the particle update; the FP32 engine fuses the last two: its slots 3/5/7
+ * read 0) on `stream`, SYNCHRONISES, and writes the mean milliseconds per kernel to ms_out (HOST, 9 floats). */
 int pile_profile_step(const float* wpack, const float* attr, const float* dens, const float* s_cur,
                       const float* action, int act_stride, const pile_pusher* pusher, float adj_thresh, int B,
                       int N, void* scratch, float* s_out, int reps, float* ms_out, void* stream);

@@ -79,17 +79,19 @@ def edge_lists(adj):
 
 
 def one_hot_relations(adj, dtype=torch.float32):
-    """Dense Rr, Rs [B, n_rel, N] exactly as the reference lays them out (gnn_dyn.py:242-251)."""
+    """Dense Rr, Rs [B, n_rel, N] exactly as the reference lays them out (gnn_dyn.py:242-251): relation slots of a
+    sample in nonzero() order.  Built for the whole batch at once (the reference loops over samples in Python; the
+    result is identical)."""
     B, N, _ = adj.shape
     counts = adj.sum(dim=(1, 2))
     n_rel = int(counts.max())
     Rr = torch.zeros(B, n_rel, N, dtype=dtype, device=adj.device)
     Rs = torch.zeros(B, n_rel, N, dtype=dtype, device=adj.device)
-    for b in range(B):
-        rs = adj[b].nonzero()
-        slot = torch.arange(rs.shape[0], device=adj.device)
-        Rr[b, slot, rs[:, 0]] = 1
-        Rs[b, slot, rs[:, 1]] = 1
+    brs = adj.nonzero()                                   # sorted by (b, recv, send)
+    first = torch.cumsum(counts, 0) - counts              # index of each sample's first relation
+    slot = torch.arange(brs.shape[0], device=adj.device) - first[brs[:, 0]]
+    Rr[brs[:, 0], slot, brs[:, 1]] = 1
+    Rs[brs[:, 0], slot, brs[:, 2]] = 1
     return Rr, Rs
 
 

@@ -23,3 +23,17 @@ def golden():
 def golden_weights(golden):
     import torch
     return {k[2:]: torch.from_numpy(v) for k, v in golden.items() if k.startswith("w/")}
+
+
+@pytest.fixture(scope="session")
+def golden_big():
+    """Reference-generated vectors at BASELINE.json's particle counts (tests/golden/make_golden_big.py)."""
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_big_v1.npz"), allow_pickle=False))
+
+
+def tamed_weights(weights, tame):
+    """Seed-0 weights with the predictor's output layer scaled (cases J/K of golden_big_v1.npz)."""
+    out = {k: v.clone() for k, v in weights.items()}
+    for k in ("model.particle_predictor.linear_1.weight", "model.particle_predictor.linear_1.bias"):
+        out[k] = out[k] * float(tame)
+    return out

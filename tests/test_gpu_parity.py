@@ -203,3 +203,63 @@ def test_mppi_weighting_vs_reference(golden, planner):
     rew = rng.uniform(-900, -1, (1000, 1))
     np.testing.assert_allclose(planner.optimize_action(acts, rew), O.mppi_optimize_action(acts, rew, 0.1),
                                rtol=1e-4, atol=1e-5)
+
+
+class _RealEnv(synthetic.FakeEnv):
+    """FakeEnv with the attributes the real-robot branch reads (planners.py:271-278, 409-410)."""
+    is_real = True
+    crop_w_lower, crop_w_off, crop_h_lower, crop_h_off = 100, 20, 80, 10
+
+    def __init__(self, g):
+        super().__init__()
+        self.wkspc_center_x, self.wkspc_center_y = float(g["wkspc_center_x"]), float(g["wkspc_center_y"])
+        self.s2r_scale = float(g["s2r_scale"])
+
+
+def test_gen_s_delta_irl_vs_reference():
+    """Real-robot pusher model on the device (planners.py:259-300) against the reference's own output and autograd
+    gradients (tests/golden/make_golden_irl.py), through a planner built for env.is_real."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_irl_v1.npz"))
+    planner = P.PlannerGD(synthetic.default_config(), _RealEnv(g))
+    planner.particle_num = g["s_cur"].shape[1]
+    s = cuda(g["s_cur"]).requires_grad_(True)
+    a = cuda(g["action"]).requires_grad_(True)
+    out = planner.gen_s_delta_irl(s, a)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["s_delta"], rtol=0, atol=2e-7)
+    assert (np.abs(g["s_delta"]).sum(-1) > 0).sum() > 10
+    (out * cuda(g["weight"])).sum().backward()
+    np.testing.assert_allclose(s.grad.cpu().numpy(), g["g_s_cur"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(a.grad.cpu().numpy(), g["g_action"], rtol=1e-4, atol=1e-5)
+    assert planner.reward_offset() == (-80.0, -70.0)
+    # a planner built for the simulator exposes the same method (it reads the three attributes from the env)
+    sim = P.PlannerGD(synthetic.default_config(), synthetic.FakeEnv())
+    sim.env.wkspc_center_x, sim.env.wkspc_center_y, sim.env.s2r_scale = planner.env.wkspc_center_x, planner.env.wkspc_center_y, planner.env.s2r_scale
+    sim.particle_num = planner.particle_num
+    assert torch.equal(sim.gen_s_delta_irl(s.detach(), a.detach()), out.detach())
+
+
+def test_real_robot_rollout_uses_the_irl_pusher(model, golden_weights):
+    """planners.py:345-348: with env.is_real the horizon rollout takes its s_delta from gen_s_delta_irl; the fused
+    rollout must equal stepping the model by hand with the stand-alone irl kernel, and match the oracle."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_irl_v1.npz"))
+    env = _RealEnv(g)
+    planner = P.PlannerGD(synthetic.default_config(), env)
+    N = g["s_cur"].shape[1]
+    planner.particle_num = N
+    s0, T = cuda(g["s_cur"][:2]), 3
+    acts = cuda(np.stack([g["action"][[0, 1]], g["action"][[2, 3]], g["action"][[4, 0]]], axis=1))      # [2, T, 4]
+    dens = torch.full((2,), 1500.0, device=DEV)
+    with torch.no_grad():
+        out = planner.ptcl_model_rollout(s0, dens, torch.zeros(2, N, device=DEV), model, acts)["model_rollout"]["state_pred"]
+        s = s0
+        for t in range(T):
+            sd = planner.gen_s_delta_irl(s, acts[:, t].contiguous())
+            s = model.predict_one_step(torch.zeros(2, N, device=DEV), s, sd, dens)
+            assert torch.equal(s, out[:, t]), t
+    s = torch.from_numpy(g["s_cur"][:2])
+    for t in range(T):
+        sd = O.gen_s_delta_irl(s, acts[:, t].cpu(), env.wkspc_center_x, env.wkspc_center_y, env.s2r_scale)
+        s = O.predict_one_step(golden_weights, 0.08, torch.zeros(2, N), s, sd, dens.cpu())
+    assert relerr(out[:, -1], s) < 1e-4

@@ -155,3 +155,80 @@ def test_adam_clamp_kernel_equals_torch_adam():
             ref.data = torch.minimum(torch.maximum(ref.data, torch.tensor(lo)), torch.tensor(hi))
         ops.adam_clamp(mine, torch.tensor(g, device=DEV), m, v, step, 0.05, lo, hi)
         np.testing.assert_allclose(mine.cpu().numpy(), ref.detach().numpy(), rtol=0, atol=2e-6)
+
+
+def test_gd_planner_graph_replay_equals_launch_by_launch(setup):
+    """The captured iteration (two CUDA graphs replayed n_iter times) gives bit for bit what the same launches give
+    one by one, and a second call reuses the capture."""
+    cfg, env, model, planner = setup
+    st, dn = synthetic.make_pile_batch(3, 60, seed=9)
+    act0 = synthetic.random_actions(5, 2, seed=9).transpose(1, 0, 2).astype(np.float64)
+    goal = synthetic.make_goal("tee")
+    args = (st, dn, np.zeros((3, 60), np.float32), goal, model, act0, np.zeros(2), 5, 2, 6, None, None)
+    planner.use_graph = False
+    a = planner.trajectory_optimization_ptcl_multi_traj(*args)
+    planner.use_graph = True
+    b = planner.trajectory_optimization_ptcl_multi_traj(*args)
+    c = planner.trajectory_optimization_ptcl_multi_traj(*args)
+    for k in ("action_sequence", "action_full", "reward_full", "rew_mean", "rew_std", "observation_sequence"):
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(b[k], c[k]), k
+    assert a["iter_num"] == b["iter_num"] == 5
+    assert b["times"]["rollout_time"] > 0 and b["times"]["optim_time"] > 0
+
+
+def test_gd_planner_sees_a_changed_goal(setup):
+    """the shaped goal image must follow the goal's CONTENT.  Two calls with different goals of the
+    same shape (fresh tensors that the allocator places at the same address) must each equal a fresh planner's result."""
+    cfg, env, model, planner = setup
+    st, dn = synthetic.make_pile_batch(2, 50, seed=10)
+    act0 = synthetic.random_actions(4, 1, seed=10).transpose(1, 0, 2).astype(np.float64)
+    res = {}
+    for kind in ("bar", "disc", "bar"):
+        args = (st, dn, np.zeros((2, 50), np.float32), synthetic.make_goal(kind), model, act0, np.zeros(1), 4, 1, 3, None, None)
+        got = planner.trajectory_optimization_ptcl_multi_traj(*args)
+        fresh = P.PlannerGD(cfg, env).trajectory_optimization_ptcl_multi_traj(*args)
+        assert np.array_equal(got["reward_full"], fresh["reward_full"]), kind
+        assert np.array_equal(got["action_full"], fresh["action_full"]), kind
+        assert np.array_equal(got["reward"], fresh["reward"]), kind
+        res.setdefault(kind, got)
+    assert not np.array_equal(res["bar"]["reward_full"], res["disc"]["reward_full"])
+    # the reward entry point with a torch goal: same storage address, different contents
+    planner.particle_num = 50
+    s = torch.tensor(st, device=DEV)
+    coor = planner.goal_coordinates(synthetic.make_goal("bar"), torch.device(DEV))
+    r = []
+    for kind in ("bar", "disc"):
+        goal_t = torch.tensor(synthetic.make_goal(kind), device=DEV)
+        r.append(P.config_reward_ptcl(s, goal_t, env.get_cam_params(), coor, cache=planner.goals).cpu().numpy())
+        ref = P.config_reward_ptcl(s, goal_t, env.get_cam_params(), coor).cpu().numpy()
+        assert np.array_equal(r[-1], ref), kind
+        del goal_t
+    assert not np.array_equal(r[0], r[1])
+
+
+def test_mppi_planner_matches_oracle_composition(setup):
+    """trajectory_optimization_mppi == sample_action_sequences -> rollout -> last-step reward -> softmax-weighted mean
+    written with the oracle pieces (reference planners.py:69-190, 302-370, 549-561), same numpy seed."""
+    cfg, env, model, planner = setup
+    N, T, NS, iters = 60, 4, 48, 2
+    st, dn = synthetic.make_pile_batch(1, N, seed=12)
+    goal = synthetic.make_goal("bar")
+    mean0 = synthetic.random_actions(1, T, seed=12, lim=3.0)[0]
+    got = planner.trajectory_optimization_mppi(st, dn, np.zeros((1, N), np.float32), goal, model, mean0, n_sample=NS,
+                                               n_update_iter=iters, seed=4)
+    W = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    coords = np.argwhere(goal < 0.5)[:, ::-1].astype(np.float32)
+    coor, _ = synthetic.fps_np(coords, min(5 * N, len(coords)), 0)
+    np.random.seed(4)
+    mean = np.asarray(mean0, dtype=np.float64).reshape(T, 1, 4)
+    for _ in range(iters):
+        sampled = O.sample_action_sequences(mean, NS, cfg["mpc"]["sigma"] * synthetic.GLOBAL_SCALE / 12.0,
+                                            cfg["mpc"]["mppi"]["beta_filter"], env.cvx_region)
+        with torch.no_grad():
+            pred = O.rollout(W, 0.08, env.get_cam_extrinsics(), synthetic.GLOBAL_SCALE, torch.tensor(st), torch.tensor(dn),
+                             torch.zeros(1, N), torch.tensor(sampled[:, :, 0, :], dtype=torch.float))
+            rew = O.reward_ptcl(pred[:, -1], torch.from_numpy(goal), env.get_cam_params(), torch.from_numpy(coor))
+        mean = O.mppi_optimize_action(sampled, rew.numpy()[:, None].astype(np.float64), cfg["mpc"]["mppi"]["reward_weight"])
+    np.testing.assert_allclose(got["reward"], rew.numpy(), rtol=2e-4)
+    np.testing.assert_allclose(got["action_sequence"], mean[:, 0, :], rtol=0, atol=1e-4)

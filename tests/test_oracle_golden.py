@@ -61,6 +61,35 @@ def test_rollout_reward_and_action_gradient(golden, golden_weights):
     np.testing.assert_allclose(g, ref, rtol=2e-3, atol=2e-4 * np.abs(ref).max())
 
 
+def test_oracle_at_baseline_sizes(golden, golden_big, golden_weights):
+    """golden_big_v1.npz: one step at 8 x 300 and the T=10 / T=20 rollouts at 100 / 300 particles (incl. action
+    gradients through the reference's autograd): the oracle must reproduce the reference at BASELINE's sizes too."""
+    from conftest import tamed_weights
+    g = golden_big
+    adj = O.adjacency(torch.from_numpy(g["F/s_cur"]), torch.from_numpy(g["F/s_delta"]), 0.08)
+    assert np.array_equal(_coo(adj), g["F/rel"])
+    with torch.no_grad():
+        out = O.predict_one_step(golden_weights, 0.08, torch.zeros(8, 300), torch.from_numpy(g["F/s_cur"]),
+                                 torch.from_numpy(g["F/s_delta"]), torch.from_numpy(g["F/dens"]))
+    np.testing.assert_allclose(out.numpy(), g["F/s_pred"], rtol=0, atol=2e-6)
+    for tag in ("G", "J", "K"):
+        nb, ns, N, T = [int(v) for v in g[tag + "/dims"]]
+        W = tamed_weights(golden_weights, float(g[tag + "/tame"]))
+        acts = torch.tensor(g[tag + "/acts"], requires_grad=True)
+        pred, adjs = O.rollout(W, 0.08, golden["cam_extrinsic"], synthetic.GLOBAL_SCALE, torch.from_numpy(g[tag + "/s0"]),
+                               torch.from_numpy(g[tag + "/dens"]), torch.zeros(nb, N), acts, return_adj=True)
+        for t, a in enumerate(adjs):
+            assert np.array_equal(_coo(a), g[tag + "/rel%d" % t]), (tag, t)
+        np.testing.assert_allclose(pred.detach().numpy(), g[tag + "/state_pred"], rtol=0, atol=1e-5)
+        goal = torch.from_numpy(synthetic.make_goal(str(g[tag + "/goal_kind"])))
+        obs = pred.reshape(ns * nb, 1, T, N, 3).permute(0, 2, 1, 3, 4)
+        reward, next_r = O.evaluate_traj(obs, goal, list(golden["cam_params"]), torch.from_numpy(g[tag + "/goal_coor"]))
+        np.testing.assert_allclose(next_r.detach().numpy(), g[tag + "/next_r"], rtol=1e-5)
+        torch.sum(-reward).backward()
+        ref = g[tag + "/act_grad"]
+        np.testing.assert_allclose(acts.grad.numpy(), ref, rtol=2e-3, atol=2e-4 * np.abs(ref).max())
+
+
 def test_mppi_pieces(golden):
     env = synthetic.FakeEnv()
     np.random.seed(12)

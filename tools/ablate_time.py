@@ -19,7 +19,7 @@ eng.load_state(st, dn)
 eng.actions.copy_(torch.from_numpy(synthetic.random_actions(B, 1, seed=1)))
 eng.evaluate(); torch.cuda.synchronize()
 lib = _lib.load()
-ms6 = (_lib.C.c_float * 6)()
+ms6 = (_lib.C.c_float * 9)()
 s_out = torch.empty(B, N, 3, device="cuda")
 wpack = model.model.packed_weights(torch.device("cuda"))
 _lib.check(lib.pile_profile_step(_lib.ptr(wpack), _lib.ptr(eng.attr), _lib.ptr(eng.dens), _lib.ptr(eng.s0),
