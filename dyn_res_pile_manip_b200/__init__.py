@@ -9,6 +9,7 @@ from . import _lib, ops, synthetic  # noqa: F401
 from .propnet import PropModuleDiffDen, PropNetDiffDenModel  # noqa: F401
 from .planner import Planner, PlannerGD, particle_num_to_iter_time  # noqa: F401
 from .rewards import config_reward_ptcl  # noqa: F401
+from .regressor import MPCResRgrNoPool  # noqa: F401
 
-__all__ = ["PropNetDiffDenModel", "PropModuleDiffDen", "Planner", "PlannerGD", "config_reward_ptcl",
+__all__ = ["PropNetDiffDenModel", "PropModuleDiffDen", "Planner", "PlannerGD", "config_reward_ptcl", "MPCResRgrNoPool",
            "particle_num_to_iter_time", "ops", "synthetic"]

@@ -134,6 +134,8 @@ int pile_debug_set_trace(long long* device_buf, int capacity, int which) {
   return which == 0 ? set_edge_trace(device_buf, capacity) : set_node_trace(device_buf, capacity);
 }
 
+int pile_debug_set_nbr_split(int split) { return set_nbr_split(split); }
+
 int pile_wpack_num_slots(void) { return W_NUM; }
 long long pile_wpack_slot_offset(int slot) { return (slot < 0 || slot > W_NUM) ? -1 : wslot_offset(slot); }
 long long pile_wpack_slot_size(int slot) { return (slot < 0 || slot >= W_NUM) ? -1 : wslot_size(slot); }
@@ -449,6 +451,16 @@ int pile_gd_track(const float* reward, const float* actions, int n_sample, int n
     return (int)cudaErrorInvalidValue;
   return launch_gd_track(reward, actions, n_sample, n_batch, T, max_reward, max_idx, best_actions, rew_mean, rew_std,
                          iter_dev, (cudaStream_t)stream);
+}
+
+long long pile_rgr_param_offset(int tensor_index) {
+  return (tensor_index < 0 || tensor_index > 20) ? -1 : rgr_param_offset(tensor_index);
+}
+long long pile_rgr_workspace_bytes(int B, int H, int W) { return rgr_workspace_bytes(B, H, W); }
+int pile_rgr_forward(const float* params, const float* x, int B, int H, int W, void* workspace, float* y,
+                     void* stream) {
+  if (!params || !x || !workspace || !y) return (int)cudaErrorInvalidValue;
+  return launch_rgr_forward(params, x, B, H, W, workspace, y, (cudaStream_t)stream);
 }
 
 int pile_mppi_num_chunks(int S) { return mppi_num_chunks(S); }

@@ -44,6 +44,7 @@ struct StepScratch {
 int launch_gen_s_delta(const float* s_cur, long long s_stride, const float* action, int act_stride,
                        const PushCam& cam, int B, int N, float* s_delta, cudaStream_t st);
 size_t nbr_smem_bytes(int N);
+int set_nbr_split(int split);   // 0 = automatic (by batch size), 1..3 = forced pieces per receiver; returns the old value
 // s_delta either given (s_delta_in) or computed from `action` and written to s_delta_out
 int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_delta_in, const float* action,
                       int act_stride, const PushCam& cam, float* s_delta_out, const int* particle_nums, int B,
@@ -123,6 +124,11 @@ int mppi_num_chunks(int S);
 int launch_mppi_partials(const float* reward, const float* acts, int S, int T, float weight, float* part,
                          cudaStream_t st);
 int launch_mppi_combine(const float* part, int P, int T, float* out, cudaStream_t st);
+
+// resolution regressor (rgr.cu)
+long long rgr_param_offset(int idx);
+long long rgr_workspace_bytes(int B, int H, int W);
+int launch_rgr_forward(const float* params, const float* x, int B, int H, int W, void* ws, float* y, cudaStream_t st);
 
 size_t bwd_scratch_bytes(int B, int N);
 // backward of one model step: g_pred [B,N,3] (strided) -> g_s_cur [B,N,3] dense (overwritten, includes the

@@ -137,7 +137,14 @@ __device__ __forceinline__ int block_exscan(int v, int* warp_sums, int* total) {
 }
 
 // One CTA per sample.  Optional fused s_delta (action != nullptr).
+// SPLIT > 1 (small batches, where one 10-warp CTA per SM is latency-bound): the candidate range of every receiver is
+// cut into SPLIT contiguous pieces scanned by SPLIT different warps (thread = piece * T0 + receiver slot, T0 =
+// blockDim / SPLIT); the pieces share their admission bound through shared memory (a candidate farther than ANY
+// piece's current 10th best cannot be in the union's top 10) and the SPLIT sorted lists are merged by (distance,
+// index) -- the same order a single ascending scan produces, so the relation set is identical.
 // dynamic smem: pos[N] (float4) | cutd[N] | cuti[N] | deg[N] | roff[N+1] | sel[N*KMAX] | perm[N]
+//               | SPLIT > 1: bound[N] | list_d[SPLIT*N*KMAX] | list_j[SPLIT*N*KMAX]
+template <int SPLIT>
 __global__ void __launch_bounds__(NBR_THREADS)
 k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* __restrict__ s_delta_in,
              const float* __restrict__ action, int act_stride, PushCam cam, float* __restrict__ s_delta_out,
@@ -153,6 +160,9 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
   int* roff = deg + N;           // N+1
   int* sel = roff + (N + 1);     // N*KMAX
   int* perm = sel + N * KMAX;    // N: receivers in coarse spatial order (which lane handles which receiver)
+  int* bound = perm + N;         // SPLIT > 1: per receiver, min over the pieces of the 10th best distance (float bits)
+  float* list_d = reinterpret_cast<float*>(bound + N);     // [SPLIT][N][KMAX]
+  int* list_j = reinterpret_cast<int*>(list_d + SPLIT * N * KMAX);
   __shared__ int warp_sums[NBR_THREADS / 32];
   __shared__ int total_s;
   __shared__ float box[6];
@@ -241,9 +251,17 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
   // so candidates are parked in a 3-deep per-lane FIFO and the warp runs the insertion code only when a lane's
   // FIFO is full: ~5x fewer executions on a 300-particle pile.  The pre-filter then uses a slightly stale
   // 10th-best distance, which only lets a few extra candidates through; the insertion itself re-checks.
-  for (int base_i = 0; base_i < N; base_i += blockDim.x) {     // every thread takes part in the warp votes
-    const bool active = base_i + (int)threadIdx.x < N;
-    const int i = active ? perm[base_i + threadIdx.x] : N;
+  const int T0 = (int)blockDim.x / SPLIT;                // receiver slots per pass; a multiple of 32
+  const int piece = (int)threadIdx.x / T0, slot = (int)threadIdx.x - piece * T0;      // piece is warp-uniform
+  const int jper = (N + SPLIT - 1) / SPLIT;
+  const int jlo = min(piece * jper, N), jhi = min(jlo + jper, N);
+  for (int base_i = 0; base_i < N; base_i += T0) {     // every thread takes part in the warp votes
+    const bool active = base_i + slot < N;
+    const int i = active ? perm[base_i + slot] : N;
+    if (SPLIT > 1) {
+      if (piece == 0 && active) bound[i] = 0x7f800000;
+      __syncthreads();
+    }
     float bd[KMAX];
     int id[KMAX];
 #pragma unroll
@@ -272,11 +290,22 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
           bd[s] = nd; id[s] = ni;
         }
         if (d < bd[0]) { bd[0] = d; id[0] = j; }
-        lim = fminf(thr, bd[KMAX - 1]);
+        if (SPLIT == 1) {
+          lim = fminf(thr, bd[KMAX - 1]);
+        } else {
+          // publish this piece's 10th best, take the tightest one of all pieces.  A candidate AT another piece's
+          // bound may still win by its lower index, so foreign bounds admit d <= bound: compare against the next
+          // float up (the insertion and the final merge re-check exactly)
+          const int mine = __float_as_int(bd[KMAX - 1]);          // non-negative floats order like their bit patterns
+          if (mine < 0x7f800000) atomicMin(&bound[ic], mine);
+          const int seen = bound[ic];
+          const float up = seen < 0x7f800000 ? __int_as_float(seen + 1) : __int_as_float(0x7f800000);
+          lim = fminf(thr, up);
+        }
       }
     };
 #pragma unroll 4
-    for (int j = 0; j < N; ++j) {
+    for (int j = jlo; j < jhi; ++j) {
       const float4 pj = pos[j];
       const float d = sqdist_rn(xi, yi, zi, pj.x, pj.y, pj.z);
       if (d < lim) {
@@ -286,7 +315,40 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
       if (__any_sync(0xffffffffu, qn == 3)) drain_one();
     }
     while (__any_sync(0xffffffffu, qn > 0)) drain_one();
-    if (active) {
+    if (SPLIT > 1) {
+      // every piece leaves its sorted list in shared memory; piece 0 merges them by (distance, index)
+      if (active) {
+#pragma unroll
+        for (int s = 0; s < KMAX; ++s) {
+          list_d[(piece * N + i) * KMAX + s] = bd[s];
+          list_j[(piece * N + i) * KMAX + s] = id[s];
+        }
+      }
+      __syncthreads();
+      if (piece == 0 && active) {
+        int head[SPLIT];
+#pragma unroll
+        for (int q = 0; q < SPLIT; ++q) head[q] = 0;
+#pragma unroll
+        for (int s = 0; s < KMAX; ++s) {
+          float best_d = __int_as_float(0x7f800000);
+          int best_j = 0x7fffffff, best_q = 0;
+#pragma unroll
+          for (int q = 0; q < SPLIT; ++q) {
+            // heads past the end read as (+inf, INT_MAX); pieces hold ascending index ranges, so on equal distances
+            // the lower piece has the lower index: strict '<' keeps it
+            const float dq = head[q] < KMAX ? list_d[(q * N + i) * KMAX + head[q]] : __int_as_float(0x7f800000);
+            const int jq = head[q] < KMAX ? list_j[(q * N + i) * KMAX + head[q]] : 0x7fffffff;
+            if (dq < best_d || (dq == best_d && jq < best_j)) { best_d = dq; best_j = jq; best_q = q; }
+          }
+#pragma unroll
+          for (int q = 0; q < SPLIT; ++q) head[q] += (q == best_q && best_j != 0x7fffffff) ? 1 : 0;
+          bd[s] = best_d;
+          id[s] = best_j;
+        }
+      }
+    }
+    if (active && piece == 0) {
       cutd[i] = bd[KMAX - 1];          // +inf when fewer than 10 in radius
       cuti[i] = id[KMAX - 1];
       int n = 0;
@@ -302,6 +364,7 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
       for (int s = 0; s < KMAX; ++s) sel[i * KMAX + s] = (i < nvalid) ? id[s] : 0x7fffffff;
       deg[i] = n;
     }
+    if (SPLIT > 1) __syncthreads();     // the lists and bounds are rewritten by the next pass
   }
   __syncthreads();
 
@@ -541,26 +604,50 @@ int launch_gen_s_delta(const float* s_cur, long long s_stride, const float* acti
   return 0;
 }
 
-size_t nbr_smem_bytes(int N) { return sizeof(float) * (size_t)(4 * N + N) + sizeof(int) * (size_t)(N + N + N + 1 + N * KMAX + N); }
+static size_t nbr_smem_bytes_split(int N, int split) {
+  size_t b = sizeof(float) * (size_t)(4 * N + N) + sizeof(int) * (size_t)(N + N + N + 1 + N * KMAX + N);
+  if (split > 1) b += sizeof(int) * (size_t)N + 2 * sizeof(float) * (size_t)split * N * KMAX;
+  return b;
+}
+size_t nbr_smem_bytes(int N) { return nbr_smem_bytes_split(N, 1); }
+
+// pieces per receiver: 1 when the batch alone fills the SMs with warps, up to 3 for small batches
+static std::atomic<int> g_nbr_split_override{0};
+int set_nbr_split(int split) { return g_nbr_split_override.exchange(split < 0 ? 0 : (split > 3 ? 3 : split)); }
+
+static int nbr_split(int B, int T0, int N) {
+  const int forced = g_nbr_split_override.load();
+  int split = 1;
+  const double fill = (double)B * T0 / (148.0 * 1024.0);       // resident threads per SM / 1024
+  if (fill < 0.6) split = 3;
+  else if (fill < 1.3) split = 2;
+  if (forced >= 1 && forced <= 3) split = forced;
+  while (split > 1 && (split * T0 > NBR_THREADS || nbr_smem_bytes_split(N, split) > 200 * 1024)) --split;
+  return split;
+}
 
 int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_delta_in, const float* action,
                       int act_stride, const PushCam& cam, float* s_delta_out, const int* particle_nums, int B,
                       int N, float thr, const Csr& csr, cudaStream_t st, const float* attr, const float* dens,
                       float* efeat) {
-  const size_t smem = nbr_smem_bytes(N);
-  if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+  if (nbr_smem_bytes(N) > 200 * 1024) return (int)cudaErrorInvalidValue;
   static DeviceOnce once;
   const int dev = once.pending();
   if (dev >= 0) {
-    cudaError_t e = cudaFuncSetAttribute(k_nbr_search, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_nbr_search<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_nbr_search<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_nbr_search<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
     once.done(dev);
   }
   int threads = (N + 31) / 32 * 32;
   threads = threads < 64 ? 64 : (threads > NBR_THREADS ? NBR_THREADS : threads);
-  k_nbr_search<<<B, threads, smem, st>>>(s_cur, s_stride, s_delta_in, action, act_stride, cam, s_delta_out,
-                                             particle_nums, N, thr, csr.rowptr, csr.col, csr.row, csr.trowptr,
-                                             csr.trecv, csr.tedge, attr, dens, efeat);
+  const int split = nbr_split(B, threads, N);
+  const size_t smem = nbr_smem_bytes_split(N, split);
+  auto kern = split == 3 ? k_nbr_search<3> : (split == 2 ? k_nbr_search<2> : k_nbr_search<1>);
+  kern<<<B, threads * split, smem, st>>>(s_cur, s_stride, s_delta_in, action, act_stride, cam, s_delta_out,
+                                         particle_nums, N, thr, csr.rowptr, csr.col, csr.row, csr.trowptr,
+                                         csr.trecv, csr.tedge, attr, dens, efeat);
   PILE_CHECK_LAUNCH();
   return 0;
 }

@@ -15,10 +15,30 @@ from .rewards import config_reward_ptcl
 
 
 class MPCStep:
-    def __init__(self, planner, model_dy, env, batch_size=30):
-        """planner: PlannerGD; env: anything with get_cam_params() and global_scale (FlexEnv's interface)."""
+    def __init__(self, planner, model_dy, env, batch_size=30, res_rgr=None, resolution_buckets=None):
+        """planner: PlannerGD; env: anything with get_cam_params() and global_scale (FlexEnv's interface);
+        res_rgr: optional `regressor.MPCResRgrNoPool` -- the dynamic-resolution loop of step_subgoal_ptcl with
+        auto_particle_r=True (flex_env.py:981-998, 1080-1090): when `plan` is called without a particle count the
+        regressor picks it from (foreground mask, goal mask).  resolution_buckets: optional ascending list of
+        allowed counts; the regressor's output is snapped to the nearest one (fewer distinct problem sizes means
+        the planner's captured loops are reused more often).  Default: the reference's behaviour, the raw count."""
         self.planner, self.model_dy, self.env = planner, model_dy, env
         self.batch_size = int(batch_size)
+        self.res_rgr = res_rgr
+        self.resolution_buckets = None if resolution_buckets is None else sorted(int(b) for b in resolution_buckets)
+
+    def select_resolution(self, obs, subgoal):
+        """particle_num = res_rgr.infer_param(fg_mask, subgoal_mask)  (flex_env.py:993-997)."""
+        if self.res_rgr is None:
+            raise ValueError("MPCStep was built without a resolution regressor: pass particle_num")
+        fg_mask = (np.asarray(obs)[..., -1] / self.env.global_scale < 0.599 / 0.8).astype(np.float32)
+        subgoal_mask = (np.asarray(subgoal) < 0.5).astype(np.float32)
+        n = int(self.res_rgr.infer_param(fg_mask, subgoal_mask))
+        if self.resolution_buckets:
+            n = min(self.resolution_buckets, key=lambda b: (abs(b - n), b))
+        if n < 1:
+            raise ValueError("resolution regressor returned %d particles" % n)
+        return n
 
     def observe(self, obs, particle_num, init_idx=None, seed=None):
         """obs [H,W,5] -> (particles [batch,N,3] float64, particle_den [batch]) as flex_env.py:1028-1030."""
@@ -37,11 +57,16 @@ class MPCStep:
         return config_reward_ptcl(state, goal, cam_params=self.env.get_cam_params(), goal_coor=coor,
                                   normalize=True)[0].item()
 
-    def plan(self, obs, subgoal, particle_num, action_seq_mpc_init, action_label_seq_mpc_init, n_sample, n_look_ahead,
-             n_update_iter, action_lower_lim, action_upper_lim, gd_loop=1, time_lim=float('inf'), reward_params=None,
-             init_idx=None, seed=None):
-        """One MPC step: -> dict(action, traj_opt_out, obs_cur, particle_den, reward, action_seq_mpc_init,
-        action_label_seq_mpc_init) where the last two are the warm start of the next step."""
+    def plan(self, obs, subgoal, particle_num=None, action_seq_mpc_init=None, action_label_seq_mpc_init=None,
+             n_sample=None, n_look_ahead=1, n_update_iter=100, action_lower_lim=None, action_upper_lim=None, gd_loop=1,
+             time_lim=float('inf'), reward_params=None, init_idx=None, seed=None):
+        """One MPC step: -> dict(action, traj_opt_out, obs_cur, particle_den, particle_num, reward,
+        action_seq_mpc_init, action_label_seq_mpc_init) where the last two are the warm start of the next step.
+        particle_num=None: the resolution regressor selects it (dynamic resolution)."""
+        if particle_num is None:
+            particle_num = self.select_resolution(obs, subgoal)
+        if n_sample is None:
+            n_sample = action_seq_mpc_init.shape[1]
         obs_cur, particle_den = self.observe(obs, particle_num, init_idx, seed)
         attr_cur = np.zeros((obs_cur.shape[0], particle_num))
         out = self.planner.trajectory_optimization_ptcl_multi_traj(
@@ -56,5 +81,5 @@ class MPCStep:
         if action_seq_mpc_init.shape[0] > 1 and action_label_seq_mpc_init is not None:
             nxt_label = action_label_seq_mpc_init[1:]
         return {'action': out['action_sequence'][0], 'traj_opt_out': out, 'obs_cur': obs_cur,
-                'particle_den': particle_den, 'reward': self.reward(obs_cur, subgoal),
+                'particle_den': particle_den, 'particle_num': int(particle_num), 'reward': self.reward(obs_cur, subgoal),
                 'action_seq_mpc_init': nxt, 'action_label_seq_mpc_init': nxt_label}

@@ -37,6 +37,11 @@ int pile_get_tensor_cores(void);
  * (tag << 56 | clock64) stamps of its per-layer phases into device_buf[0..capacity). NULL disables. */
 int pile_debug_set_trace(long long* device_buf, int capacity, int which /*0 relation encoder, 1 particle kernels*/);
 
+/* test hook: the relation search cuts every receiver's candidate range into 1..3 pieces scanned by different warps
+ * (chosen from the batch size so that small batches still fill the SMs); 0 = automatic, 1..3 = forced.  The relation
+ * set does not depend on it.  Returns the previous setting. */
+int pile_debug_set_nbr_split(int split);
+
 /* ---- packed weights ---------------------------------------------------------------------------
  * The host packs the 18 checkpoint tensors into one float buffer; slots are listed in
  * csrc/common.cuh (enum WSlot): transposed [in][out] blocks for the forward, [out][in] for the dgrad. */
@@ -191,6 +196,17 @@ int pile_cover_radius(const double* cloud, int m, const float* picks, int n_sets
  * out[set][k] = mean of the cloud points closer than r to pick k, float32 like the reference's zeros_like(picks). */
 int pile_recenter(const double* cloud, int m, const float* picks, int n_sets, int count, const double* radius,
                   double r_cap, double r_scale, float* out, void* stream);
+
+/* ---- resolution regressor: replaces MPCResRgrNoPool.forward (model/res_regressor.py:106-144), the network that
+ * picks the particle count once per MPC step (env/flex_env.py:981-998, 1080-1090).  params: all 20 tensors of the
+ * module's state_dict in its own order (model.0.weight, model.0.bias, model.2.weight, ... model.19.bias) flattened
+ * into one float buffer; pile_rgr_param_offset(2*l) / (2*l+1) = offset of layer l's weight / bias (l = 0..9),
+ * pile_rgr_param_offset(20) = total floats (114 193 217).  x [B, 6, H, W] (H = W = 224: five stride-2 convolutions
+ * must end at 7 x 7), y [B, 1].  workspace: pile_rgr_workspace_bytes(B, H, W) bytes (-1: unsupported size). */
+long long pile_rgr_param_offset(int tensor_index);
+long long pile_rgr_workspace_bytes(int B, int H, int W);
+int pile_rgr_forward(const float* params, const float* x, int B, int H, int W, void* workspace, float* y,
+                     void* stream);
 
 /* ---- MPPI weighting: replaces PlannerGD.optimize_action (planners.py:549-561) -------------------
  * partials: [pile_mppi_num_chunks(S)][2 + 4T] = (max z, sum exp(z-max), sum exp(z-max)*act) with

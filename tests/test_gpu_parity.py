@@ -81,6 +81,29 @@ def test_relation_sets_bit_exact_vs_oracle(N, B):
     assert deg.min() >= 1 and deg.max() <= min(10, N)
 
 
+@pytest.mark.parametrize("split", [1, 2, 3])
+@pytest.mark.parametrize("N,B", [(1, 2), (7, 3), (10, 3), (33, 5), (100, 4), (300, 3), (341, 2), (500, 2)])
+def test_relation_search_pieces_give_identical_sets(N, B, split):
+    """The candidate range of a receiver may be scanned in 1..3 pieces by different warps (small batches): every
+    split must give the reference's relation set, including exact ties (duplicated points) at the 10th place."""
+    rng = np.random.RandomState(100 + N)
+    s = rng.uniform(-.12, .12, (B, N, 3)).astype(np.float32)
+    s[..., 2] = 0.74
+    if N >= 33:
+        s[:, N // 2:N // 2 + 12] = s[:, 5:6]                  # 13 coincident particles: ties across piece borders
+        s[:, N - 3:] = s[:, 0:1] + np.float32(0.01)
+    sd = (rng.normal(0, 0.02, size=s.shape) * (rng.uniform(size=s.shape[:2] + (1,)) < 0.3)).astype(np.float32)
+    nums = np.array([N] + [max(1, N - 3 - b) for b in range(1, B)], dtype=np.int32)
+    adj = O.adjacency(torch.from_numpy(s), torch.from_numpy(sd), 0.08, nums)
+    lib = ops._lib.load()
+    old = lib.pile_debug_set_nbr_split(split)
+    try:
+        rel = ops.build_relations(cuda(s), cuda(sd), 0.08, nums)
+    finally:
+        lib.pile_debug_set_nbr_split(old)
+    assert np.array_equal(coo_from_relations(rel), adj.nonzero().to(torch.int16).numpy())
+
+
 def test_relations_duplicate_points_lowest_index_wins():
     # 14 coincident particles: every distance ties at 0 -> the 10 lowest sender indices must be kept
     s = np.zeros((1, 14, 3), dtype=np.float32)

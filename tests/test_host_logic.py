@@ -171,3 +171,26 @@ def test_from_dense_rejects_more_than_ten_relations_per_receiver():
     rr[0, 10:, 4] = 1.0                                # ten into particle 3, two into particle 4: fine
     rel = ops.Relations.from_dense(rr, rs)
     assert rel.rowptr[0, 4].item() - rel.rowptr[0, 3].item() == 10
+
+
+def test_regressor_module_matches_reference_layout_and_init():
+    """dyn_res_pile_manip_b200.regressor.MPCResRgrNoPool: the reference's state_dict keys and, under the same seed,
+    its initial weights (oracle.regressor_oracle.build_network reproduces the reference's construction, pinned by
+    tests/golden/golden_rgr_v1.npz); the input builder is the reference's cv2 sequence."""
+    from oracle import regressor_oracle as RO
+    from dyn_res_pile_manip_b200.regressor import MPCResRgrNoPool, regressor_input
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_rgr_v1.npz"))
+    torch.manual_seed(int(g["seed"]))
+    mine = MPCResRgrNoPool({"train_res_cls": {"state_h": 224, "state_w": 224, "res_dim": 6}})
+    ref = RO.build_network(int(g["seed"]))
+    sd, rsd = mine.state_dict(), ref.state_dict()
+    assert list(sd) == ["model." + k for k in rsd]
+    assert list(sd)[0] == "model.0.weight" and list(sd)[-1] == "model.19.bias"
+    for k, v in rsd.items():
+        assert torch.equal(sd["model." + k], v), k
+    x = regressor_input(g["fg"].astype(np.float32), g["goal"].astype(np.float32), 224, 224)
+    assert np.array_equal(x, g["x"])
+    lib = _lib.load()
+    assert lib.pile_rgr_param_offset(20) == sum(v.numel() for v in sd.values()) == 114_193_217
+    assert lib.pile_rgr_param_offset(1) == 6 * 64 * 16
+    assert lib.pile_rgr_workspace_bytes(1, 224, 224) > 0 and lib.pile_rgr_workspace_bytes(1, 200, 200) == -1
