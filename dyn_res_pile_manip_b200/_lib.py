@@ -36,7 +36,6 @@ SIGNATURES = {
     "pile_set_tensor_cores": (_I, [_I]),
     "pile_get_tensor_cores": (_I, []),
     "pile_debug_set_trace": (_I, [_P, _I, _I]),
-    "pile_debug_set_nbr_split": (_I, [_I]),
     "pile_wpack_num_slots": (_I, []),
     "pile_wpack_slot_offset": (_LL, [_I]),
     "pile_wpack_slot_size": (_LL, [_I]),
@@ -68,6 +67,12 @@ SIGNATURES = {
     "pile_voxel_downsample": (_I, [_P, _I, _D, _P, _P, _P, _P]),
     "pile_cover_radius": (_I, [_P, _I, _P, _I, _I, _P, _P]),
     "pile_recenter": (_I, [_P, _I, _P, _I, _I, _P, _D, _D, _P, _P]),
+    "pile_train_tape_bytes": (_LL, [_I, _I]),
+    "pile_train_scratch_bytes": (_LL, [_I, _I]),
+    "pile_train_grad_offset": (_LL, [_I]),
+    "pile_train_forward": (_I, [_P, _P, _P, _P, _P, _P, _F, _I, _I, _P, _P, _P]),
+    "pile_train_backward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "pile_train_relations_view": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "pile_rgr_param_offset": (_LL, [_I]),
     "pile_rgr_workspace_bytes": (_LL, [_I, _I, _I]),
     "pile_rgr_forward": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),

@@ -134,8 +134,6 @@ int pile_debug_set_trace(long long* device_buf, int capacity, int which) {
   return which == 0 ? set_edge_trace(device_buf, capacity) : set_node_trace(device_buf, capacity);
 }
 
-int pile_debug_set_nbr_split(int split) { return set_nbr_split(split); }
-
 int pile_wpack_num_slots(void) { return W_NUM; }
 long long pile_wpack_slot_offset(int slot) { return (slot < 0 || slot > W_NUM) ? -1 : wslot_offset(slot); }
 long long pile_wpack_slot_size(int slot) { return (slot < 0 || slot >= W_NUM) ? -1 : wslot_size(slot); }
@@ -451,6 +449,32 @@ int pile_gd_track(const float* reward, const float* actions, int n_sample, int n
     return (int)cudaErrorInvalidValue;
   return launch_gd_track(reward, actions, n_sample, n_batch, T, max_reward, max_idx, best_actions, rew_mean, rew_std,
                          iter_dev, (cudaStream_t)stream);
+}
+
+long long pile_train_tape_bytes(int B, int N) { return bad_dims(B, N) ? -1 : train_tape_bytes(B, N); }
+long long pile_train_scratch_bytes(int B, int N) { return bad_dims(B, N) ? -1 : train_bwd_scratch_bytes(B, N); }
+long long pile_train_grad_offset(int tensor_index) { return train_grad_offset(tensor_index); }
+
+int pile_train_forward(const float* wpack, const float* attr, const float* dens, const int* particle_nums,
+                       const float* s_cur, const float* s_delta, float adj_thresh, int B, int N, void* train_tape,
+                       float* s_pred, void* stream) {
+  if (bad_dims(B, N) || !wpack || !attr || !dens || !s_cur || !s_delta || !train_tape || !s_pred)
+    return (int)cudaErrorInvalidValue;
+  return launch_train_forward(wpack, attr, dens, particle_nums, s_cur, s_delta, adj_thresh, B, N, train_tape, s_pred,
+                              (cudaStream_t)stream);
+}
+
+int pile_train_backward(const float* wpack, const float* dens, void* train_tape, int B, int N, const float* g_pred,
+                        float* g_s_cur, float* g_s_delta, float* grads, void* scratch, void* stream) {
+  if (bad_dims(B, N) || !wpack || !dens || !train_tape || !g_pred || !g_s_cur || !g_s_delta || !grads || !scratch)
+    return (int)cudaErrorInvalidValue;
+  return launch_train_backward(wpack, dens, train_tape, B, N, g_pred, g_s_cur, g_s_delta, grads, scratch,
+                               (cudaStream_t)stream);
+}
+
+int pile_train_relations_view(void* train_tape, int B, int N, int** rowptr, int** col, int** row) {
+  if (!train_tape || bad_dims(B, N)) return (int)cudaErrorInvalidValue;
+  return train_relations_view(train_tape, B, N, rowptr, col, row);
 }
 
 long long pile_rgr_param_offset(int tensor_index) {

@@ -44,7 +44,6 @@ struct StepScratch {
 int launch_gen_s_delta(const float* s_cur, long long s_stride, const float* action, int act_stride,
                        const PushCam& cam, int B, int N, float* s_delta, cudaStream_t st);
 size_t nbr_smem_bytes(int N);
-int set_nbr_split(int split);   // 0 = automatic (by batch size), 1..3 = forced pieces per receiver; returns the old value
 // s_delta either given (s_delta_in) or computed from `action` and written to s_delta_out
 int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_delta_in, const float* action,
                       int act_stride, const PushCam& cam, float* s_delta_out, const int* particle_nums, int B,
@@ -124,6 +123,17 @@ int mppi_num_chunks(int S);
 int launch_mppi_partials(const float* reward, const float* acts, int S, int T, float weight, float* part,
                          cudaStream_t st);
 int launch_mppi_combine(const float* part, int P, int T, float* out, cudaStream_t st);
+
+// training path (train.cu): forward that keeps every layer input, backward with weight gradients
+long long train_tape_bytes(int B, int N);
+long long train_bwd_scratch_bytes(int B, int N);
+long long train_grad_offset(int tensor_index);
+int train_relations_view(void* tape, int B, int N, int** rowptr, int** col, int** row);
+int launch_train_forward(const float* wpack, const float* attr, const float* dens, const int* particle_nums,
+                         const float* s_cur, const float* s_delta, float adj_thresh, int B, int N, void* tape,
+                         float* s_pred, cudaStream_t st);
+int launch_train_backward(const float* wpack, const float* dens, void* tape, int B, int N, const float* g_pred,
+                          float* g_s_cur, float* g_s_delta, float* grads, void* scratch, cudaStream_t st);
 
 // resolution regressor (rgr.cu)
 long long rgr_param_offset(int idx);

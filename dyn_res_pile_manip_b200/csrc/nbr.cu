@@ -136,15 +136,20 @@ __device__ __forceinline__ int block_exscan(int v, int* warp_sums, int* total) {
   return warp_sums[warp] + inc - v;
 }
 
+// packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2, two IEEE round-to-nearest results per instruction).  Only the
+// subtraction and the multiplication are packed: ptxas contracts a packed multiply feeding a packed add into FFMA2
+// even with explicit .rn (seen in SASS), which would break bit-exactness against torch's separately rounded
+// (d*d).sum(-1); with scalar __fadd_rn it does not.
+__device__ __forceinline__ uint64_t pack2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t sub2_rn(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t mul2_rn(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+constexpr int NBR_BLOCK = 32;     // candidates per admission mask
+
 // One CTA per sample.  Optional fused s_delta (action != nullptr).
-// SPLIT > 1 (small batches, where one 10-warp CTA per SM is latency-bound): the candidate range of every receiver is
-// cut into SPLIT contiguous pieces scanned by SPLIT different warps (thread = piece * T0 + receiver slot, T0 =
-// blockDim / SPLIT); the pieces share their admission bound through shared memory (a candidate farther than ANY
-// piece's current 10th best cannot be in the union's top 10) and the SPLIT sorted lists are merged by (distance,
-// index) -- the same order a single ascending scan produces, so the relation set is identical.
-// dynamic smem: pos[N] (float4) | cutd[N] | cuti[N] | deg[N] | roff[N+1] | sel[N*KMAX] | perm[N]
-//               | SPLIT > 1: bound[N] | list_d[SPLIT*N*KMAX] | list_j[SPLIT*N*KMAX]
-template <int SPLIT>
+// dynamic smem: pos[N] (float4) | cutd[N] | cuti[N] | deg[N] | roff[N+1] | sel[N*KMAX] | perm[N] | xs[NP] | ys[NP] | zs[NP]
+// (NP = N rounded up to a multiple of 32; the tail of xs holds +inf so that padded candidates are never admitted)
 __global__ void __launch_bounds__(NBR_THREADS)
 k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* __restrict__ s_delta_in,
              const float* __restrict__ action, int act_stride, PushCam cam, float* __restrict__ s_delta_out,
@@ -160,9 +165,11 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
   int* roff = deg + N;           // N+1
   int* sel = roff + (N + 1);     // N*KMAX
   int* perm = sel + N * KMAX;    // N: receivers in coarse spatial order (which lane handles which receiver)
-  int* bound = perm + N;         // SPLIT > 1: per receiver, min over the pieces of the 10th best distance (float bits)
-  float* list_d = reinterpret_cast<float*>(bound + N);     // [SPLIT][N][KMAX]
-  int* list_j = reinterpret_cast<int*>(list_d + SPLIT * N * KMAX);
+  const int NP = (N + NBR_BLOCK - 1) / NBR_BLOCK * NBR_BLOCK;
+  // SoA copy of the positions, 16-byte aligned (the pair loads of phase A are merged into 128-bit loads)
+  float* xs = smem + (19 * N + 1 + 3) / 4 * 4;
+  float* ys = xs + NP;
+  float* zs = ys + NP;
   __shared__ int warp_sums[NBR_THREADS / 32];
   __shared__ int total_s;
   __shared__ float box[6];
@@ -186,8 +193,11 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
       const float* d = s_delta_in + (base + i) * 3;
       dx = d[0]; dy = d[1]; dz = d[2];
     }
-    pos[i] = make_float4(__fadd_rn(x, dx), __fadd_rn(y, dy), __fadd_rn(z, dz), 0.f);
+    const float px = __fadd_rn(x, dx), py = __fadd_rn(y, dy), pz = __fadd_rn(z, dz);
+    pos[i] = make_float4(px, py, pz, 0.f);
+    xs[i] = px; ys[i] = py; zs[i] = pz;
   }
+  for (int i = N + threadIdx.x; i < NP; i += blockDim.x) { xs[i] = __int_as_float(0x7f800000); ys[i] = 0.f; zs[i] = 0.f; }
   __syncthreads();
 
   // Which lane handles which receiver does not change any result (every receiver scans all candidates in ascending
@@ -251,104 +261,64 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
   // so candidates are parked in a 3-deep per-lane FIFO and the warp runs the insertion code only when a lane's
   // FIFO is full: ~5x fewer executions on a 300-particle pile.  The pre-filter then uses a slightly stale
   // 10th-best distance, which only lets a few extra candidates through; the insertion itself re-checks.
-  const int T0 = (int)blockDim.x / SPLIT;                // receiver slots per pass; a multiple of 32
-  const int piece = (int)threadIdx.x / T0, slot = (int)threadIdx.x - piece * T0;      // piece is warp-uniform
-  const int jper = (N + SPLIT - 1) / SPLIT;
-  const int jlo = min(piece * jper, N), jhi = min(jlo + jper, N);
-  for (int base_i = 0; base_i < N; base_i += T0) {     // every thread takes part in the warp votes
-    const bool active = base_i + slot < N;
-    const int i = active ? perm[base_i + slot] : N;
-    if (SPLIT > 1) {
-      if (piece == 0 && active) bound[i] = 0x7f800000;
-      __syncthreads();
-    }
+  // pass 1: per receiver (one thread each), the (up to) 10 nearest in-radius senders in (distance, index) order, then
+  // sorted by index.  Candidates are taken 32 at a time in two phases:
+  //   A  distances of the 32 candidates (packed fp32x2 subtract / multiply, no branches, no cross-lane traffic) and
+  //      a 32-bit mask of those below the lane's admission bound min(radius^2, current 10th best);
+  //   B  while any lane of the warp has mask bits left, every such lane pops its lowest one and runs the sorted
+  //      insertion (~50 instructions, divergent) on it.
+  // The bound is up to 32 candidates stale in phase A, which only lets a few extra candidates through; phase B
+  // re-checks.  A lane visits its candidates in ascending index, so equal distances keep the lower index first.
+  for (int base_i = 0; base_i < N; base_i += blockDim.x) {     // every thread takes part in the warp votes
+    const bool active = base_i + (int)threadIdx.x < N;
+    const int i = active ? perm[base_i + threadIdx.x] : N;
     float bd[KMAX];
     int id[KMAX];
 #pragma unroll
     for (int s = 0; s < KMAX; ++s) { bd[s] = __int_as_float(0x7f800000); id[s] = 0x7fffffff; }
-    float qd0 = 0.f, qd1 = 0.f, qd2 = 0.f;
-    int qj0 = 0, qj1 = 0, qj2 = 0, qn = 0;
     const int ic = active ? i : 0;
     const float4 pi = pos[ic];
     const float xi = pi.x, yi = pi.y, zi = pi.z;
-    // admission bound min(radius^2, current 10th best); -1 keeps lanes without a receiver out (d >= 0)
+    const uint64_t X2 = pack2(xi, xi), Y2 = pack2(yi, yi), Z2 = pack2(zi, zi);
+    // admission bound; -1 keeps lanes without a receiver out (d >= 0)
     float lim = active ? thr : -1.f;
-    // pop the oldest parked candidate (if any) and insert it keeping (d, index) ascending; candidates of a
-    // lane are inserted in ascending j, so equal distances keep the lower index first
-    auto drain_one = [&]() {
-      if (qn > 0) {
-        const float d = qd0;
-        const int j = qj0;
-        qd0 = qd1; qj0 = qj1; qd1 = qd2; qj1 = qj2;
-        --qn;
+    for (int jb = 0; jb < NP; jb += NBR_BLOCK) {
+      unsigned m = 0;
 #pragma unroll
-        for (int s = KMAX - 1; s > 0; --s) {
-          const bool shift = d < bd[s - 1];
-          const bool here = !shift && d < bd[s];
-          const float nd = shift ? bd[s - 1] : (here ? d : bd[s]);
-          const int ni = shift ? id[s - 1] : (here ? j : id[s]);
-          bd[s] = nd; id[s] = ni;
-        }
-        if (d < bd[0]) { bd[0] = d; id[0] = j; }
-        if (SPLIT == 1) {
-          lim = fminf(thr, bd[KMAX - 1]);
-        } else {
-          // publish this piece's 10th best, take the tightest one of all pieces.  A candidate AT another piece's
-          // bound may still win by its lower index, so foreign bounds admit d <= bound: compare against the next
-          // float up (the insertion and the final merge re-check exactly)
-          const int mine = __float_as_int(bd[KMAX - 1]);          // non-negative floats order like their bit patterns
-          if (mine < 0x7f800000) atomicMin(&bound[ic], mine);
-          const int seen = bound[ic];
-          const float up = seen < 0x7f800000 ? __int_as_float(seen + 1) : __int_as_float(0x7f800000);
-          lim = fminf(thr, up);
-        }
+      for (int q = 0; q < NBR_BLOCK / 2; ++q) {
+        const uint64_t dx = sub2_rn(*reinterpret_cast<const uint64_t*>(xs + jb + 2 * q), X2);
+        const uint64_t dy = sub2_rn(*reinterpret_cast<const uint64_t*>(ys + jb + 2 * q), Y2);
+        const uint64_t dz = sub2_rn(*reinterpret_cast<const uint64_t*>(zs + jb + 2 * q), Z2);
+        float a0, a1, b0, b1, c0, c1;
+        unpack2(mul2_rn(dx, dx), a0, a1);
+        unpack2(mul2_rn(dy, dy), b0, b1);
+        unpack2(mul2_rn(dz, dz), c0, c1);
+        const float d0 = __fadd_rn(__fadd_rn(a0, b0), c0), d1 = __fadd_rn(__fadd_rn(a1, b1), c1);
+        m |= (d0 < lim ? 1u : 0u) << (2 * q);
+        m |= (d1 < lim ? 1u : 0u) << (2 * q + 1);
       }
-    };
-#pragma unroll 4
-    for (int j = jlo; j < jhi; ++j) {
-      const float4 pj = pos[j];
-      const float d = sqdist_rn(xi, yi, zi, pj.x, pj.y, pj.z);
-      if (d < lim) {
-        if (qn == 0) { qd0 = d; qj0 = j; } else if (qn == 1) { qd1 = d; qj1 = j; } else { qd2 = d; qj2 = j; }
-        ++qn;
-      }
-      if (__any_sync(0xffffffffu, qn == 3)) drain_one();
-    }
-    while (__any_sync(0xffffffffu, qn > 0)) drain_one();
-    if (SPLIT > 1) {
-      // every piece leaves its sorted list in shared memory; piece 0 merges them by (distance, index)
-      if (active) {
+      while (__any_sync(0xffffffffu, m != 0u)) {
+        if (m != 0u) {
+          const int j = jb + __ffs((int)m) - 1;
+          m &= m - 1u;
+          const float4 pj = pos[j];
+          const float d = sqdist_rn(xi, yi, zi, pj.x, pj.y, pj.z);
+          if (d < lim) {
 #pragma unroll
-        for (int s = 0; s < KMAX; ++s) {
-          list_d[(piece * N + i) * KMAX + s] = bd[s];
-          list_j[(piece * N + i) * KMAX + s] = id[s];
-        }
-      }
-      __syncthreads();
-      if (piece == 0 && active) {
-        int head[SPLIT];
-#pragma unroll
-        for (int q = 0; q < SPLIT; ++q) head[q] = 0;
-#pragma unroll
-        for (int s = 0; s < KMAX; ++s) {
-          float best_d = __int_as_float(0x7f800000);
-          int best_j = 0x7fffffff, best_q = 0;
-#pragma unroll
-          for (int q = 0; q < SPLIT; ++q) {
-            // heads past the end read as (+inf, INT_MAX); pieces hold ascending index ranges, so on equal distances
-            // the lower piece has the lower index: strict '<' keeps it
-            const float dq = head[q] < KMAX ? list_d[(q * N + i) * KMAX + head[q]] : __int_as_float(0x7f800000);
-            const int jq = head[q] < KMAX ? list_j[(q * N + i) * KMAX + head[q]] : 0x7fffffff;
-            if (dq < best_d || (dq == best_d && jq < best_j)) { best_d = dq; best_j = jq; best_q = q; }
+            for (int s = KMAX - 1; s > 0; --s) {
+              const bool shift = d < bd[s - 1];
+              const bool here = !shift && d < bd[s];
+              const float nd = shift ? bd[s - 1] : (here ? d : bd[s]);
+              const int ni = shift ? id[s - 1] : (here ? j : id[s]);
+              bd[s] = nd; id[s] = ni;
+            }
+            if (d < bd[0]) { bd[0] = d; id[0] = j; }
+            lim = fminf(thr, bd[KMAX - 1]);
           }
-#pragma unroll
-          for (int q = 0; q < SPLIT; ++q) head[q] += (q == best_q && best_j != 0x7fffffff) ? 1 : 0;
-          bd[s] = best_d;
-          id[s] = best_j;
         }
       }
     }
-    if (active && piece == 0) {
+    if (active) {
       cutd[i] = bd[KMAX - 1];          // +inf when fewer than 10 in radius
       cuti[i] = id[KMAX - 1];
       int n = 0;
@@ -364,7 +334,6 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
       for (int s = 0; s < KMAX; ++s) sel[i * KMAX + s] = (i < nvalid) ? id[s] : 0x7fffffff;
       deg[i] = n;
     }
-    if (SPLIT > 1) __syncthreads();     // the lists and bounds are rewritten by the next pass
   }
   __syncthreads();
 
@@ -604,48 +573,27 @@ int launch_gen_s_delta(const float* s_cur, long long s_stride, const float* acti
   return 0;
 }
 
-static size_t nbr_smem_bytes_split(int N, int split) {
-  size_t b = sizeof(float) * (size_t)(4 * N + N) + sizeof(int) * (size_t)(N + N + N + 1 + N * KMAX + N);
-  if (split > 1) b += sizeof(int) * (size_t)N + 2 * sizeof(float) * (size_t)split * N * KMAX;
-  return b;
-}
-size_t nbr_smem_bytes(int N) { return nbr_smem_bytes_split(N, 1); }
-
-// pieces per receiver: 1 when the batch alone fills the SMs with warps, up to 3 for small batches
-static std::atomic<int> g_nbr_split_override{0};
-int set_nbr_split(int split) { return g_nbr_split_override.exchange(split < 0 ? 0 : (split > 3 ? 3 : split)); }
-
-static int nbr_split(int B, int T0, int N) {
-  const int forced = g_nbr_split_override.load();
-  int split = 1;
-  const double fill = (double)B * T0 / (148.0 * 1024.0);       // resident threads per SM / 1024
-  if (fill < 0.6) split = 3;
-  else if (fill < 1.3) split = 2;
-  if (forced >= 1 && forced <= 3) split = forced;
-  while (split > 1 && (split * T0 > NBR_THREADS || nbr_smem_bytes_split(N, split) > 200 * 1024)) --split;
-  return split;
+size_t nbr_smem_bytes(int N) {
+  const size_t NP = (size_t)(N + NBR_BLOCK - 1) / NBR_BLOCK * NBR_BLOCK;
+  return sizeof(float) * ((size_t)(19 * N + 1 + 3) / 4 * 4 + 3 * NP);      // 4N pos + 15N + 1 words, then xs | ys | zs
 }
 
 int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_delta_in, const float* action,
                       int act_stride, const PushCam& cam, float* s_delta_out, const int* particle_nums, int B,
                       int N, float thr, const Csr& csr, cudaStream_t st, const float* attr, const float* dens,
                       float* efeat) {
-  if (nbr_smem_bytes(N) > 200 * 1024) return (int)cudaErrorInvalidValue;
+  const size_t smem = nbr_smem_bytes(N);
+  if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
   static DeviceOnce once;
   const int dev = once.pending();
   if (dev >= 0) {
-    cudaError_t e = cudaFuncSetAttribute(k_nbr_search<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_nbr_search<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_nbr_search<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_nbr_search, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
     once.done(dev);
   }
   int threads = (N + 31) / 32 * 32;
   threads = threads < 64 ? 64 : (threads > NBR_THREADS ? NBR_THREADS : threads);
-  const int split = nbr_split(B, threads, N);
-  const size_t smem = nbr_smem_bytes_split(N, split);
-  auto kern = split == 3 ? k_nbr_search<3> : (split == 2 ? k_nbr_search<2> : k_nbr_search<1>);
-  kern<<<B, threads * split, smem, st>>>(s_cur, s_stride, s_delta_in, action, act_stride, cam, s_delta_out,
+  k_nbr_search<<<B, threads, smem, st>>>(s_cur, s_stride, s_delta_in, action, act_stride, cam, s_delta_out,
                                          particle_nums, N, thr, csr.rowptr, csr.col, csr.row, csr.trowptr,
                                          csr.trecv, csr.tedge, attr, dens, efeat);
   PILE_CHECK_LAUNCH();

@@ -339,10 +339,13 @@ def build_relations(s_cur, s_delta, adj_thresh, particle_nums=None):
 
 
 def relations_from_buffer(buf, is_tape, B, N):
-    """View the relation lists a step left in its scratch / tape buffer (no copy)."""
+    """View the relation lists a step left in its scratch / tape / training-tape (is_tape == 2) buffer (no copy)."""
     lib = _lib.load()
     ps = [C.c_void_p() for _ in range(3)]
-    _lib.check(lib.pile_relations_view(_lib.ptr(buf), int(is_tape), B, N, *[C.byref(p) for p in ps]), "pile_relations_view")
+    if int(is_tape) == 2:
+        _lib.check(lib.pile_train_relations_view(_lib.ptr(buf), B, N, *[C.byref(p) for p in ps]), "pile_train_relations_view")
+    else:
+        _lib.check(lib.pile_relations_view(_lib.ptr(buf), int(is_tape), B, N, *[C.byref(p) for p in ps]), "pile_relations_view")
     base = buf.data_ptr()
     out = []
     for p, n in zip(ps, [B * (N + 1), B * KMAX * N, B * KMAX * N]):
@@ -490,3 +493,23 @@ def gd_track(reward, actions, n_sample, n_batch, T, max_reward, max_idx, best_ac
                                          _lib.ptr(max_reward), _lib.ptr(max_idx), _lib.ptr(best_actions),
                                          _lib.ptr(rew_mean), _lib.ptr(rew_std), _lib.ptr(iter_dev), _stream()),
                "pile_gd_track")
+
+
+def train_forward_raw(wpack, attr, dens, s_cur, s_delta, adj_thresh, particle_nums, tape):
+    """Model step that keeps every layer input in `tape` for the weight-gradient backward (csrc/train.cu)."""
+    B, N, _ = s_cur.shape
+    out = torch.empty_like(s_cur)
+    _lib.check(_lib.load().pile_train_forward(_lib.ptr(wpack), _lib.ptr(attr), _lib.ptr(dens), _lib.ptr(particle_nums),
+                                              _lib.ptr(s_cur), _lib.ptr(s_delta), float(adj_thresh), B, N, _lib.ptr(tape),
+                                              _lib.ptr(out), _stream()), "pile_train_forward")
+    return out
+
+
+def train_backward_raw(wpack, dens, tape, B, N, g_pred, grads, scratch):
+    """-> (g_s_cur, g_s_delta); the 18 weight gradients are accumulated into the flat buffer `grads`."""
+    g_s = torch.empty(B, N, 3, dtype=torch.float32, device=g_pred.device)
+    g_sd = torch.empty_like(g_s)
+    _lib.check(_lib.load().pile_train_backward(_lib.ptr(wpack), _lib.ptr(dens), _lib.ptr(tape), B, N, _lib.ptr(g_pred),
+                                               _lib.ptr(g_s), _lib.ptr(g_sd), _lib.ptr(grads), _lib.ptr(scratch),
+                                               _stream()), "pile_train_backward")
+    return g_s, g_sd

@@ -7,8 +7,10 @@ Same constructor, same `state_dict` keys (so reference checkpoints load with
 tensor op runs in libpilegnn's sm_100a kernels.  `Rr`/`Rs` may be the reference's dense
 one-hot matrices or (preferred) one `ops.Relations` object passed as `Rr` with `Rs=None`.
 
-Differentiable w.r.t. `s_cur` and `s_delta` (the only gradients the planner needs,
-planners.py:674); the parameters are inference-only on this path.
+Differentiable w.r.t. `s_cur` and `s_delta` (the only gradients the planner needs, planners.py:674) through the
+dgrad-only kernels; when gradients are enabled and a parameter requires grad (the training loop,
+train/train_gnn_dyn.py:150-199) the step runs through the training kernels (csrc/train.cu) and returns the
+gradients of all 18 tensors as well.  `model.requires_grad_(False)` selects the dgrad-only path.
 """
 import torch
 import torch.nn as nn
@@ -71,6 +73,48 @@ class _StepFn(torch.autograd.Function):
         return g_s, g_sd, None, None, None, None, None
 
 
+class _TrainStepFn(torch.autograd.Function):
+    """One model step with weight gradients (relations always searched; `particle_nums` masks padded particles)."""
+
+    @staticmethod
+    def forward(ctx, s_cur, s_delta, attr, dens, owner, particle_nums, *params):
+        s_cur_c, s_delta_c = ops._f32(s_cur.detach()), ops._f32(s_delta.detach())
+        ops._require_cuda(s_cur_c, "s_cur")
+        dev = s_cur_c.device
+        B, N, _ = s_cur_c.shape
+        attr_c, dens_c = ops._f32(attr.detach(), dev), ops._f32(dens.detach(), dev)
+        wpack = owner.packed_weights(dev)
+        lib = _lib.load()
+        nbytes = lib.pile_train_tape_bytes(B, N)
+        if nbytes < 0:
+            raise _lib.PileLibraryError("unsupported sizes B=%d N=%d" % (B, N))
+        tape = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        pn = None
+        if particle_nums is not None:
+            pn = torch.as_tensor(particle_nums).to(device=dev, dtype=torch.int32).contiguous()
+        out = ops.train_forward_raw(wpack, attr_c, dens_c, s_cur_c, s_delta_c, owner.adj_thresh, pn, tape)
+        owner.last_relations_buffer = (tape, 2, B, N)
+        ctx.save_for_backward(wpack, dens_c, tape)
+        ctx.dims, ctx.shapes = (B, N), [tuple(p.shape) for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        wpack, dens, tape = ctx.saved_tensors
+        B, N = ctx.dims
+        g = ops._f32(g)
+        lib = _lib.load()
+        total = lib.pile_train_grad_offset(len(ctx.shapes))
+        grads = torch.zeros(total, dtype=torch.float32, device=g.device)
+        scratch = torch.empty(lib.pile_train_scratch_bytes(B, N), dtype=torch.uint8, device=g.device)
+        g_s, g_sd = ops.train_backward_raw(wpack, dens, tape, B, N, g, grads, scratch)
+        out = []
+        for i, shape in enumerate(ctx.shapes):
+            off, end = lib.pile_train_grad_offset(i), lib.pile_train_grad_offset(i + 1)
+            out.append(grads[off:end].view(shape))
+        return (g_s, g_sd, None, None, None, None) + tuple(out)
+
+
 class PropModuleDiffDen(nn.Module):
     """Propagation network (reference model/gnn_dyn.py:113-198), weights only + CUDA forward."""
 
@@ -126,6 +170,10 @@ class PropNetDiffDenModel(nn.Module):
         assert a_cur.shape == s_cur.shape[:2]
         assert s_cur.shape == s_delta.shape
         self.model.adj_thresh = self.adj_thresh
+        params = [p for _, p in self.model.named_parameters()]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            # training: weight gradients wanted (train/train_gnn_dyn.py:150-199)
+            return _TrainStepFn.apply(s_cur, s_delta, a_cur, particle_dens, self.model, particle_nums, *params)
         return _StepFn.apply(s_cur, s_delta, a_cur, particle_dens, self.model, None, particle_nums)
 
     def relations_of_last_step(self):

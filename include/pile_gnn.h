@@ -37,11 +37,6 @@ int pile_get_tensor_cores(void);
  * (tag << 56 | clock64) stamps of its per-layer phases into device_buf[0..capacity). NULL disables. */
 int pile_debug_set_trace(long long* device_buf, int capacity, int which /*0 relation encoder, 1 particle kernels*/);
 
-/* test hook: the relation search cuts every receiver's candidate range into 1..3 pieces scanned by different warps
- * (chosen from the batch size so that small batches still fill the SMs); 0 = automatic, 1..3 = forced.  The relation
- * set does not depend on it.  Returns the previous setting. */
-int pile_debug_set_nbr_split(int split);
-
 /* ---- packed weights ---------------------------------------------------------------------------
  * The host packs the 18 checkpoint tensors into one float buffer; slots are listed in
  * csrc/common.cuh (enum WSlot): transposed [in][out] blocks for the forward, [out][in] for the dgrad. */
@@ -196,6 +191,23 @@ int pile_cover_radius(const double* cloud, int m, const float* picks, int n_sets
  * out[set][k] = mean of the cloud points closer than r to pick k, float32 like the reference's zeros_like(picks). */
 int pile_recenter(const double* cloud, int m, const float* picks, int n_sets, int count, const double* radius,
                   double r_cap, double r_scale, float* out, void* stream);
+
+/* ---- training step: replaces predict_one_step under autograd as driven by train/train_gnn_dyn.py:150-199 (Adam on
+ * all 18 tensors).  pile_train_forward = the same model step (relation search incl. the particle_nums padding mask,
+ * model/gnn_dyn.py:238-241) that leaves every layer input in train_tape (pile_train_tape_bytes(B, N) bytes);
+ * pile_train_backward: g_pred [B,N,3] dense -> g_s_cur, g_s_delta [B,N,3] (overwritten) and the weight gradients
+ * ACCUMULATED (+=) into `grads`: the 18 tensors of the model's state_dict, in its order and natural [out][in]
+ * shapes, flattened into one float buffer; pile_train_grad_offset(i) = offset of tensor i (i = 18: total floats).
+ * scratch: pile_train_scratch_bytes(B, N).  Sums run in fixed orders: deterministic. */
+long long pile_train_tape_bytes(int B, int N);
+long long pile_train_scratch_bytes(int B, int N);
+long long pile_train_grad_offset(int tensor_index);
+int pile_train_forward(const float* wpack, const float* attr, const float* dens, const int* particle_nums,
+                       const float* s_cur, const float* s_delta, float adj_thresh, int B, int N, void* train_tape,
+                       float* s_pred, void* stream);
+int pile_train_backward(const float* wpack, const float* dens, void* train_tape, int B, int N, const float* g_pred,
+                        float* g_s_cur, float* g_s_delta, float* grads, void* scratch, void* stream);
+int pile_train_relations_view(void* train_tape, int B, int N, int** rowptr, int** col, int** row);
 
 /* ---- resolution regressor: replaces MPCResRgrNoPool.forward (model/res_regressor.py:106-144), the network that
  * picks the particle count once per MPC step (env/flex_env.py:981-998, 1080-1090).  params: all 20 tensors of the

@@ -38,7 +38,7 @@ def relerr(a, b):
 def model_with(weights):
     m = P.PropNetDiffDenModel(synthetic.default_config(), True)
     m.load_state_dict(weights)
-    return m.to(DEV)
+    return m.to(DEV).requires_grad_(False)
 
 
 def pair_set(coo):

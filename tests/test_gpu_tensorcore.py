@@ -15,7 +15,7 @@ DEV = "cuda"
 @pytest.fixture(scope="module")
 def model():
     torch.manual_seed(0)
-    return P.PropNetDiffDenModel(synthetic.default_config(), True).to(DEV)
+    return P.PropNetDiffDenModel(synthetic.default_config(), True).to(DEV).requires_grad_(False)     # planner-side engines
 
 
 @pytest.mark.parametrize("mode", [1, 2])

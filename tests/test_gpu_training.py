@@ -1,0 +1,140 @@
+"""Training path on the device (csrc/train.cu through PropNetDiffDenModel.predict_one_step under autograd): the
+loss of train/train_gnn_dyn.py:150-192 on a padded variable-N batch and the gradients of all 18 weight tensors against
+the REAL reference's own autograd (tests/golden/golden_train_v1.npz), then a few Adam steps against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import dyn_res_pile_manip_b200 as P
+from dyn_res_pile_manip_b200 import ops, synthetic
+from oracle import pile_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def training_loss(model, states, states_delta, attrs, dens, particle_nums, pass_nums=True):
+    """The reference's loop (train/train_gnn_dyn.py:150-192) with the drop-in model."""
+    B, n_roll = states_delta.shape[0], states_delta.shape[1]
+    s_cur, a_cur = states[:, 0], attrs[:, 0]
+    loss = 0.
+    for t in range(n_roll):
+        s_pred = model.predict_one_step(a_cur, s_cur, states_delta[:, t], dens, particle_nums if pass_nums else None)
+        for j in range(B):
+            n = int(particle_nums[j])
+            loss = loss + F.mse_loss(s_pred[j, :n], states[j, t + 1, :n])
+        s_cur = s_pred
+    return loss / (n_roll * B)
+
+
+@pytest.fixture(scope="module")
+def gtrain():
+    return np.load(os.path.join(HERE, "golden", "golden_train_v1.npz"))
+
+
+def test_loss_and_all_weight_gradients_vs_reference(gtrain, golden_weights):
+    g = gtrain
+    model = P.PropNetDiffDenModel(synthetic.default_config(), True)
+    model.load_state_dict(golden_weights)
+    model = model.to(DEV)
+    args = [torch.tensor(g[k]).to(DEV) for k in ("states", "states_delta", "attrs", "dens")]
+    loss = training_loss(model, *args, torch.tensor(g["particle_nums"]))
+    assert abs(loss.item() - float(g["loss"])) <= 2e-7 + 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    named = dict(model.named_parameters())
+    assert len(named) == 18
+    worst = 0.0
+    for k, p in named.items():
+        ref = g["g/" + k]
+        assert p.grad is not None and p.grad.shape == ref.shape, k
+        err = np.abs(p.grad.cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1e-12)
+        worst = max(worst, err)
+        assert err <= 2e-4, (k, err)
+    print("18 weight gradients vs reference autograd: worst max-abs error relative to the tensor's max = %.2e" % worst)
+    # deterministic (fixed-order partial sums)
+    grads1 = {k: p.grad.clone() for k, p in named.items()}
+    model.zero_grad()
+    training_loss(model, *args, torch.tensor(g["particle_nums"])).backward()
+    for k, p in named.items():
+        assert torch.equal(p.grad, grads1[k]), k
+
+
+def test_training_forward_equals_inference_forward(gtrain, golden_weights):
+    g = gtrain
+    model = P.PropNetDiffDenModel(synthetic.default_config(), True)
+    model.load_state_dict(golden_weights)
+    model = model.to(DEV)
+    s, sd, a, dn = (torch.tensor(g[k]).to(DEV) for k in ("states", "states_delta", "attrs", "dens"))
+    nums = torch.tensor(g["particle_nums"])
+    out_train = model.predict_one_step(a[:, 0], s[:, 0], sd[:, 0], dn, nums)
+    assert out_train.requires_grad
+    rel_train = model.relations_of_last_step().edge_sets()
+    old = ops.set_tensor_cores(0)
+    try:
+        with torch.no_grad():
+            out_inf = model.predict_one_step(a[:, 0], s[:, 0], sd[:, 0], dn, nums)
+        rel_inf = model.relations_of_last_step().edge_sets()
+    finally:
+        ops.set_tensor_cores(old)
+    np.testing.assert_allclose(out_train.detach().cpu().numpy(), out_inf.cpu().numpy(), rtol=0, atol=2e-6)
+    for x, y in zip(rel_train, rel_inf):
+        assert np.array_equal(x, y)
+    # gradients w.r.t. the inputs agree with the dgrad-only (sign-bit) path
+    s1 = s[:, 0].clone().requires_grad_(True)
+    d1 = sd[:, 0].clone().requires_grad_(True)
+    w = torch.randn(out_train.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0))
+    (model.predict_one_step(a[:, 0], s1, d1, dn, nums) * w).sum().backward()
+    model.requires_grad_(False)
+    old = ops.set_tensor_cores(0)
+    try:
+        s2 = s[:, 0].clone().requires_grad_(True)
+        d2 = sd[:, 0].clone().requires_grad_(True)
+        (model.predict_one_step(a[:, 0], s2, d2, dn, nums) * w).sum().backward()
+    finally:
+        ops.set_tensor_cores(old)
+        model.requires_grad_(True)
+    np.testing.assert_allclose(s1.grad.cpu().numpy(), s2.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(d1.grad.cpu().numpy(), d2.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_adam_training_steps_follow_the_oracle():
+    """Five optimiser steps of the reference's training loop (Adam, lr 1e-3) on a synthetic batch of 6 x 120 particles
+    (variable N, 3 roll-out steps): loss curve and final weights against the same loop on the CPU oracle + autograd."""
+    torch.manual_seed(0)
+    cfg = synthetic.default_config()
+    model = P.PropNetDiffDenModel(cfg, True).to(DEV)
+    W = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    B, N, n_roll = 6, 120, 3
+    rng = np.random.RandomState(3)
+    st0, dens = synthetic.make_pile_batch(B, N, seed=31)
+    nums = np.array([120, 97, 120, 64, 33, 110])
+    states = np.stack([st0 + rng.normal(0, 0.003, st0.shape).astype(np.float32) * k for k in range(n_roll + 1)], 1)
+    sdel = (rng.normal(0, 0.01, (B, n_roll, N, 3)) * (rng.uniform(size=(B, n_roll, N, 1)) < 0.3)).astype(np.float32)
+    for b in range(B):
+        states[b, :, nums[b]:] = 0
+        sdel[b, :, nums[b]:] = 0
+    attrs = np.zeros((B, n_roll + 1, N), np.float32)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt_ref = torch.optim.Adam(list(W.values()), lr=1e-3)
+    dev_args = [torch.tensor(x).to(DEV) for x in (states, sdel, attrs, dens)]
+    cpu_args = [torch.tensor(x) for x in (states, sdel, attrs, dens)]
+    losses, losses_ref = [], []
+    for it in range(5):
+        opt.zero_grad()
+        loss = training_loss(model, *dev_args, torch.tensor(nums))
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+        opt_ref.zero_grad()
+        lr = O.training_loss(W, 0.08, *cpu_args, torch.tensor(nums))
+        lr.backward()
+        opt_ref.step()
+        losses_ref.append(lr.item())
+    np.testing.assert_allclose(losses, losses_ref, rtol=2e-3)
+    assert losses[-1] < losses[0]
+    for k, v in model.state_dict().items():
+        np.testing.assert_allclose(v.cpu().numpy(), W[k].detach().numpy(), rtol=0, atol=2e-4), k
