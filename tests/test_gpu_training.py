@@ -47,14 +47,20 @@ def test_loss_and_all_weight_gradients_vs_reference(gtrain, golden_weights):
     loss.backward()
     named = dict(model.named_parameters())
     assert len(named) == 18
-    worst = 0.0
+    # This fixture contains one knife-edge ReLU: relation 148 of sample 0, channel 41 of the relation encoder's last
+    # layer has a pre-activation of exactly 0.0 when evaluated row by row in fp32 and +1.5e-8 inside torch's batched
+    # CPU GEMM (tools/train_diag2.py), so that single activation's mask -- and with it ~1e-3 of the three relation-
+    # encoder gradients -- depends on the summation order.  Every other tensor must agree to fp32 round-off.
+    worst = {}
     for k, p in named.items():
         ref = g["g/" + k]
         assert p.grad is not None and p.grad.shape == ref.shape, k
         err = np.abs(p.grad.cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1e-12)
-        worst = max(worst, err)
-        assert err <= 2e-4, (k, err)
-    print("18 weight gradients vs reference autograd: worst max-abs error relative to the tensor's max = %.2e" % worst)
+        worst[k] = err
+        assert err <= (4e-3 if "relation_encoder" in k else 5e-6), (k, err)
+    print("18 weight gradients vs reference autograd, max-abs error relative to the tensor's max:")
+    for k, v in worst.items():
+        print("   %-45s %.1e" % (k, v))
     # deterministic (fixed-order partial sums)
     grads1 = {k: p.grad.clone() for k, p in named.items()}
     model.zero_grad()
@@ -127,14 +133,22 @@ def test_adam_training_steps_follow_the_oracle():
         opt.zero_grad()
         loss = training_loss(model, *dev_args, torch.tensor(nums))
         loss.backward()
+        if it == 0:
+            first_grads = {"model." + k: p.grad.detach().cpu().clone() for k, p in model.model.named_parameters()}
         opt.step()
         losses.append(loss.item())
         opt_ref.zero_grad()
         lr = O.training_loss(W, 0.08, *cpu_args, torch.tensor(nums))
         lr.backward()
+        if it == 0:
+            first_ref = {k: v.grad.detach().clone() for k, v in W.items()}
         opt_ref.step()
         losses_ref.append(lr.item())
     np.testing.assert_allclose(losses, losses_ref, rtol=2e-3)
+    # first-iteration gradients (before any weight moved) of all 18 tensors against oracle autograd: relative L2
+    for k, gdev in first_grads.items():
+        ref = first_ref[k]
+        assert float((gdev - ref).norm() / ref.norm()) < 2e-4, k
     assert losses[-1] < losses[0]
     for k, v in model.state_dict().items():
         np.testing.assert_allclose(v.cpu().numpy(), W[k].detach().numpy(), rtol=0, atol=2e-4), k
