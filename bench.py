@@ -574,6 +574,28 @@ def plan_latency(model, planner, env, goal, dev, args):
                                               "fwd = rollout with tape + reward + best tracking, bwd = reward/rollout backward + Adam/clamp"}
     planner._gd_loops.clear()
 
+    # many concurrent MPC calls (the Bayesian-optimisation data generation runs five episodes per candidate resolution,
+    # data_gen/res_rgr_data.py:128-221): five scenes of the shipped MPC call planned one after the other vs in one
+    # batched loop (trajectory_optimization_ptcl_multi_scene)
+    scenes = [synthetic.make_pile_batch(30, 100, seed=60 + k) for k in range(5)]
+    attr5 = np.zeros((30, 100), np.float32)
+    seq_ms, bat_ms = [], []
+    for rep in range(5):
+        t_a = time.perf_counter()
+        for st_k, dn_k in scenes:
+            planner.trajectory_optimization_ptcl_multi_traj(st_k, dn_k, attr5, goal, model, act3, np.zeros(1), 50, 1, 200,
+                                                            None, None, time_lim=2000)
+        seq_ms.append((time.perf_counter() - t_a) * 1e3)
+        t_a = time.perf_counter()
+        planner.trajectory_optimization_ptcl_multi_scene([a_ for a_, _ in scenes], [b_ for _, b_ in scenes], [attr5] * 5, goal,
+                                                         model, act3, np.zeros(1), 50, 1, 200, time_lim=2000)
+        bat_ms.append((time.perf_counter() - t_a) * 1e3)
+    plan["bo_concurrent_planning"] = {"scenes": 5, "one_by_one_ms": sorted(seq_ms[1:])[len(seq_ms[1:]) // 2],
+                                      "batched_ms": sorted(bat_ms[1:])[len(bat_ms[1:]) // 2],
+                                      "workload": "5 x (50 traj x 30 variants x 100 particles, T=1, 27 Adam iterations): five "
+                                                  "trajectory_optimization_ptcl_multi_traj calls vs one ..._multi_scene call"}
+    planner._gd_loops.clear()
+
     # the other planner-side piece of an MPC step: RGB-D observation -> 30 particle
     # re-samplings (env/flex_env.py:933-951), host observation in -> host particles out
     from dyn_res_pile_manip_b200 import observation as OBS

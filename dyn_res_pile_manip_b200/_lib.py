@@ -58,7 +58,7 @@ SIGNATURES = {
     "pile_adam_clamp": (_I, [_P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _P, _P, _P]),
     "pile_adam_clamp_dev": (_I, [_P, _P, _P, _P, _LL, _P, _F, _F, _F, _F, _P, _P, _P]),
     "pile_counter_add": (_I, [_P, _I, _P]),
-    "pile_gd_track": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "pile_gd_track": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "pile_fps": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "pile_fps_sets": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P]),
     "pile_depth_counts_len": (_I, [_I, _I]),

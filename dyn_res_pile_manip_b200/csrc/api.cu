@@ -443,12 +443,12 @@ int pile_counter_add(int* counter_dev, int delta, void* stream) {
 
 int pile_gd_track(const float* reward, const float* actions, int n_sample, int n_batch, int T, float* max_reward,
                   int* max_idx, float* best_actions, float* rew_mean, float* rew_std, const int* iter_dev,
-                  void* stream) {
+                  int stat_every, int stat_stride, void* stream) {
   if (!reward || !actions || n_sample <= 0 || n_batch <= 0 || T <= 0 || !max_reward || !max_idx || !best_actions ||
-      !rew_mean || !rew_std || !iter_dev)
+      !rew_mean || !rew_std || !iter_dev || stat_every <= 0 || stat_stride <= 0)
     return (int)cudaErrorInvalidValue;
   return launch_gd_track(reward, actions, n_sample, n_batch, T, max_reward, max_idx, best_actions, rew_mean, rew_std,
-                         iter_dev, (cudaStream_t)stream);
+                         iter_dev, stat_every, stat_stride, (cudaStream_t)stream);
 }
 
 long long pile_train_tape_bytes(int B, int N) { return bad_dims(B, N) ? -1 : train_tape_bytes(B, N); }

@@ -14,7 +14,8 @@ constexpr int TRK_THREADS = 128;
 __global__ void __launch_bounds__(TRK_THREADS)
 k_gd_track(const float* __restrict__ reward, const float* __restrict__ acts, int n_sample, int n_batch, int T,
            float* __restrict__ max_reward, int* __restrict__ max_idx, float* __restrict__ best_actions,
-           float* __restrict__ rew_mean, float* __restrict__ rew_std, const int* __restrict__ iter_dev) {
+           float* __restrict__ rew_mean, float* __restrict__ rew_std, const int* __restrict__ iter_dev, int stat_every,
+           int stat_stride) {
   __shared__ float s_best[TRK_THREADS / 32];
   __shared__ int s_arg[TRK_THREADS / 32];
   __shared__ double s_sum[TRK_THREADS / 32], s_sq[TRK_THREADS / 32];
@@ -55,12 +56,12 @@ k_gd_track(const float* __restrict__ reward, const float* __restrict__ acts, int
     const float* src = acts + ((long long)take * n_batch + b) * T * 4;
     for (int k = threadIdx.x; k < T * 4; k += blockDim.x) best_actions[(long long)b * T * 4 + k] = src[k];
   }
-  if (b != 0) return;
-  // statistics of state variant 0 over the samples (reward_seqs[:, 0].mean() / .std(), unbiased like torch)
+  if (b % stat_every != 0) return;
+  // statistics of a scene's state variant 0 over the samples (reward_seqs[:, 0].mean() / .std(), unbiased like torch)
   mean = s_sum[0];
   double sq = 0.0;
   for (int s = threadIdx.x; s < n_sample; s += blockDim.x) {
-    const double d = (double)reward[(long long)s * n_batch] - mean;
+    const double d = (double)reward[(long long)s * n_batch + b] - mean;
     sq += d * d;
   }
 #pragma unroll
@@ -69,7 +70,7 @@ k_gd_track(const float* __restrict__ reward, const float* __restrict__ acts, int
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < TRK_THREADS / 32; ++w) sq += s_sq[w];
-    const int it = *iter_dev;
+    const long long it = (long long)(b / stat_every) * stat_stride + *iter_dev;
     rew_mean[it] = (float)mean;
     rew_std[it] = n_sample > 1 ? (float)sqrt(sq / (double)(n_sample - 1)) : __int_as_float(0x7fc00000);
   }
@@ -77,9 +78,9 @@ k_gd_track(const float* __restrict__ reward, const float* __restrict__ acts, int
 
 int launch_gd_track(const float* reward, const float* acts, int n_sample, int n_batch, int T, float* max_reward,
                     int* max_idx, float* best_actions, float* rew_mean, float* rew_std, const int* iter_dev,
-                    cudaStream_t st) {
+                    int stat_every, int stat_stride, cudaStream_t st) {
   k_gd_track<<<n_batch, TRK_THREADS, 0, st>>>(reward, acts, n_sample, n_batch, T, max_reward, max_idx, best_actions,
-                                              rew_mean, rew_std, iter_dev);
+                                              rew_mean, rew_std, iter_dev, stat_every, stat_stride);
   PILE_CHECK_LAUNCH();
   return 0;
 }

@@ -118,7 +118,7 @@ int launch_adam_clamp_dev(float* p, const float* g, float* m, float* v, long lon
 int launch_counter_add(int* counter, int delta, cudaStream_t st);
 int launch_gd_track(const float* reward, const float* acts, int n_sample, int n_batch, int T, float* max_reward,
                     int* max_idx, float* best_actions, float* rew_mean, float* rew_std, const int* iter_dev,
-                    cudaStream_t st);
+                    int stat_every, int stat_stride, cudaStream_t st);
 int mppi_num_chunks(int S);
 int launch_mppi_partials(const float* reward, const float* acts, int S, int T, float weight, float* part,
                          cudaStream_t st);

@@ -487,12 +487,16 @@ def counter_add(counter, delta=1):
     _lib.check(_lib.load().pile_counter_add(_lib.ptr(counter), int(delta), _stream()), "pile_counter_add")
 
 
-def gd_track(reward, actions, n_sample, n_batch, T, max_reward, max_idx, best_actions, rew_mean, rew_std, iter_dev):
-    """Per-iteration best tracking + reward statistics of the GD planner on the device (planners.py:721-740)."""
+def gd_track(reward, actions, n_sample, n_batch, T, max_reward, max_idx, best_actions, rew_mean, rew_std, iter_dev,
+             stat_every=None, stat_stride=None):
+    """Per-iteration best tracking + reward statistics of the GD planner on the device (planners.py:721-740);
+    rew_mean / rew_std are [n_batch // stat_every, stat_stride] (one row per scene)."""
+    stat_every = int(n_batch) if stat_every is None else int(stat_every)
+    stat_stride = int(rew_mean.shape[-1]) if stat_stride is None else int(stat_stride)
     _lib.check(_lib.load().pile_gd_track(_lib.ptr(reward), _lib.ptr(actions), int(n_sample), int(n_batch), int(T),
                                          _lib.ptr(max_reward), _lib.ptr(max_idx), _lib.ptr(best_actions),
-                                         _lib.ptr(rew_mean), _lib.ptr(rew_std), _lib.ptr(iter_dev), _stream()),
-               "pile_gd_track")
+                                         _lib.ptr(rew_mean), _lib.ptr(rew_std), _lib.ptr(iter_dev), stat_every,
+                                         stat_stride, _stream()), "pile_gd_track")
 
 
 def train_forward_raw(wpack, attr, dens, s_cur, s_delta, adj_thresh, particle_nums, tape):

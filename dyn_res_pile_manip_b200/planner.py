@@ -73,9 +73,11 @@ class _GDLoop:
     REW_CAP = 1024
 
     def __init__(self, key, net, device):
-        rows, n_batch, N, T, M, Hh, Ww = key[:7]
+        rows, n_batch, N, T, M, Hh, Ww, n_batch1 = key[:8]
         self.key = key
         self.rows, self.n_batch, self.N, self.T, self.M = rows, n_batch, N, T, M
+        self.n_batch1 = n_batch1                 # state variants per scene (n_batch = scenes * n_batch1)
+        self.calls = 0
         f = dict(dtype=torch.float32, device=device)
         i32 = dict(dtype=torch.int32, device=device)
         self.acts = torch.zeros(rows, T, 4, **f)
@@ -95,8 +97,8 @@ class _GDLoop:
         self.max_reward = torch.zeros(n_batch, **f)
         self.max_idx = torch.zeros(n_batch, **i32)
         self.best_actions = torch.zeros(n_batch, T, 4, **f)
-        self.rew_mean = torch.zeros(self.REW_CAP, **f)
-        self.rew_std = torch.zeros(self.REW_CAP, **f)
+        self.rew_mean = torch.zeros(n_batch // n_batch1, self.REW_CAP, **f)
+        self.rew_std = torch.zeros(n_batch // n_batch1, self.REW_CAP, **f)
         self.iter = torch.zeros(1, **i32)
         self.scratch = net.workspace.scratch(rows, N, device)
         self.bwd_scratch = net.workspace.bwd(rows, N, device)
@@ -120,7 +122,8 @@ class _GDLoop:
                        want_argmin=True, out=self.reward, arg=self.argmin)
         # per state variant: keep the best trajectory seen so far (planners.py:721-727) + rew_mean / rew_std
         ops.gd_track(self.reward, self.acts, self.rows // self.n_batch, self.n_batch, T, self.max_reward, self.max_idx,
-                     self.best_actions, self.rew_mean, self.rew_std, self.iter)
+                     self.best_actions, self.rew_mean, self.rew_std, self.iter, stat_every=self.n_batch1,
+                     stat_stride=self.REW_CAP)
 
     def _enqueue_bwd(self, c):
         N, T = self.N, self.T
@@ -190,6 +193,7 @@ class PlannerGD(Planner):
         self._goal_coor_cache = {}
         self._gd_loops = OrderedDict()      # captured optimisation loops, most recently used last
         self.use_graph = True               # False: launch every iteration's kernels one by one (debugging)
+        self.capture_first_call = False     # True: capture the loop already when a problem size is seen the first time
 
     def reward_offset(self):
         """Pixel offset of the reward projection (planners.py:409-412): the real camera image is cropped."""
@@ -331,29 +335,57 @@ class PlannerGD(Planner):
                                                 action_upper_lim, use_gpu=True, rollout_best_action_sequence=True,
                                                 reward_params=None, funnel_dist=None, distractor_df_fn=None, gd_loop=1,
                                                 time_lim=float('inf')):
-        time_lim = time_lim / 1000.0
         assert type(state_cur_np) == np.ndarray
         assert len(state_cur_np.shape) == 3
         assert state_cur_np.shape[0] == state_param.shape[0]
         assert state_cur_np.shape[2] == 3
+        assert type(state_param) == np.ndarray
+        return self._plan_scenes([state_cur_np], [state_param], [attr_cur_np], obs_goal, model_dy, act_seq, act_label_seq,
+                                 n_sample, n_look_ahead, n_update_iter, use_gpu, rollout_best_action_sequence, gd_loop,
+                                 time_lim)[0]
+
+    def trajectory_optimization_ptcl_multi_scene(self, state_cur_list, state_param_list, attr_cur_list, obs_goal, model_dy,
+                                                 act_seq, act_label_seq, n_sample, n_look_ahead, n_update_iter,
+                                                 action_lower_lim=None, action_upper_lim=None, use_gpu=True,
+                                                 rollout_best_action_sequence=True, gd_loop=1, time_lim=float('inf')):
+        """Several independent planner calls with the same goal, initial action set, particle count and number of
+        state variants in ONE optimisation loop -- the heaviest caller of the hot path, the Bayesian-optimisation data
+        generation, evaluates every candidate resolution with five MPC episodes from the same start
+        (data_gen/res_rgr_data.py:128-221, test_repeat = 5; :419-432).  Scene k's state variants simply become
+        variants k*n_batch .. (k+1)*n_batch-1 of one batch (rows are independent through rollout, reward, backward
+        and Adam), the per-variant best tracking is unchanged, and the vote / best-sequence re-rollout
+        (planners.py:771-851) runs per scene.  Returns one result dict per scene, each bit-identical to what
+        `trajectory_optimization_ptcl_multi_traj` returns for that scene alone."""
+        assert len(state_cur_list) == len(state_param_list) == len(attr_cur_list) and len(state_cur_list) >= 1
+        for st, sp in zip(state_cur_list, state_param_list):
+            assert type(st) == np.ndarray and st.shape == state_cur_list[0].shape and st.shape[0] == sp.shape[0]
+        return self._plan_scenes(state_cur_list, state_param_list, attr_cur_list, obs_goal, model_dy, act_seq, act_label_seq,
+                                 n_sample, n_look_ahead, n_update_iter, use_gpu, rollout_best_action_sequence, gd_loop,
+                                 time_lim)
+
+    def _plan_scenes(self, state_cur_list, state_param_list, attr_cur_list, obs_goal, model_dy, act_seq, act_label_seq,
+                     n_sample, n_look_ahead, n_update_iter, use_gpu, rollout_best_action_sequence, gd_loop, time_lim):
+        time_lim = time_lim / 1000.0
         assert type(obs_goal) == np.ndarray
         assert len(obs_goal.shape) == 2
         assert type(act_seq) == np.ndarray
         assert len(act_seq.shape) == 3
         assert act_seq.shape[0] == act_label_seq.shape[0]
         assert len(act_label_seq.shape) == 1
-        assert type(state_param) == np.ndarray
         if not use_gpu:
             raise _lib.PileLibraryError("use_gpu=False: this planner has no CPU path")
 
+        n_scene = len(state_cur_list)
+        state_cur_np = np.concatenate(state_cur_list, axis=0)
         self.particle_num = state_cur_np.shape[1]
-        n_batch = state_cur_np.shape[0]
+        n_batch1 = state_cur_list[0].shape[0]               # state variants per scene
+        n_batch = state_cur_np.shape[0]                     # ... of the whole batch (scene-major)
         device = torch.device('cuda')
         state_cur_tensor = torch.tensor(state_cur_np, device=device, dtype=torch.float)
-        attr_cur_tensor = torch.tensor(attr_cur_np, device=device, dtype=torch.float)
+        attr_cur_tensor = torch.tensor(np.concatenate(attr_cur_list, axis=0), device=device, dtype=torch.float)
         obs_goal_tensor = torch.tensor(obs_goal, device=device, dtype=torch.float)
         obs_goal_coor_tensor = self.goal_coordinates(obs_goal, device)
-        state_param_tensor = torch.from_numpy(state_param).to(device=device, dtype=torch.float)
+        state_param_tensor = torch.from_numpy(np.concatenate(state_param_list, axis=0)).to(device=device, dtype=torch.float)
 
         n_act = act_seq.shape[0]
         traj_num = int(act_seq.shape[1])
@@ -363,8 +395,6 @@ class PlannerGD(Planner):
         n_iter = min(n_update_iter, int(time_lim * 1000.0 / particle_num_to_iter_time(self.particle_num))) \
             if time_lim != float('inf') else n_update_iter
         n_iter = min(n_iter, _GDLoop.REW_CAP)
-        rew_mean = np.zeros((1, n_update_iter * gd_loop), dtype=np.float32)
-        rew_std = np.zeros((1, n_update_iter * gd_loop), dtype=np.float32)
 
         # ---- static device state of the optimisation: no autograd graph, no host-side value and no host sync
         # inside an iteration, so each half of it is one CUDA-graph replay ------------------------------------
@@ -386,7 +416,7 @@ class PlannerGD(Planner):
         loop = None
         try:
             M = int(obs_goal_coor_tensor.shape[0])
-            key = (rows, n_batch, N, T, M, int(obs_goal_tensor.shape[0]), int(obs_goal_tensor.shape[1]), str(device))
+            key = (rows, n_batch, N, T, M, int(obs_goal_tensor.shape[0]), int(obs_goal_tensor.shape[1]), n_batch1, str(device))
             loop = self._gd_loops.pop(key, None)
             if loop is None:
                 while len(self._gd_loops) >= 2:          # each loop owns a tape: keep the two most recent sizes
@@ -398,17 +428,21 @@ class PlannerGD(Planner):
                       attr_cur_tensor.repeat(traj_num, 1), act_seqs_tensor.view(rows, T, 4), goal_img,
                       obs_goal_coor_tensor)
             loop.reset(*inputs)
-            if n_iter > 0 and self.use_graph and loop.ensure_captured(sig, ctx):
+            # a problem size seen for the first time runs launch by launch (the loop is GPU-bound, the host keeps up);
+            # from the second call on the two captured graphs are replayed
+            loop.calls += 1
+            graph = self.use_graph and n_iter > 0 and (loop.calls >= 2 or self.capture_first_call)
+            if graph and loop.ensure_captured(sig, ctx):
                 loop.reset(*inputs)                      # the capture's warm-up iteration moved the actions
             for i in range(n_iter):
                 e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
                 e0.record()
-                if self.use_graph:
+                if graph:
                     loop.g_fwd.replay()
                 else:
                     loop._enqueue_fwd(ctx)
                 e1.record()
-                if self.use_graph:
+                if graph:
                     loop.g_bwd.replay()
                 else:
                     loop._enqueue_bwd(ctx)
@@ -424,65 +458,77 @@ class PlannerGD(Planner):
         rollout_time = float(sum(a.elapsed_time(b) for a, b, _ in timed))
         optim_time = float(sum(b.elapsed_time(c) for _, b, c in timed))
         if loop is not None and done > 0:
-            rew_mean[0, :done] = loop.rew_mean[:done].cpu().numpy()
-            rew_std[0, :done] = loop.rew_std[:done].cpu().numpy()
-            reward_seqs_tensor = loop.reward.reshape(n_sample, n_batch)
+            rew_mean_all = loop.rew_mean[:n_scene, :done].cpu().numpy()
+            rew_std_all = loop.rew_std[:n_scene, :done].cpu().numpy()
+            reward_all = loop.reward.reshape(n_sample, n_batch)
             act_seqs_tensor = loop.acts.view(rows, T, 1, 4)
-            max_reward, max_reward_traj_idx = loop.max_reward.clone(), loop.max_idx.long()
-            best_actions_of_samples = loop.best_actions.clone()
+            max_reward_all, max_idx_all = loop.max_reward.clone(), loop.max_idx.long()
+            best_actions_all = loop.best_actions.clone()
         else:
-            reward_seqs_tensor = torch.ones((n_sample, n_batch), device=device, dtype=torch.float)
-            max_reward = -float('inf') * torch.ones(n_batch, device=device, dtype=torch.float)
-            max_reward_traj_idx = torch.zeros(n_batch, device=device, dtype=torch.long)
-            best_actions_of_samples = torch.zeros((n_batch, n_act, self.action_dim), device=device, dtype=torch.float)
+            rew_mean_all = rew_std_all = np.zeros((n_scene, 0), dtype=np.float32)
+            reward_all = torch.ones((n_sample, n_batch), device=device, dtype=torch.float)
+            max_reward_all = -float('inf') * torch.ones(n_batch, device=device, dtype=torch.float)
+            max_idx_all = torch.zeros(n_batch, device=device, dtype=torch.long)
+            best_actions_all = torch.zeros((n_batch, n_act, self.action_dim), device=device, dtype=torch.float)
+        reward_all_np = reward_all.data.cpu().numpy()
+        act_all_np = act_seqs_tensor.data.cpu().numpy().reshape(traj_num, n_batch, T, 1, 4)
 
-        reward_seqs = reward_seqs_tensor.data.cpu().numpy()
-        act_seqs = act_seqs_tensor.data.cpu().numpy()
-        # trajectories sharded over ranks (set planner.dist_group / traj_offset): the only exchange of the GD
-        # planner is this one merge of the per-variant winners
-        max_reward, max_reward_traj_idx, best_actions_of_samples = merge_best_across_ranks(
-            max_reward, max_reward_traj_idx + int(getattr(self, 'traj_offset', 0)), best_actions_of_samples,
-            self.dist_group)
-        # vote over state variants for the winning trajectory, then the best variant of it (planners.py:771-781)
-        max_reward_traj_count = torch.bincount(max_reward_traj_idx)
-        idx_best_act = torch.argmax(max_reward_traj_count).item()
-        mr, mi = max_reward.cpu().numpy(), max_reward_traj_idx.cpu().numpy()
-        idx_best_sample, reward_from_best_sample = -1, -float('inf')
-        for j in range(n_batch):
-            if idx_best_act == mi[j] and mr[j] > reward_from_best_sample:
-                idx_best_sample, reward_from_best_sample = j, mr[j]
-        act_seq_best = best_actions_of_samples.detach().cpu().numpy()[idx_best_sample][:, None, :]
+        results = []
+        for k in range(n_scene):
+            sl = slice(k * n_batch1, (k + 1) * n_batch1)
+            rew_mean = np.zeros((1, n_update_iter * gd_loop), dtype=np.float32)
+            rew_std = np.zeros((1, n_update_iter * gd_loop), dtype=np.float32)
+            rew_mean[0, :done] = rew_mean_all[k]
+            rew_std[0, :done] = rew_std_all[k]
+            reward_seqs = reward_all_np[:, sl]
+            act_seqs_k = act_all_np[:, sl].reshape(traj_num * n_batch1, T, 1, 4)
+            # trajectories sharded over ranks (set planner.dist_group / traj_offset): the only exchange of the GD
+            # planner is this one merge of the per-variant winners
+            max_reward, max_reward_traj_idx, best_actions_of_samples = merge_best_across_ranks(
+                max_reward_all[sl], max_idx_all[sl] + int(getattr(self, 'traj_offset', 0)), best_actions_all[sl],
+                self.dist_group)
+            # vote over state variants for the winning trajectory, then the best variant of it (planners.py:771-781)
+            max_reward_traj_count = torch.bincount(max_reward_traj_idx)
+            idx_best_act = torch.argmax(max_reward_traj_count).item()
+            mr, mi = max_reward.cpu().numpy(), max_reward_traj_idx.cpu().numpy()
+            idx_best_sample, reward_from_best_sample = -1, -float('inf')
+            for j in range(n_batch1):
+                if idx_best_act == mi[j] and mr[j] > reward_from_best_sample:
+                    idx_best_sample, reward_from_best_sample = j, mr[j]
+            act_seq_best = best_actions_of_samples.detach().cpu().numpy()[idx_best_sample][:, None, :]
 
-        obs_seq_best = None
-        reward_best = None
-        next_r = None
-        reward_best_idx = 0
-        act_seq_out = act_seq_best.transpose(1, 0, 2)
-        if rollout_best_action_sequence:
-            assert act_seq_out.shape == (1, n_act, self.action_dim)
-            act_seq_tensor = torch.from_numpy(act_seq_out).float().to(device)
-            out = self.ptcl_model_rollout(state_cur_tensor[0:1], state_param_tensor[0:1], attr_cur_tensor[0:1],
-                                          model_dy, act_seq_tensor, enable_grad=True)
-            obs_seq = out['model_rollout']['state_pred'].permute(1, 0, 2, 3).unsqueeze(0)
-            reward_seq_best, next_seq_r = self.ptcl_evaluate_traj(obs_seq.contiguous(), obs_goal_tensor,
-                                                                  obs_goal_coor_tensor)
-            reward_best_idx = next_seq_r[:, 0].argmax()
-            next_r = next_seq_r[reward_best_idx]
-            reward_best = reward_seq_best[reward_best_idx]
-            obs_seq_best = out['model_rollout']['state_pred'][reward_best_idx].detach().cpu().numpy()
-        action_seq_future = act_seq_out[int(reward_best_idx)]
-        total_time = time.time() - start
-        return {'action_sequence': action_seq_future,
-                'action_full': act_seqs[:, 0, 0, :],
-                'reward_full': reward_seqs[:, 0],
-                'observation_sequence': obs_seq_best,
-                'observation_distractor_sequence': None,
-                'reward': None if reward_best is None else reward_best.detach().cpu().numpy(),
-                'next_r': None if next_r is None else next_r.detach().cpu().numpy(),
-                'rew_mean': rew_mean,
-                'rew_std': rew_std,
-                'times': {'total_time': total_time, 'rollout_time': rollout_time, 'optim_time': optim_time},
-                'iter_num': i}
+            obs_seq_best = None
+            reward_best = None
+            next_r = None
+            reward_best_idx = 0
+            act_seq_out = act_seq_best.transpose(1, 0, 2)
+            if rollout_best_action_sequence:
+                assert act_seq_out.shape == (1, n_act, self.action_dim)
+                act_seq_tensor = torch.from_numpy(act_seq_out).float().to(device)
+                v0 = k * n_batch1
+                out = self.ptcl_model_rollout(state_cur_tensor[v0:v0 + 1], state_param_tensor[v0:v0 + 1],
+                                              attr_cur_tensor[v0:v0 + 1], model_dy, act_seq_tensor, enable_grad=True)
+                obs_seq = out['model_rollout']['state_pred'].permute(1, 0, 2, 3).unsqueeze(0)
+                reward_seq_best, next_seq_r = self.ptcl_evaluate_traj(obs_seq.contiguous(), obs_goal_tensor,
+                                                                      obs_goal_coor_tensor)
+                reward_best_idx = next_seq_r[:, 0].argmax()
+                next_r = next_seq_r[reward_best_idx]
+                reward_best = reward_seq_best[reward_best_idx]
+                obs_seq_best = out['model_rollout']['state_pred'][reward_best_idx].detach().cpu().numpy()
+            action_seq_future = act_seq_out[int(reward_best_idx)]
+            total_time = time.time() - start
+            results.append({'action_sequence': action_seq_future,
+                            'action_full': act_seqs_k[:, 0, 0, :],
+                            'reward_full': reward_seqs[:, 0],
+                            'observation_sequence': obs_seq_best,
+                            'observation_distractor_sequence': None,
+                            'reward': None if reward_best is None else reward_best.detach().cpu().numpy(),
+                            'next_r': None if next_r is None else next_r.detach().cpu().numpy(),
+                            'rew_mean': rew_mean,
+                            'rew_std': rew_std,
+                            'times': {'total_time': total_time, 'rollout_time': rollout_time, 'optim_time': optim_time},
+                            'iter_num': i})
+        return results
 
     # ---- helpers -----------------------------------------------------------------------------------------
     def goal_coordinates(self, obs_goal, device):

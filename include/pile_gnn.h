@@ -147,11 +147,13 @@ int pile_counter_add(int* counter_dev, int delta, void* stream);
 /* Per-iteration bookkeeping of the GD planner on the device (planners.py:721-740): reward [n_sample*n_batch] with
  * row = sample*n_batch + b, actions [rows, T, 4] BEFORE the update.  For every state variant b: the best sample of
  * this iteration (lowest index on ties); if it beats max_reward[b] (strictly) it replaces max_reward[b],
- * max_idx[b] and best_actions[b, T, 4].  rew_mean[it] / rew_std[it] (it = *iter_dev) receive the mean and the
- * unbiased standard deviation of reward[:, 0] over the samples. */
+ * max_idx[b] and best_actions[b, T, 4].  Statistics: for every scene k (state variants k*stat_every ..., one scene =
+ * stat_every variants; a single planner call has stat_every = n_batch) rew_mean[k*stat_stride + it] /
+ * rew_std[...] (it = *iter_dev) receive the mean and the unbiased standard deviation of reward[:, k*stat_every]
+ * over the samples (planners.py:737-738 reads reward_seqs[:, 0]). */
 int pile_gd_track(const float* reward, const float* actions, int n_sample, int n_batch, int T, float* max_reward,
                   int* max_idx, float* best_actions, float* rew_mean, float* rew_std, const int* iter_dev,
-                  void* stream);
+                  int stat_every, int stat_stride, void* stream);
 
 /* ---- farthest-point sampling: replaces utils.fps_np (utils.py:451-466) as used for the goal pixels
  * (planners.py:620-624).  pts [n_sets, n, dim] (dim <= 3); per set: start at init_idx, take the farthest

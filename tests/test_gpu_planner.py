@@ -232,3 +232,25 @@ def test_mppi_planner_matches_oracle_composition(setup):
         mean = O.mppi_optimize_action(sampled, rew.numpy()[:, None].astype(np.float64), cfg["mpc"]["mppi"]["reward_weight"])
     np.testing.assert_allclose(got["reward"], rew.numpy(), rtol=2e-4)
     np.testing.assert_allclose(got["action_sequence"], mean[:, 0, :], rtol=0, atol=1e-4)
+
+
+def test_multi_scene_planning_equals_scene_by_scene(setup):
+    """trajectory_optimization_ptcl_multi_scene (the batched entry for many concurrent MPC calls, e.g. the five repeats
+    per candidate resolution of data_gen/res_rgr_data.py:128-221): every scene's result equals its own single call."""
+    cfg, env, model, planner = setup
+    n_scene, n_batch, N, n_traj, T, iters = 3, 4, 60, 5, 2, 4
+    scenes = [synthetic.make_pile_batch(n_batch, N, seed=40 + k) for k in range(n_scene)]
+    act0 = synthetic.random_actions(n_traj, T, seed=41).transpose(1, 0, 2).astype(np.float64)
+    goal = synthetic.make_goal("tee")
+    attr = np.zeros((n_batch, N), np.float32)
+    many = planner.trajectory_optimization_ptcl_multi_scene(
+        [s for s, _ in scenes], [d for _, d in scenes], [attr] * n_scene, goal, model, act0, np.zeros(T), n_traj, T, iters)
+    assert len(many) == n_scene
+    for k, (st, dn) in enumerate(scenes):
+        one = planner.trajectory_optimization_ptcl_multi_traj(st, dn, attr, goal, model, act0, np.zeros(T), n_traj, T, iters,
+                                                              None, None)
+        for key in ("action_sequence", "action_full", "reward_full", "rew_mean", "rew_std", "observation_sequence", "reward",
+                    "next_r"):
+            assert np.array_equal(many[k][key], one[key]), (k, key)
+        assert many[k]["iter_num"] == one["iter_num"] == iters - 1
+    assert not np.array_equal(many[0]["reward_full"], many[1]["reward_full"])
