@@ -319,8 +319,6 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
       }
     }
     if (active) {
-      cutd[i] = bd[KMAX - 1];          // +inf when fewer than 10 in radius
-      cuti[i] = id[KMAX - 1];
       int n = 0;
       if (i < nvalid) {
 #pragma unroll
@@ -372,20 +370,18 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
   }
 
   if (trowptr == nullptr) return;
-  // sender-major transpose: for sender j the receivers i (ascending) with j in nbr(i), and the edge id
+  // sender-major transpose: for sender j the receivers i (ascending) with j in nbr(i), and the edge id.  Built from
+  // the receiver lists by a counting sort in shared memory (O(E) shared-memory atomics) instead of a second O(N^2)
+  // distance scan per sender; the atomics fill a sender's segment in arbitrary order, so every segment is then sorted
+  // by receiver (each receiver appears at most once per sender): the result is deterministic.
+  int* tre = reinterpret_cast<int*>(zs + NP);      // [KMAX*N] receiver of transposed slot (tape runs only)
+  int* ted = tre + KMAX * N;                       // [KMAX*N] edge id
   __syncthreads();
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    int n = 0;
-    if (j < nvalid) {
-      const float4 pj = pos[j];
-      for (int i = 0; i < nvalid; ++i) {
-        const float4 pi = pos[i];
-        const float d = sqdist_rn(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
-        const float cd = cutd[i];
-        n += (d < thr) && (d < cd || (d == cd && j <= cuti[i]));
-      }
-    }
-    deg[j] = n;     // reuse as in-degree
+  for (int j = threadIdx.x; j < N; j += blockDim.x) deg[j] = 0;       // reuse as in-degree / fill cursor
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < N * KMAX; idx += blockDim.x) {
+    const int c = sel[idx];
+    if (c != 0x7fffffff) atomicAdd(&deg[c], 1);
   }
   __syncthreads();
   {
@@ -394,26 +390,35 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
     for (int i = lo; i < hi; ++i) s += deg[i];
     int run = block_exscan(s, warp_sums, &total_s);
     int* trp = trowptr + (size_t)b * (N + 1);
-    for (int i = lo; i < hi; ++i) { const int d = deg[i]; trp[i] = run; deg[i] = run; run += d; }
+    // cuti is free now (the search is over): keep the segment starts there, deg becomes the running fill cursor
+    for (int i = lo; i < hi; ++i) { const int d = deg[i]; trp[i] = run; cuti[i] = run; deg[i] = run; run += d; }
     if (threadIdx.x == 0) trp[N] = total_s;
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < nvalid; j += blockDim.x) {
-    const float4 pj = pos[j];
-    int o = deg[j];
-    for (int i = 0; i < nvalid; ++i) {
-      const float4 pi = pos[i];
-      const float d = sqdist_rn(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
-      const float cd = cutd[i];
-      if ((d < thr) && (d < cd || (d == cd && j <= cuti[i]))) {
-        int pos = 0;
-#pragma unroll
-        for (int s = 0; s < KMAX; ++s) pos += sel[i * KMAX + s] < j;
-        trecv[ebase + o] = i;
-        tedge[ebase + o] = roff[i] + pos;
-        ++o;
-      }
+  for (int idx = threadIdx.x; idx < N * KMAX; idx += blockDim.x) {
+    const int c = sel[idx];
+    if (c != 0x7fffffff) {
+      const int i = idx / KMAX, s = idx - i * KMAX;
+      const int p = atomicAdd(&deg[c], 1);
+      tre[p] = i;
+      ted[p] = roff[i] + s;
     }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {       // insertion sort of sender j's segment by receiver
+    const int lo = cuti[j], hi = deg[j];
+    for (int a = lo + 1; a < hi; ++a) {
+      const int r = tre[a], e = ted[a];
+      int q = a - 1;
+      while (q >= lo && tre[q] > r) { tre[q + 1] = tre[q]; ted[q + 1] = ted[q]; --q; }
+      tre[q + 1] = r;
+      ted[q + 1] = e;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < total_s; idx += blockDim.x) {
+    trecv[ebase + idx] = tre[idx];
+    tedge[ebase + idx] = ted[idx];
   }
 }
 
@@ -573,17 +578,20 @@ int launch_gen_s_delta(const float* s_cur, long long s_stride, const float* acti
   return 0;
 }
 
-size_t nbr_smem_bytes(int N) {
+static size_t nbr_smem_bytes_mode(int N, bool transpose) {
   const size_t NP = (size_t)(N + NBR_BLOCK - 1) / NBR_BLOCK * NBR_BLOCK;
-  return sizeof(float) * ((size_t)(19 * N + 1 + 3) / 4 * 4 + 3 * NP);      // 4N pos + 15N + 1 words, then xs | ys | zs
+  size_t words = (size_t)(19 * N + 1 + 3) / 4 * 4 + 3 * NP;      // 4N pos + 15N + 1 words, then xs | ys | zs
+  if (transpose) words += 2 * (size_t)KMAX * N;                 // + the transposed lists being sorted
+  return sizeof(float) * words;
 }
+size_t nbr_smem_bytes(int N) { return nbr_smem_bytes_mode(N, true); }
 
 int launch_nbr_search(const float* s_cur, long long s_stride, const float* s_delta_in, const float* action,
                       int act_stride, const PushCam& cam, float* s_delta_out, const int* particle_nums, int B,
                       int N, float thr, const Csr& csr, cudaStream_t st, const float* attr, const float* dens,
                       float* efeat) {
-  const size_t smem = nbr_smem_bytes(N);
-  if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+  const size_t smem = nbr_smem_bytes_mode(N, csr.trowptr != nullptr);
+  if (nbr_smem_bytes(N) > 200 * 1024) return (int)cudaErrorInvalidValue;
   static DeviceOnce once;
   const int dev = once.pending();
   if (dev >= 0) {

@@ -322,8 +322,10 @@ def gen_s_delta(s_cur, action, pusher):
     return _GenSDelta.apply(s_cur, action, pusher)
 
 
-def build_relations(s_cur, s_delta, adj_thresh, particle_nums=None):
-    """model/gnn_dyn.py:221-251 -> Relations (bit-exact relation set, torch.nonzero order)."""
+def build_relations(s_cur, s_delta, adj_thresh, particle_nums=None, with_transpose=False):
+    """model/gnn_dyn.py:221-251 -> Relations (bit-exact relation set, torch.nonzero order).
+    with_transpose: also return (trowptr [B,N+1], trecv [B,10N], tedge [B,10N]), the sender-major transpose the
+    backward uses (for sender j: its receivers in ascending order and the ids of those relations)."""
     s_cur, s_delta = _f32(s_cur.detach()), _f32(s_delta.detach())
     _require_cuda(s_cur, "s_cur")
     B, N, _ = s_cur.shape
@@ -332,10 +334,16 @@ def build_relations(s_cur, s_delta, adj_thresh, particle_nums=None):
     col = torch.zeros(B, KMAX * N, dtype=torch.int32, device=dev)
     row = torch.zeros(B, KMAX * N, dtype=torch.int32, device=dev)
     pn = None if particle_nums is None else torch.as_tensor(particle_nums).to(device=dev, dtype=torch.int32).contiguous()
+    trowptr = trecv = tedge = None
+    if with_transpose:
+        trowptr = torch.empty(B, N + 1, dtype=torch.int32, device=dev)
+        trecv = torch.zeros(B, KMAX * N, dtype=torch.int32, device=dev)
+        tedge = torch.zeros(B, KMAX * N, dtype=torch.int32, device=dev)
     _lib.check(_lib.load().pile_build_relations(_lib.ptr(s_cur), _lib.ptr(s_delta), _lib.ptr(pn), B, N, float(adj_thresh),
-                                                _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(row), None, None, None,
-                                                _stream()), "pile_build_relations")
-    return Relations(rowptr, col, row)
+                                                _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(row), _lib.ptr(trowptr),
+                                                _lib.ptr(trecv), _lib.ptr(tedge), _stream()), "pile_build_relations")
+    rel = Relations(rowptr, col, row)
+    return (rel, (trowptr, trecv, tedge)) if with_transpose else rel
 
 
 def relations_from_buffer(buf, is_tape, B, N):

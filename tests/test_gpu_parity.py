@@ -97,6 +97,27 @@ def test_relation_search_block_borders_and_padding_mask(N, B):
     assert np.array_equal(coo_from_relations(rel), adj.nonzero().to(torch.int16).numpy())
 
 
+@pytest.mark.parametrize("N,B", [(7, 2), (40, 3), (100, 4), (300, 3), (341, 2)])
+def test_sender_major_transpose(N, B):
+    """The transposed relation lists the backward gathers over: for every sender its receivers in ascending order and
+    the ids of those relations (built by a counting sort + per-segment sort in shared memory)."""
+    rng = np.random.RandomState(7 + N)
+    s = rng.uniform(-.12, .12, (B, N, 3)).astype(np.float32)
+    if N >= 40:
+        s[:, 3:20, :2] = s[:, 0:1, :2] + rng.normal(0, 1e-3, (B, 17, 2)).astype(np.float32)     # a hub: large in-degrees
+    nums = np.array([N] + [max(1, N - 2 - b) for b in range(1, B)], dtype=np.int32)
+    rel, (trp, trecv, tedge) = ops.build_relations(cuda(s), cuda(np.zeros_like(s)), 0.08, nums, with_transpose=True)
+    rp, col, row = rel.rowptr.cpu().numpy(), rel.col.cpu().numpy(), rel.row.cpu().numpy()
+    trp, trecv, tedge = trp.cpu().numpy(), trecv.cpu().numpy(), tedge.cpu().numpy()
+    for b in range(B):
+        ne = rp[b, -1]
+        assert trp[b, -1] == ne and trp[b, 0] == 0
+        order = np.lexsort((row[b, :ne], col[b, :ne]))          # by sender, then receiver
+        assert np.array_equal(tedge[b, :ne], order)
+        assert np.array_equal(trecv[b, :ne], row[b, :ne][order])
+        assert np.array_equal(np.diff(trp[b]), np.bincount(col[b, :ne], minlength=N))
+
+
 def test_relations_duplicate_points_lowest_index_wins():
     # 14 coincident particles: every distance ties at 0 -> the 10 lowest sender indices must be kept
     s = np.zeros((1, 14, 3), dtype=np.float32)

@@ -31,3 +31,29 @@ obs = synthetic.render_observation(st[0], env)
 p, rad = observation.obs2ptcl_fixed_num_batch(obs, 37, 3, env.get_cam_params(), env.global_scale, seed=0)
 print("obs", p.shape, float(rad.mean()))
 torch.cuda.synchronize()
+
+# ---- round 2 paths: training step (weight gradients), real-robot pusher, graph-less GD planner loop with the device-side
+# bookkeeping kernels, multi-scene planning, resolution regressor
+ops.set_tensor_cores(2)
+torch.manual_seed(0)
+tm = PropNetDiffDenModel(cfg, True).cuda()
+st, dn = synthetic.make_pile_batch(3, 45, seed=2)
+nums = torch.tensor([45, 31, 20])
+s = torch.tensor(st).cuda()
+sd = torch.tensor((np.random.RandomState(0).normal(0, 0.01, st.shape)).astype(np.float32)).cuda()
+out = tm.predict_one_step(torch.zeros(3, 45).cuda(), s, sd, torch.tensor(dn).cuda(), nums)
+out2 = tm.predict_one_step(torch.zeros(3, 45).cuda(), out, sd, torch.tensor(dn).cuda(), nums)
+(out2 ** 2).mean().backward()
+assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in tm.parameters())
+planner.use_graph = False
+st, dn = synthetic.make_pile_batch(3, 37, seed=3)
+act0 = synthetic.random_actions(4, 2, seed=3).transpose(1, 0, 2).astype(np.float64)
+res = planner.trajectory_optimization_ptcl_multi_scene([st, st + 0.001], [dn, dn], [np.zeros((3, 37), np.float32)] * 2,
+                                                       synthetic.make_goal("bar"), model, act0, np.zeros(2), 4, 2, 2)
+assert len(res) == 2 and np.isfinite(res[0]["action_sequence"]).all()
+from dyn_res_pile_manip_b200 import MPCResRgrNoPool
+rg = MPCResRgrNoPool({"train_res_cls": {"state_h": 224, "state_w": 224, "res_dim": 6}})
+y = rg.forward(torch.rand(2, 6, 224, 224).cuda())
+assert torch.isfinite(y).all()
+torch.cuda.synchronize()
+print("round-2 paths ok")
