@@ -516,7 +516,7 @@ def parity_report(model, planner, dev):
 
 def plan_latency(model, planner, env, goal, dev, args):
     """MPC plan latency (BASELINE.json metric, second half) and the GD refinement (config 4)."""
-    from dyn_res_pile_manip_b200 import synthetic
+    from dyn_res_pile_manip_b200 import PropNetDiffDenModel, synthetic
     from dyn_res_pile_manip_b200.engine import RolloutEngine
     # one MPPI planner evaluation of BASELINE config 2 (256 samples x 100 particles x T=10) through the host-buffer
     # call, >= 50 timed calls after 5 warm-ups
@@ -595,6 +595,67 @@ def plan_latency(model, planner, env, goal, dev, args):
                                       "workload": "5 x (50 traj x 30 variants x 100 particles, T=1, 27 Adam iterations): five "
                                                   "trajectory_optimization_ptcl_multi_traj calls vs one ..._multi_scene call"}
     planner._gd_loops.clear()
+
+    # resolution regressor: infer_param = host cv2 planes + H2D + captured 15-launch graph + D2H;
+    # device part alone timed with CUDA events around graph replays (457 MB weight stream)
+    from dyn_res_pile_manip_b200 import MPCResRgrNoPool
+    torch.manual_seed(5)
+    rgr = MPCResRgrNoPool({"train_res_cls": {"state_h": 224, "state_w": 224, "res_dim": 6}})
+    st6, _ = synthetic.make_pile_batch(1, 200, seed=4)
+    fg6 = (synthetic.render_observation(st6[0], env)[..., -1] / env.global_scale < 0.599 / 0.8).astype(np.float32)
+    gm6 = (goal < 0.5).astype(np.float32)
+    rl = []
+    for i in range(14):
+        t_a = time.perf_counter()
+        rgr.infer_param(fg6, gm6)
+        rl.append((time.perf_counter() - t_a) * 1e3)
+    g6 = rgr._graph
+    evs = []
+    for i in range(10):
+        flush_rgr = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev).fill_(i)      # evict L2
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record(); g6['graph'].replay(); b_.record()
+        evs.append((a_, b_))
+    torch.cuda.synchronize()
+    dev_ms = sorted(a_.elapsed_time(b_) for a_, b_ in evs)[len(evs) // 2]
+    plan["resolution_regressor"] = {"infer_param_p50_ms": sorted(rl[4:])[len(rl[4:]) // 2], "device_graph_ms": dev_ms,
+                                    "weight_stream_gbs": 114193217 * 4 / (dev_ms * 1e-3) / 1e9,
+                                    "workload": "MPCResRgrNoPool.infer_param: two 720x720 masks -> particle count (cv2 planes on "
+                                                "the host, 5 conv + 5 linear layers on the device, batch 1, 457 MB of weights)"}
+    del rgr, g6
+
+    # training step: the reference's loop body (train/train_gnn_dyn.py:150-199) on a padded variable-N
+    # batch: 3 roll-out steps forward, MSE, backward with all 18 weight gradients, Adam
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    tmodel = PropNetDiffDenModel(synthetic.default_config(), True).to(dev)
+    opt = torch.optim.Adam(tmodel.parameters(), lr=1e-4)
+    Bt, Nt, n_roll = 32, 300, 3
+    st7, dn7 = synthetic.make_pile_batch(Bt, Nt, seed=7)
+    rng7 = np.random.RandomState(7)
+    nums7 = rng7.randint(150, Nt + 1, size=Bt)
+    states7 = torch.tensor(np.stack([st7 + rng7.normal(0, 0.003, st7.shape).astype(np.float32) * k for k in range(n_roll + 1)], 1)).to(dev)
+    sdel7 = torch.tensor((rng7.normal(0, 0.01, (Bt, n_roll, Nt, 3)) * (rng7.uniform(size=(Bt, n_roll, Nt, 1)) < 0.3)).astype(np.float32)).to(dev)
+    attr7, dens7, nums_t = torch.zeros(Bt, Nt, device=dev), torch.tensor(dn7).to(dev), torch.tensor(nums7)
+    tl = []
+    for i in range(8):
+        torch.cuda.synchronize()
+        t_a = time.perf_counter()
+        opt.zero_grad()
+        s_cur, loss = states7[:, 0], 0.
+        for t in range(n_roll):
+            s_pred = tmodel.predict_one_step(attr7, s_cur, sdel7[:, t], dens7, nums_t)
+            for j in range(Bt):
+                loss = loss + F.mse_loss(s_pred[j, :nums7[j]], states7[j, t + 1, :nums7[j]])
+            s_cur = s_pred
+        (loss / (n_roll * Bt)).backward()
+        opt.step()
+        torch.cuda.synchronize()
+        tl.append((time.perf_counter() - t_a) * 1e3)
+    plan["training_step"] = {"p50_ms": sorted(tl[2:])[len(tl[2:]) // 2], "particle_steps_per_s": Bt * Nt * n_roll / (sorted(tl[2:])[len(tl[2:]) // 2] * 1e-3),
+                             "workload": "32 samples x <=300 particles (padded, particle_nums), 3 roll-out steps: forward + "
+                                         "per-sample MSE + backward (18 weight gradients) + torch Adam, through predict_one_step"}
+    del tmodel, opt
 
     # the other planner-side piece of an MPC step: RGB-D observation -> 30 particle
     # re-samplings (env/flex_env.py:933-951), host observation in -> host particles out
