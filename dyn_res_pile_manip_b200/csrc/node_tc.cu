@@ -321,7 +321,9 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
                  long long s_stride, float* __restrict__ s_out, long long o_stride, int B, int N, int packed_ps) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   NodeUpdSmemTc& S = *reinterpret_cast<NodeUpdSmemTc*>(smem_raw);
+#ifdef PILE_ENABLE_TRACE
   const long long t_entry = clock64();
+#endif
   // non-last: [WRS | WA]; last: [WA | V0 | V1]
   GroupCtx c = tile_prologue(S, wpack, LAST ? OFF_WA : OFF_WRS, LAST ? (NB_WA + NB_K80 + NB_V1) : (NB_WRS + NB_WA));
   const int g = c.g, wig = c.wig, t = threadIdx.x % GROUP_THREADS;
@@ -336,7 +338,9 @@ k_node_update_tc(const float* __restrict__ wpack, const float* __restrict__ agg,
   const int R = B * N;
   const int ntiles = (R + TILE - 1) / TILE;
   PILE_TRACE_DECL();
+#ifdef PILE_ENABLE_TRACE
   if (trace && tr_cap > 0) trace[tr_n++] = (7ll << 56) | (t_entry & 0x00ffffffffffffffLL);
+#endif
   PILE_TRACE(8);
   if (LAST && half == 1) {       // constant aux chunk (1, 0, ...) for the predictor biases
     const float f[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

@@ -17,6 +17,9 @@ namespace pile {
 // includes this header gets its own copy and exposes a setter
 static __device__ long long* g_trace = nullptr;
 static __device__ int g_trace_cap = 0;
+// The trace points cost a clock read + a predicated store each in every tile chain, so they are compiled in only
+// with -DPILE_ENABLE_TRACE (tools/trace_edge_tc.py builds such a variant library); the setters always exist.
+#ifdef PILE_ENABLE_TRACE
 #define PILE_TRACE_DECL()                                                                                  \
   long long* trace = (blockIdx.x == 0 && threadIdx.x == 32 * 9) ? g_trace : nullptr; /* group 1, warp 1 */ \
   const int tr_cap = g_trace_cap;                                                                          \
@@ -25,6 +28,10 @@ static __device__ int g_trace_cap = 0;
   do {                                                                                                       \
     if (trace && tr_n < tr_cap) trace[tr_n++] = ((long long)(tag_) << 56) | (clock64() & 0x00ffffffffffffffLL); \
   } while (0)
+#else
+#define PILE_TRACE_DECL()
+#define PILE_TRACE(tag_) do { } while (0)
+#endif
 #define PILE_TRACE_SETTER(name_)                                              \
   int name_(long long* buf, int cap) {                                        \
     cudaError_t e = cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf));           \

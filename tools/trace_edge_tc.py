@@ -1,4 +1,7 @@
-"""Cycle trace of one warp of k_edge_encode_tc (measurement aid; run on the GPU box)."""
+"""Cycle trace of one warp of k_edge_encode_tc (measurement aid; run on the GPU box).
+The trace points are compiled in only with -DPILE_ENABLE_TRACE: build a variant library, e.g.
+  cp -r dyn_res_pile_manip_b200/csrc abl/trace && make -C abl/trace FLAGS+=-DPILE_ENABLE_TRACE
+and run with PILE_GNN_LIB=abl/trace/libpilegnn.so."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
