@@ -83,9 +83,9 @@ __device__ __forceinline__ void tile_epilogue(Smem& S) {
 __device__ __forceinline__ void store_pr_ps(const GroupCtx& c, uint8_t* stage, int t, int r, int half,
                                             float* __restrict__ Pr, float* __restrict__ Ps, long long row0, long long R,
                                             int packed_ps) {
-#pragma unroll
+#pragma unroll 1
   for (int which = 0; which < 2; ++which) {
-#pragma unroll
+#pragma unroll 1
     for (int q = 0; q < 2; ++q) {
       float v[16];
       tc::tmem_ld16(c.taddr + which * 64 + half * 32 + q * 16, v);
