@@ -71,6 +71,7 @@ SIGNATURES = {
     "pile_train_scratch_bytes": (_LL, [_I, _I]),
     "pile_train_grad_offset": (_LL, [_I]),
     "pile_train_forward": (_I, [_P, _P, _P, _P, _P, _P, _F, _I, _I, _P, _P, _P]),
+    "pile_train_forward_relations": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "pile_train_backward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "pile_train_relations_view": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "pile_rgr_param_offset": (_LL, [_I]),

@@ -464,6 +464,15 @@ int pile_train_forward(const float* wpack, const float* attr, const float* dens,
                               (cudaStream_t)stream);
 }
 
+int pile_train_forward_relations(const float* wpack, const float* attr, const float* dens, const float* s_cur,
+                                 const float* s_delta, const int* rowptr, const int* col, const int* row, int B, int N,
+                                 void* train_tape, float* s_pred, void* stream) {
+  if (bad_dims(B, N) || !wpack || !attr || !dens || !s_cur || !s_delta || !rowptr || !col || !row || !train_tape || !s_pred)
+    return (int)cudaErrorInvalidValue;
+  return launch_train_forward_relations(wpack, attr, dens, s_cur, s_delta, rowptr, col, row, B, N, train_tape, s_pred,
+                                        (cudaStream_t)stream);
+}
+
 int pile_train_backward(const float* wpack, const float* dens, void* train_tape, int B, int N, const float* g_pred,
                         float* g_s_cur, float* g_s_delta, float* grads, void* scratch, void* stream) {
   if (bad_dims(B, N) || !wpack || !dens || !train_tape || !g_pred || !g_s_cur || !g_s_delta || !grads || !scratch)

@@ -132,6 +132,9 @@ int train_relations_view(void* tape, int B, int N, int** rowptr, int** col, int*
 int launch_train_forward(const float* wpack, const float* attr, const float* dens, const int* particle_nums,
                          const float* s_cur, const float* s_delta, float adj_thresh, int B, int N, void* tape,
                          float* s_pred, cudaStream_t st);
+int launch_train_forward_relations(const float* wpack, const float* attr, const float* dens, const float* s_cur,
+                                   const float* s_delta, const int* rowptr, const int* col, const int* row, int B,
+                                   int N, void* tape, float* s_pred, cudaStream_t st);
 int launch_train_backward(const float* wpack, const float* dens, void* tape, int B, int N, const float* g_pred,
                           float* g_s_cur, float* g_s_delta, float* grads, void* scratch, cudaStream_t st);
 

@@ -379,6 +379,21 @@ __global__ void k_tl_node_in(const float* __restrict__ s_delta, const float* __r
   st4(X0 + r * 8 + 4, make_float4(dens[r / N] / 5000.f, 0.f, 0.f, 0.f));
 }
 
+// Y0[e] = (attr_r, attr_s, s_r - s_s, dens / 5000, 0, 0) for caller-provided relation lists (gnn_dyn.py:164-172, 179-180)
+__global__ void k_tl_edge_in(const float* __restrict__ attr, const float* __restrict__ dens, const float* __restrict__ s_cur,
+                             const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ row,
+                             float* __restrict__ Y0, int B, int N) {
+  const int b = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rowptr[(long long)b * (N + 1) + N]) return;
+  const long long slot = (long long)b * KMAX * N + e;
+  const int r = row[slot], c = col[slot];
+  const float* pr = s_cur + ((long long)b * N + r) * 3;
+  const float* ps = s_cur + ((long long)b * N + c) * 3;
+  st4(Y0 + slot * 8, make_float4(attr[(long long)b * N + r], attr[(long long)b * N + c], pr[0] - ps[0], pr[1] - ps[1]));
+  st4(Y0 + slot * 8 + 4, make_float4(pr[2] - ps[2], dens[b] / 5000.f, 0.f, 0.f));
+}
+
 // agg[i] = sum_{e in row i} M[e]   (gnn_dyn.py:189), half-warp per particle
 __global__ void k_tl_segsum(const int* __restrict__ rowptr, const float* __restrict__ M, float* __restrict__ agg, int B, int N) {
   const int l16 = threadIdx.x & 15;
@@ -663,6 +678,9 @@ int train_relations_view(void* tape, int B, int N, int** rowptr, int** col, int*
   return 0;
 }
 
+static int train_forward_body(const float* wpack, const float* attr, const float* dens, const float* s_cur,
+                              const float* s_delta, int B, int N, const TrainTape& t, float* s_pred, cudaStream_t st);
+
 int launch_train_forward(const float* wpack, const float* attr, const float* dens, const int* particle_nums,
                          const float* s_cur, const float* s_delta, float adj_thresh, int B, int N, void* tape,
                          float* s_pred, cudaStream_t st) {
@@ -673,6 +691,32 @@ int launch_train_forward(const float* wpack, const float* attr, const float* den
   e = launch_nbr_search(s_cur, (long long)N * 3, s_delta, nullptr, 0, none, nullptr, particle_nums, B, N,
                         adj_thresh * adj_thresh, t.csr, st, attr, dens, t.Y0);
   if (e) return e;
+  return train_forward_body(wpack, attr, dens, s_cur, s_delta, B, N, t, s_pred, st);
+}
+
+// the same step on caller-provided relation lists (receiver-grouped CSR, any number of relations per receiver as long
+// as a sample has at most KMAX * N in total): the "Rr / Rs" entry of PropModuleDiffDen.forward (gnn_dyn.py:147)
+int launch_train_forward_relations(const float* wpack, const float* attr, const float* dens, const float* s_cur,
+                                   const float* s_delta, const int* rowptr, const int* col, const int* row, int B,
+                                   int N, void* tape, float* s_pred, cudaStream_t st) {
+  int e = tl_configure();
+  if (e) return e;
+  const TrainTape t = carve_train_tape(tape, B, N);
+  const size_t E = (size_t)B * KMAX * N;
+  cudaError_t ce;
+  if ((ce = cudaMemcpyAsync(t.csr.rowptr, rowptr, sizeof(int) * (size_t)B * (N + 1), cudaMemcpyDeviceToDevice, st))) return (int)ce;
+  if ((ce = cudaMemcpyAsync(t.csr.col, col, sizeof(int) * E, cudaMemcpyDeviceToDevice, st))) return (int)ce;
+  if ((ce = cudaMemcpyAsync(t.csr.row, row, sizeof(int) * E, cudaMemcpyDeviceToDevice, st))) return (int)ce;
+  if ((e = launch_transpose_relations(t.csr, B, N, st))) return e;
+  const dim3 fgrid((KMAX * N + 255) / 256, B);
+  k_tl_edge_in<<<fgrid, 256, 0, st>>>(attr, dens, s_cur, t.csr.rowptr, t.csr.col, t.csr.row, t.Y0, B, N);
+  PILE_CHECK_LAUNCH();
+  return train_forward_body(wpack, attr, dens, s_cur, s_delta, B, N, t, s_pred, st);
+}
+
+static int train_forward_body(const float* wpack, const float* attr, const float* dens, const float* s_cur,
+                              const float* s_delta, int B, int N, const TrainTape& t, float* s_pred, cudaStream_t st) {
+  int e = 0;
   const long long R = (long long)B * N;
   k_tl_node_in<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(s_delta, attr, dens, t.X0, B, N);
   PILE_CHECK_LAUNCH();

@@ -196,6 +196,7 @@ class Relations:
     rowptr: torch.Tensor   # [B, N+1] int32, offsets local to the sample
     col: torch.Tensor      # [B, 10N] int32 sender of relation e
     row: torch.Tensor      # [B, 10N] int32 receiver of relation e
+    max_degree: int = KMAX  # most relations any particle receives (the planner's engines handle up to KMAX)
 
     @property
     def n_rel(self):
@@ -239,12 +240,11 @@ class Relations:
         counts = torch.zeros(B, N + 1, dtype=torch.int64, device=dev)
         counts.scatter_add_(1, torch.where(live, recv + 1, torch.zeros_like(recv)), live.long())
         counts[:, 0] = 0
-        # the kernels keep one receiver's relations in a KMAX-row shared-memory slab (the reference's own builder
-        # never emits more: topk(k=10), gnn_dyn.py:231); reject anything else instead of computing garbage
-        if n_rel > 0 and int(counts.max()) > KMAX:
-            raise ValueError("a particle receives %d relations; at most %d per receiver are supported" %
-                             (int(counts.max()), KMAX))
-        return Relations(counts.cumsum(1).int().contiguous(), col, row)
+        # the planner's engines keep one receiver's relations in a KMAX-row shared-memory slab (the reference's own
+        # builder never emits more: topk(k=10), gnn_dyn.py:231); lists with higher degrees are routed to the general
+        # kernels of the training path by PropModuleDiffDen.forward
+        max_degree = int(counts.max()) if n_rel > 0 else 0
+        return Relations(counts.cumsum(1).int().contiguous(), col, row, max(max_degree, 1))
 
 
 class Workspace:
@@ -514,6 +514,17 @@ def train_forward_raw(wpack, attr, dens, s_cur, s_delta, adj_thresh, particle_nu
     _lib.check(_lib.load().pile_train_forward(_lib.ptr(wpack), _lib.ptr(attr), _lib.ptr(dens), _lib.ptr(particle_nums),
                                               _lib.ptr(s_cur), _lib.ptr(s_delta), float(adj_thresh), B, N, _lib.ptr(tape),
                                               _lib.ptr(out), _stream()), "pile_train_forward")
+    return out
+
+
+def train_forward_relations_raw(wpack, attr, dens, s_cur, s_delta, rel, tape):
+    """train_forward_raw on caller-provided relation lists (any degree, at most 10 N relations per sample)."""
+    B, N, _ = s_cur.shape
+    out = torch.empty_like(s_cur)
+    _lib.check(_lib.load().pile_train_forward_relations(
+        _lib.ptr(wpack), _lib.ptr(attr), _lib.ptr(dens), _lib.ptr(s_cur), _lib.ptr(s_delta), _lib.ptr(rel.rowptr),
+        _lib.ptr(rel.col), _lib.ptr(rel.row), B, N, _lib.ptr(tape), _lib.ptr(out), _stream()),
+        "pile_train_forward_relations")
     return out
 
 

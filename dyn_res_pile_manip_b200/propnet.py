@@ -77,7 +77,7 @@ class _TrainStepFn(torch.autograd.Function):
     """One model step with weight gradients (relations always searched; `particle_nums` masks padded particles)."""
 
     @staticmethod
-    def forward(ctx, s_cur, s_delta, attr, dens, owner, particle_nums, *params):
+    def forward(ctx, s_cur, s_delta, attr, dens, owner, particle_nums, rel, *params):
         s_cur_c, s_delta_c = ops._f32(s_cur.detach()), ops._f32(s_delta.detach())
         ops._require_cuda(s_cur_c, "s_cur")
         dev = s_cur_c.device
@@ -92,7 +92,10 @@ class _TrainStepFn(torch.autograd.Function):
         pn = None
         if particle_nums is not None:
             pn = torch.as_tensor(particle_nums).to(device=dev, dtype=torch.int32).contiguous()
-        out = ops.train_forward_raw(wpack, attr_c, dens_c, s_cur_c, s_delta_c, owner.adj_thresh, pn, tape)
+        if rel is None:
+            out = ops.train_forward_raw(wpack, attr_c, dens_c, s_cur_c, s_delta_c, owner.adj_thresh, pn, tape)
+        else:
+            out = ops.train_forward_relations_raw(wpack, attr_c, dens_c, s_cur_c, s_delta_c, rel, tape)
         owner.last_relations_buffer = (tape, 2, B, N)
         ctx.save_for_backward(wpack, dens_c, tape)
         ctx.dims, ctx.shapes = (B, N), [tuple(p.shape) for p in params]
@@ -112,7 +115,7 @@ class _TrainStepFn(torch.autograd.Function):
         for i, shape in enumerate(ctx.shapes):
             off, end = lib.pile_train_grad_offset(i), lib.pile_train_grad_offset(i + 1)
             out.append(grads[off:end].view(shape))
-        return (g_s, g_sd, None, None, None, None) + tuple(out)
+        return (g_s, g_sd, None, None, None, None, None) + tuple(out)
 
 
 class PropModuleDiffDen(nn.Module):
@@ -148,6 +151,11 @@ class PropModuleDiffDen(nn.Module):
 
     def forward(self, a_cur, s_cur, s_delta, Rr, Rs, particle_dens, verbose=False):
         rel = Rr if isinstance(Rr, ops.Relations) else ops.Relations.from_dense(Rr, Rs)
+        params = [p for _, p in self.named_parameters()]
+        wants_wgrad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if wants_wgrad or rel.max_degree > ops.KMAX:
+            # training (weight gradients), or relation lists denser than the planner's engines take: general kernels
+            return _TrainStepFn.apply(s_cur, s_delta, a_cur, particle_dens, self, None, rel, *params)
         return _StepFn.apply(s_cur, s_delta, a_cur, particle_dens, self, rel, None)
 
 
@@ -173,7 +181,7 @@ class PropNetDiffDenModel(nn.Module):
         params = [p for _, p in self.model.named_parameters()]
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             # training: weight gradients wanted (train/train_gnn_dyn.py:150-199)
-            return _TrainStepFn.apply(s_cur, s_delta, a_cur, particle_dens, self.model, particle_nums, *params)
+            return _TrainStepFn.apply(s_cur, s_delta, a_cur, particle_dens, self.model, particle_nums, None, *params)
         return _StepFn.apply(s_cur, s_delta, a_cur, particle_dens, self.model, None, particle_nums)
 
     def relations_of_last_step(self):

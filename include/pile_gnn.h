@@ -207,6 +207,11 @@ long long pile_train_grad_offset(int tensor_index);
 int pile_train_forward(const float* wpack, const float* attr, const float* dens, const int* particle_nums,
                        const float* s_cur, const float* s_delta, float adj_thresh, int B, int N, void* train_tape,
                        float* s_pred, void* stream);
+/* the same step on caller-provided relation lists (receiver-grouped, any number of relations per receiver, at most
+ * 10*N per sample): the training / general form of the Rr, Rs entry of PropModuleDiffDen.forward (gnn_dyn.py:147) */
+int pile_train_forward_relations(const float* wpack, const float* attr, const float* dens, const float* s_cur,
+                                 const float* s_delta, const int* rowptr, const int* col, const int* row, int B, int N,
+                                 void* train_tape, float* s_pred, void* stream);
 int pile_train_backward(const float* wpack, const float* dens, void* train_tape, int B, int N, const float* g_pred,
                         float* g_s_cur, float* g_s_delta, float* grads, void* scratch, void* stream);
 int pile_train_relations_view(void* train_tape, int B, int N, int** rowptr, int** col, int** row);

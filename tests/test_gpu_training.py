@@ -152,3 +152,44 @@ def test_adam_training_steps_follow_the_oracle():
     assert losses[-1] < losses[0]
     for k, v in model.state_dict().items():
         np.testing.assert_allclose(v.cpu().numpy(), W[k].detach().numpy(), rtol=0, atol=2e-4), k
+
+
+def test_forward_with_dense_relations_of_any_degree_and_weight_gradients(golden_weights):
+    """PropModuleDiffDen.forward(a, s, s_delta, Rr, Rs, dens) with one-hot matrices the reference's builder would never
+    emit (a hub particle receiving 25 relations, random extra relations): positions, input gradients and all 18
+    weight gradients against the oracle's dense formulation under autograd (model/gnn_dyn.py:147-198)."""
+    rng = np.random.RandomState(5)
+    B, N = 2, 40
+    st, dn = synthetic.make_pile_batch(B, N, seed=50)
+    sd = (rng.normal(0, 0.01, st.shape)).astype(np.float32)
+    adj = O.adjacency(torch.tensor(st), torch.tensor(sd), 0.08)
+    adj[:, 7, :25] = True                                   # 25 relations into particle 7
+    adj |= torch.from_numpy(rng.uniform(size=(B, N, N)) < 0.03)
+    assert int(adj.sum(2).max()) > 10 and int(adj.sum((1, 2)).max()) <= 10 * N
+    Rr, Rs = O.one_hot_relations(adj)
+    a = torch.tensor(rng.uniform(0, 1, (B, N)).astype(np.float32))
+    W = {k: v.clone().requires_grad_(True) for k, v in golden_weights.items()}
+    s_ref = torch.tensor(st, requires_grad=True)
+    sd_ref = torch.tensor(sd, requires_grad=True)
+    wgt = torch.tensor(rng.normal(size=(B, N, 3)).astype(np.float32))
+    out_ref = O.propnet_forward(W, a, s_ref, sd_ref, Rr, Rs, torch.tensor(dn))
+    (out_ref * wgt).sum().backward()
+    model = P.PropNetDiffDenModel(synthetic.default_config(), True)
+    model.load_state_dict(golden_weights)
+    model = model.to(DEV)
+    s_dev = torch.tensor(st, device=DEV, requires_grad=True)
+    sd_dev = torch.tensor(sd, device=DEV, requires_grad=True)
+    perm = torch.randperm(Rr.shape[1])                      # relation order must not matter
+    out = model.model.forward(a.to(DEV), s_dev, sd_dev, Rr[:, perm].to(DEV), Rs[:, perm].to(DEV), torch.tensor(dn).to(DEV))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), out_ref.detach().numpy(), rtol=0, atol=3e-6)
+    (out * wgt.to(DEV)).sum().backward()
+    np.testing.assert_allclose(s_dev.grad.cpu().numpy(), s_ref.grad.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(sd_dev.grad.cpu().numpy(), sd_ref.grad.numpy(), rtol=1e-4, atol=2e-5)
+    for k, p in model.named_parameters():
+        ref = W[k].grad
+        assert float((p.grad.cpu() - ref).norm() / ref.norm()) < 1e-4, k
+    # inference call (no gradients wanted) with the same dense lists: routed to the general kernels because of the degree
+    model.requires_grad_(False)
+    with torch.no_grad():
+        out2 = model.model.forward(a.to(DEV), s_dev.detach(), sd_dev.detach(), Rr.to(DEV), Rs.to(DEV), torch.tensor(dn).to(DEV))
+    assert torch.equal(out2, out.detach())

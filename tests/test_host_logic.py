@@ -159,18 +159,22 @@ def test_synthetic_observation_layout():
     assert 0 < fg.sum() < fg.size // 4           # a pile in the middle of an empty table
 
 
-def test_from_dense_rejects_more_than_ten_relations_per_receiver():
+def test_from_dense_reports_the_degree_and_rejects_overfull_samples():
+    """Dense Rr / Rs with more than ten relations into one particle are accepted (the model routes them to the general
+    kernels of the training path); more than 10 N relations per sample do not fit the fixed-capacity lists."""
     N = 14
     rr = torch.zeros(1, 12, N)
     rs = torch.zeros(1, 12, N)
     rr[0, :, 3] = 1.0                                  # twelve relations into particle 3
     rs[0, torch.arange(12), torch.arange(12)] = 1.0
-    with pytest.raises(ValueError):
-        ops.Relations.from_dense(rr, rs)
-    rr[0, 10:, 3] = 0.0
-    rr[0, 10:, 4] = 1.0                                # ten into particle 3, two into particle 4: fine
     rel = ops.Relations.from_dense(rr, rs)
-    assert rel.rowptr[0, 4].item() - rel.rowptr[0, 3].item() == 10
+    assert rel.max_degree == 12 and rel.rowptr[0, 4].item() - rel.rowptr[0, 3].item() == 12
+    rr[0, 10:, 3] = 0.0
+    rr[0, 10:, 4] = 1.0                                # ten into particle 3, two into particle 4
+    rel = ops.Relations.from_dense(rr, rs)
+    assert rel.max_degree == 10 and rel.rowptr[0, 4].item() - rel.rowptr[0, 3].item() == 10
+    with pytest.raises(ValueError):
+        ops.Relations.from_dense(torch.zeros(1, 10 * N + 1, N), torch.zeros(1, 10 * N + 1, N))
 
 
 def test_regressor_module_matches_reference_layout_and_init():
