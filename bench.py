@@ -239,23 +239,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed_loop(step_fn, steps):
-        evs = []
+    def timed_loop(step_fn, steps, step_fn2=None):
+        """Times `steps` calls of step_fn (and, interleaved one for one, of step_fn2: both arms then see the same clock /
+        power state -- a B200 settles ~3 % lower after a few hundred ms of sustained load).  -> (ms, t0, t1[, ms2])"""
+        evs, evs2 = [], []
         barrier()
         t0 = time.time()
         for i in range(steps):
-            flush.fill_(i & 0xff)                      # evict L2 between timed steps
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            step_fn(i)
-            b.record()
-            evs.append((a, b))
+            for fn, out in ((step_fn, evs), (step_fn2, evs2)):
+                if fn is None:
+                    continue
+                flush.fill_(i & 0xff)                      # evict L2 between timed steps
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn(i)
+                b.record()
+                out.append((a, b))
         barrier()
         t1 = time.time()
-        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev, dtype=torch.float64)
+        both = [sum(a.elapsed_time(b) for a, b in evs), sum(a.elapsed_time(b) for a, b in evs2)]
+        ms = torch.tensor(both, device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), t0, t1
+        if step_fn2 is None:
+            return float(ms[0].item()), t0, t1
+        return float(ms[0].item()), t0, t1, float(ms[1].item())
 
     class Arm:
         """One engine + its action pool + the record exchange of an evaluation."""
@@ -298,10 +306,10 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    total_ms, t0, t1 = timed_loop(lambda i: arm.step_device(Wm + i), K)
     for i in range(Wm):
         arm.step_host(i)
-    e2e_ms, _, t2 = timed_loop(lambda i: arm.step_host(Wm + i), K)
+    # device-resident and host-buffer evaluations interleaved one for one inside the same timed region
+    total_ms, t0, t2, e2e_ms = timed_loop(lambda i: arm.step_device(Wm + i), K, lambda i: arm.step_host(Wm + i))
     time.sleep(0.2)
     sampler.stop()
     clocks = sampler.summary(t0, t2)
@@ -538,6 +546,19 @@ def plan_latency(model, planner, env, goal, dev, args):
     plan = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "calls": len(lat),
             "workload": "cfg2: 256 samples x 100 particles x T=10, host actions in -> host reward + MPPI record out"}
     del eng2
+    # the same evaluation through the planner's MPPI entry (numpy state / goal / mean sequence in -> numpy plan out:
+    # noise sampling on the host, captured engine underneath), 3 MPPI iterations per call
+    mean2 = synthetic.random_actions(1, t2, seed=3)[0]
+    ml = []
+    for i in range(25):
+        t_a = time.perf_counter()
+        planner.trajectory_optimization_mppi(st2, dn2, np.zeros((1, n2), np.float32), goal, model, mean2, n_sample=s2,
+                                             n_update_iter=3, seed=i)
+        ml.append((time.perf_counter() - t_a) * 1e3)
+    ml = sorted(ml[5:])
+    plan["mppi_planner"] = {"p50_ms": ml[len(ml) // 2], "calls": len(ml), "iterations": 3,
+                            "workload": "trajectory_optimization_mppi: 256 samples x 100 particles x T=10, 3 iterations, "
+                                        "numpy in -> numpy plan out"}
 
     # the reference's own MPC entry point with its shipped configuration (config/mpc/config.yaml:38-43,
     # env/flex_env.py:1020): 50 trajectories x 30 state variants, 100 particles, horizon 1, time budget

@@ -55,6 +55,17 @@ class RolloutEngine:
         self.goal_coor = ops._f32(goal_coor, self.device)
         self._graph = None
 
+    def set_goal_shaped(self, goal_img, goal_coor):
+        """Goal already shaped (rewards.shape_goal_image) and thinned on the device.  Same shapes as before: copied into
+        the buffers the captured graph reads (the capture stays valid); otherwise the buffers are replaced."""
+        if self.goal_img is not None and self.goal_img.shape == goal_img.shape and self.goal_coor.shape == goal_coor.shape:
+            self.goal_img.copy_(goal_img)
+            self.goal_coor.copy_(goal_coor)
+            return
+        self.goal_img = goal_img.detach().clone()
+        self.goal_coor = ops._f32(goal_coor, self.device).clone()
+        self._graph = None
+
     def load_state(self, s0, dens, attr=None):
         """s0 [n_batch,N,3], dens [n_batch] (+attr [n_batch,N]) tiled to rows: row = sample*n_batch + b."""
         s0 = ops._f32(s0, self.device)

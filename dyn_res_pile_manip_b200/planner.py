@@ -192,6 +192,7 @@ class PlannerGD(Planner):
         self.device = torch.device('cuda')
         self._goal_coor_cache = {}
         self._gd_loops = OrderedDict()      # captured optimisation loops, most recently used last
+        self._mppi_engines = OrderedDict()  # captured MPPI evaluations (engine.RolloutEngine), most recently used last
         self.use_graph = True               # False: launch every iteration's kernels one by one (debugging)
         self.capture_first_call = False     # True: capture the loop already when a problem size is seen the first time
 
@@ -573,7 +574,7 @@ class PlannerGD(Planner):
         world, rank = 1, 0
         if self.dist_group is not None or (dist.is_available() and dist.is_initialized()):
             world, rank = dist.get_world_size(self.dist_group), dist.get_rank(self.dist_group)
-        per = shard_size(n_sample, world)
+        shard_size(n_sample, world)
         s0 = torch.tensor(state_cur_np[0:1], device=device, dtype=torch.float)
         dens = torch.tensor(np.asarray(state_param)[0:1], device=device, dtype=torch.float)
         attr = torch.tensor(attr_cur_np[0:1], device=device, dtype=torch.float)
@@ -588,16 +589,34 @@ class PlannerGD(Planner):
             lo_i, hi_i = shard_bounds(n_sample, rank, world)
             mine = torch.tensor(sampled[lo_i:hi_i, :, 0, :], device=device, dtype=torch.float)
             with torch.no_grad():
-                out = self.ptcl_model_rollout(s0, dens, attr, model_dy, mine)
-                last = out['model_rollout']['state_pred'][:, -1]
-                rewards = config_reward_ptcl(last, goal_t, self.cam_params, coor, cache=self.goals)
-                rec = ops.mppi_partials(rewards, mine, w)
+                rewards, rec = self._mppi_evaluate(s0, dens, attr, model_dy, mine, obs_goal, goal_t, coor, w)
                 if world > 1:
                     allrec = torch.empty(world * rec.numel(), device=device)
                     dist.all_gather_into_tensor(allrec, rec.contiguous(), group=self.dist_group)
                     rec = ops.mppi_combine(allrec.view(world, -1), T)
             mean = (rec[2:] / rec[1]).reshape(T, 1, 4).double().cpu().numpy()
         return {'action_sequence': mean[:, 0, :], 'reward': rewards.cpu().numpy(), 'record': rec.cpu().numpy()}
+
+    def _mppi_evaluate(self, s0, dens, attr, model_dy, acts, obs_goal, goal_t, coor, reward_weight):
+        """This rank's share of one MPPI iteration: roll `acts` [S,T,4] out from the single state variant, score the last
+        state, reduce to the (max z, sum e^z, sum e^z act) record -> (rewards [S], record [2+4T]).  One captured CUDA
+        graph per problem size (engine.RolloutEngine: T x 9 + 3 launches), reused across iterations and calls."""
+        from .engine import RolloutEngine
+        S, T = int(acts.shape[0]), int(acts.shape[1])
+        N = int(s0.shape[1])
+        key = (S, N, T, int(coor.shape[0]), tuple(goal_t.shape), float(reward_weight))
+        eng = self._mppi_engines.pop(key, None)
+        if eng is None:
+            while len(self._mppi_engines) >= 2:
+                self._mppi_engines.popitem(last=False)
+            eng = RolloutEngine(model_dy, self, S, N, T, device=s0.device, reward_weight=reward_weight)
+        self._mppi_engines[key] = eng
+        eng.model_dy = model_dy
+        eng.set_goal_shaped(self.goals.shaped_np(obs_goal, goal_t), coor)
+        eng.load_state(s0, dens, attr)
+        eng.actions.copy_(acts)
+        eng.evaluate()
+        return eng.reward.clone(), eng.record.clone()
 
 
 def merge_best_across_ranks(max_reward, traj_idx, best_actions, group=None):

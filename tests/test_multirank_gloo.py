@@ -20,17 +20,13 @@ N, T, NS = 30, 3, 8
 
 
 def _install_doubles(pl, W, env):
-    def rollout(s0, dens, attr, model_dy, acts, enable_grad=True):
+    def evaluate(s0, dens, attr, model_dy, acts, obs_goal, goal_t, coor, w):
         pred = O.rollout(W, 0.08, env.get_cam_extrinsics(), synthetic.GLOBAL_SCALE, s0, dens, attr, acts)
-        return {"model_rollout": {"state_pred": pred}, "rollout_time": 0.0}
+        rew = O.reward_ptcl(pred[:, -1], goal_t, env.get_cam_params(), coor)
+        return rew, torch.from_numpy(O.mppi_record(rew.numpy(), acts.numpy(), w)).float()
 
-    def reward(state, goal, cam_params, goal_coor, normalize=True, offset=(0., 0.), cache=None):
-        return O.reward_ptcl(state, goal, cam_params, goal_coor, normalize, offset)
-
-    pl.ptcl_model_rollout = rollout
+    pl._mppi_evaluate = evaluate
     pl.device = torch.device("cpu")
-    planner_mod.config_reward_ptcl = reward
-    ops.mppi_partials = lambda r, a, w: torch.from_numpy(O.mppi_record(r.numpy(), a.numpy(), w)).float()
     ops.mppi_combine = lambda parts, T_: torch.from_numpy(O.mppi_merge(parts.numpy())).float()
 
 
