@@ -220,8 +220,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")               # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     cfg, env = synthetic.default_config(), synthetic.FakeEnv()
