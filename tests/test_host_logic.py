@@ -198,3 +198,59 @@ def test_regressor_module_matches_reference_layout_and_init():
     assert lib.pile_rgr_param_offset(20) == sum(v.numel() for v in sd.values()) == 114_193_217
     assert lib.pile_rgr_param_offset(1) == 6 * 64 * 16
     assert lib.pile_rgr_workspace_bytes(1, 224, 224) > 0 and lib.pile_rgr_workspace_bytes(1, 200, 200) == -1
+
+
+def test_goal_cache_is_keyed_on_content():
+    """two different goals of the same shape at the same address must not share a cache entry; the same
+    contents in a fresh tensor must hit it."""
+    from dyn_res_pile_manip_b200.rewards import GoalCache, shape_goal_image
+    cache = GoalCache()
+    bar, disc = synthetic.make_goal("bar"), synthetic.make_goal("disc")
+    t = torch.from_numpy(bar.copy())
+    img_bar = cache.shaped(t)
+    assert torch.equal(img_bar, shape_goal_image(torch.from_numpy(bar)))
+    t.copy_(torch.from_numpy(disc))                          # same storage, same shape, new contents (in-place)
+    img_disc = cache.shaped(t)
+    assert torch.equal(img_disc, shape_goal_image(torch.from_numpy(disc))) and not torch.equal(img_disc, img_bar)
+    assert cache.shaped(torch.from_numpy(disc.copy())) is img_disc          # equal contents, fresh tensor: hit
+    img2 = cache.shaped_np(bar, torch.from_numpy(bar))                       # numpy entry: hash of the bytes
+    assert torch.equal(img2, img_bar)
+    assert cache.shaped_np(bar.copy(), torch.from_numpy(bar.copy())) is img2
+    assert not torch.equal(cache.shaped_np(disc, torch.from_numpy(disc)), img2)
+
+
+def test_workspace_keeps_only_recent_sizes(lib):
+    """the dynamic-resolution loop changes N every step; scratch must not accumulate."""
+    ws = ops.Workspace()
+    dev = torch.device("cpu")
+    bufs = [ws.scratch(2, n, dev) for n in (10, 11, 12, 13, 14)]
+    assert len(ws._scratch) == ops.Workspace.KEEP
+    assert ws.scratch(2, 14, dev) is bufs[-1] and ws.scratch(2, 13, dev) is bufs[-2]
+    assert ws.scratch(2, 10, dev) is not bufs[0]            # evicted and re-created
+    for n in (10, 11, 12, 13):
+        ws.bwd(2, n, dev)
+    assert len(ws._bwd) == ops.Workspace.KEEP
+    with pytest.raises(_lib.PileLibraryError):
+        ws.scratch(0, 5, dev)
+    with pytest.raises(_lib.PileLibraryError):
+        ws.bwd(3, -1, dev)
+
+
+def test_pusher_struct_layout_and_planner_frames():
+    """`pile_pusher` as ctypes sees it (kind, 12 matrix floats, global_scale, s2r_scale, centre) and the two planner
+    frames: simulator camera and real robot (planners.py:192-257 / 259-300, dispatch :345-348)."""
+    import ctypes
+    assert ctypes.sizeof(_lib.PusherStruct) == 4 + 12 * 4 + 4 * 4
+    env = synthetic.FakeEnv()
+    sim = P.PlannerGD(synthetic.default_config(), env)
+    assert sim.pusher.kind == 0 and sim.pusher.struct.global_scale == synthetic.GLOBAL_SCALE
+    assert [sim.pusher.struct.cam_m12[i] for i in range(12)] == sim.cam12 and sim.reward_offset() == (0., 0.)
+
+    class Real(synthetic.FakeEnv):
+        is_real = True
+        s2r_scale, wkspc_center_x, wkspc_center_y = 10.0, 0.03, -0.02
+        crop_w_lower, crop_w_off, crop_h_lower, crop_h_off = 100, 20, 80, 10
+    real = P.PlannerGD(synthetic.default_config(), Real())
+    assert real.pusher.kind == 1 and real.pusher.struct.s2r_scale == 10.0
+    assert abs(real.pusher.struct.wkspc_center_x - 0.03) < 1e-7 and real.reward_offset() == (-80.0, -70.0)
+    assert real.pusher.signature() != sim.pusher.signature()
