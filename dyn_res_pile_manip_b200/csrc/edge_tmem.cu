@@ -17,6 +17,7 @@
 //   hi(k in 0..31) -> P+0..15, lo(k in 0..31) -> P+16..31, hi(k in 32..63) -> P+32..47, lo(k in 32..63) -> P+48..63
 #include "kernels.h"
 #include "tc_tile.cuh"
+#include "tmap.cuh"
 
 namespace pile {
 
@@ -29,12 +30,17 @@ struct EdgeTmemSmem {
   alignas(128) uint8_t w0[TM_W0_BYTES];
   alignas(128) uint8_t wl[3][TM_WL_BYTES];
   float b_re0[H], b_re1[H], b_re2[H], wd_rp[H], b_rp[H];
-  alignas(128) uint8_t stage[TC_GROUPS][TILE * H * 4];     // C_e rows on their way out (tc_tile.cuh: stage_*)
+  // packed C_e rows on their way out: the 128-byte upper-half part and the 64-byte third-byte part of every row,
+  // each in the swizzle pattern of its tensor map (one TMA tile store per part and tile)
+  alignas(1024) uint8_t stage_hi[TC_GROUPS][TILE * 128];
+  alignas(1024) uint8_t stage_lo[TC_GROUPS][TILE * 64];
   alignas(16) float4 feat[TC_GROUPS][2][TILE][2];         // next tile's input rows, one private copy per thread
   uint64_t bar[TC_GROUPS];
   uint64_t w_bar;
   uint32_t tmem_base;
 };
+
+constexpr int EDGE_TMEM_SMEM = (int)sizeof(EdgeTmemSmem) + 1024;          // + alignment slack
 
 __device__ __forceinline__ void mma_bf16_ts_if(uint32_t pred, uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
                                                uint32_t idesc, uint32_t accumulate) {
@@ -92,13 +98,21 @@ __device__ __forceinline__ void issue_hidden_ts(uint32_t elected, uint32_t d, ui
   }
 }
 
+// q = n / d for n * d < 2^32 with magic = 2^32 / d + 1 (host: div_magic); magic 0 = plain division
+__device__ __forceinline__ int fast_div(int n, int d, uint32_t magic) {
+  return magic ? (int)__umulhi((uint32_t)n, magic) : n / d;
+}
+
 template <bool RECORD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ efeat, const int* __restrict__ rowptr,
                    uint8_t* __restrict__ m_re0, uint8_t* __restrict__ m_re1, uint8_t* __restrict__ m_re2,
-                   float* __restrict__ Ce, int B, int N) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  EdgeTmemSmem& S = *reinterpret_cast<EdgeTmemSmem*>(smem_raw);
+                   const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, int B, int N,
+                   uint32_t tps_magic) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // the swizzled staging boxes need 1024-byte alignment in the shared window
+  EdgeTmemSmem& S = *reinterpret_cast<EdgeTmemSmem*>(
+      smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
   const int g = threadIdx.x / GROUP_THREADS, t = threadIdx.x % GROUP_THREADS;
   const int wig = t >> 5;
   const int r = (wig & 3) * 32 + (t & 31);
@@ -136,10 +150,12 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
   // thread reads, so no registers are tied up across the tile chain and no barrier is needed
   float4* my_feat = &S.feat[g][half][r][0];
   const uint32_t my_feat_u32 = tc::smem_u32(my_feat);
+  int nxt_b = 0;                        // sample of the tile fetched last
   auto fetch = [&](int tile) {          // -> relation count of the tile's sample
     int ne = 0;
     if (tile < ntiles) {
-      const int b = tile / tps;
+      const int b = fast_div(tile, tps, tps_magic);
+      nxt_b = b;
       const long long slot = (long long)b * KMAX * N + (tile - b * tps) * TILE + r;
       ne = tc::ldg_nc_s32(rowptr + (long long)b * (N + 1) + N);
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(my_feat_u32), "l"(efeat + slot * 8) : "memory");
@@ -216,13 +232,25 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
   const uint64_t dw0 = tc::make_desc(tc::smem_u32(S.w0), b_lbo(H), B_SBO);
   const uint64_t dwl0 = tc::make_desc(tc::smem_u32(S.wl[0]), b_lbo(H), B_SBO);
   const uint64_t dwl1 = tc::desc_advance(dwl0, TM_WL_BYTES), dwl2 = tc::desc_advance(dwl0, 2 * TM_WL_BYTES);
-  // C_e rows of the previous tile wait in the staging tile and leave while the next tile's first MMAs run
+  // C_e rows of the previous tile wait in the staging boxes and leave (two TMA tile stores issued by one thread
+  // of a non-issuer warp) while the next tile's first MMAs run
   bool pending = false;
-  long long p_slot0 = 0;
-  int p_nrows = 0;
+  int p_b = 0, p_e0 = 0;
+  const bool store_thread = t == 32 * ((g + 4) & 7);
+  uint8_t* const my_hi = S.stage_hi[g] + r * 128;
+  uint8_t* const my_lo = S.stage_lo[g] + r * 64;
+  const uint32_t sw_hi = (uint32_t)(r & 7), sw_lo = (uint32_t)((r >> 1) & 3);
+  const uint32_t stage_hi_u32 = tc::smem_u32(S.stage_hi[g]), stage_lo_u32 = tc::smem_u32(S.stage_lo[g]);
+  auto flush = [&] {          // after a group barrier that follows the staging writes
+    if (store_thread) {
+      tc::tma_store_3d(&tm_hi, stage_hi_u32, 0, p_e0, p_b);
+      tc::tma_store_3d(&tm_lo, stage_lo_u32, 0, p_e0, p_b);
+      tc::bulk_commit();
+    }
+  };
 
   while (tile < ntiles) {
-    const int b = tile / tps;
+    const int b = nxt_b;
     const int e0 = (tile - b * tps) * TILE;
     const int nrows = min(TILE, cur_ne - e0);
     const long long slot0 = (long long)b * KMAX * N + e0;
@@ -263,7 +291,7 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
         mma_bf16_ts_if(el, Y, X + 16, dw0, idesc, 1u);
         mma_bf16_ts_if(el, Y, X, d_lo, idesc, 1u);
       }, [&] {
-        if (pending) stage_flush_packed(S.stage[g], t, reinterpret_cast<uint8_t*>(Ce), p_slot0, p_slot0 + p_nrows);
+        if (pending) flush();
         pending = false;
       });
       epilogue(Yt, Xt, S.b_re1, 0.f, nullptr, m_re0, slot0 + r, valid);
@@ -273,20 +301,34 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
       // layer 2: A = X, D = Y; then pre-load the hoisted constant w_d d + b of the propagator into X
       run([&](uint32_t el) { issue_hidden_ts(el, Y, X, dwl1, 1u); }, nothing);
       epilogue(Yt, Xt, S.b_rp, d, S.wd_rp, m_re2, slot0 + r, valid);
-      // layer E: A = Y, D = X -> C_e rows
+      // layer E: A = Y, D = X -> C_e rows.  The previous tile's stores have long finished reading the staging
+      // boxes; the wait makes that formal before this layer's group barrier releases the writers below
+      if (store_thread) tc::bulk_wait_read0();
       run([&](uint32_t el) { issue_hidden_ts(el, X, Y, dwl2, 1u); }, nothing);
       {
         float v[2][16];
         tc::tmem_ld16(Xt + half * 32, v[0]);
         tc::tmem_ld16(Xt + half * 32 + 16, v[1]);
         tc::tmem_ld_wait();
-        // one row per thread -> whole 128-byte lines per store request, through the group's staging tile; the
-        // tile is flushed after the group barrier of the NEXT tile's first layer (or after the loop)
-        stage_put16(S.stage[g], r, half * 32, v[0]);
-        stage_put16(S.stage[g], r, half * 32 + 16, v[1]);
+        // this thread's 32 columns of row r, packed to 24 bits (tc_tile.cuh: pack24) in registers: four 16-byte
+        // chunks of the row's upper-half part and two of its third-byte part, written at the swizzled positions
+        // the tensor maps expect (chunk index XOR row bits: conflict-free for one row per lane)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint2 h[4];
+          uint32_t l[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            pack24(make_float4(v[q][4 * i], v[q][4 * i + 1], v[q][4 * i + 2], v[q][4 * i + 3]), h[i], l[i]);
+          const uint32_t c = (uint32_t)(half * 4 + q * 2);
+          *reinterpret_cast<uint4*>(my_hi + ((c ^ sw_hi) << 4)) = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
+          *reinterpret_cast<uint4*>(my_hi + (((c + 1) ^ sw_hi) << 4)) = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
+          *reinterpret_cast<uint4*>(my_lo + (((uint32_t)(half * 2 + q) ^ sw_lo) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        tc::fence_async_smem();          // generic-proxy writes -> visible to the copy engine
         pending = true;
-        p_slot0 = slot0;
-        p_nrows = nrows;
+        p_b = b;
+        p_e0 = e0;
       }
     }
     PILE_TRACE(6);
@@ -295,8 +337,9 @@ k_edge_encode_tmem(const float* __restrict__ wpack, const float* __restrict__ ef
   }
   if (pending) {             // group-uniform
     group_barrier(g);
-    stage_flush_packed(S.stage[g], t, reinterpret_cast<uint8_t*>(Ce), p_slot0, p_slot0 + p_nrows);
+    flush();
   }
+  if (store_thread) tc::bulk_wait0();
   tc::fence_before_sync();
   __syncthreads();
   if (threadIdx.x < 32) tc::tmem_dealloc(S.tmem_base, 512);
@@ -310,22 +353,36 @@ int launch_edge_encode_tmem(const float* wpack, const float* efeat, const Csr& c
   const int once_dev = once.pending();
   if (once_dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(k_edge_encode_tmem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(EdgeTmemSmem));
+                                         EDGE_TMEM_SMEM);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_edge_encode_tmem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(EdgeTmemSmem));
+    e = cudaFuncSetAttribute(k_edge_encode_tmem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EDGE_TMEM_SMEM);
     if (e != cudaSuccess) return (int)e;
     once.done(once_dev);
   }
-  const long long ntiles = (long long)B * ((KMAX * N + TILE - 1) / TILE);
+  const int tps = (KMAX * N + TILE - 1) / TILE;
+  const long long ntiles = (long long)B * tps;
   const long long want = (ntiles + TC_GROUPS - 1) / TC_GROUPS;
   const int grid = (int)(want < NSM ? want : NSM);
+  // tile -> sample by multiply-high (exact while (largest tile index) * tps < 2^32), else plain division
+  const unsigned long long nmax = (unsigned long long)ntiles + (unsigned long long)grid * TC_GROUPS;
+  const uint32_t magic = tps >= 2 && nmax * (unsigned long long)tps < (1ull << 32) ? (uint32_t)((1ull << 32) / tps + 1) : 0u;
+  // packed C_e rows = [128 bytes of upper halves | 64 bytes of third bytes]; two maps over the same rows,
+  // dimensions (bytes of the part, slot in the sample, sample): the engine clips a sample's last tile at KMAX*N
+  static TmapCache<2> cache;
+  CUtensorMap tm[2];
+  const int ts = cache.get(Ce, B, N, tm, [&](CUtensorMap* m) {
+    const uint64_t row = CE_PACKED_ROW, plane = (uint64_t)KMAX * N * CE_PACKED_ROW;
+    int e = tmap_encode_rows(&m[0], Ce, 128, (uint64_t)KMAX * N, row, (uint64_t)B, plane, TILE);
+    if (e) return e;
+    return tmap_encode_rows(&m[1], reinterpret_cast<uint8_t*>(Ce) + 128, 64, (uint64_t)KMAX * N, row, (uint64_t)B, plane, TILE);
+  });
+  if (ts) return ts;
   if (mk)
-    k_edge_encode_tmem<true><<<grid, TC_THREADS, sizeof(EdgeTmemSmem), st>>>(wpack, efeat, csr.rowptr, mk->re0, mk->re1,
-                                                                             mk->re2, Ce, B, N);
+    k_edge_encode_tmem<true><<<grid, TC_THREADS, EDGE_TMEM_SMEM, st>>>(wpack, efeat, csr.rowptr, mk->re0, mk->re1,
+                                                                       mk->re2, tm[0], tm[1], B, N, magic);
   else
-    k_edge_encode_tmem<false><<<grid, TC_THREADS, sizeof(EdgeTmemSmem), st>>>(wpack, efeat, csr.rowptr, nullptr, nullptr,
-                                                                              nullptr, Ce, B, N);
+    k_edge_encode_tmem<false><<<grid, TC_THREADS, EDGE_TMEM_SMEM, st>>>(wpack, efeat, csr.rowptr, nullptr, nullptr,
+                                                                        nullptr, tm[0], tm[1], B, N, magic);
   PILE_CHECK_LAUNCH();
   return 0;
 }
