@@ -486,6 +486,44 @@ int pile_train_relations_view(void* train_tape, int B, int N, int** rowptr, int*
   return train_relations_view(train_tape, B, N, rowptr, col, row);
 }
 
+long long pile_general_wpack_slot_offset(int slot, int nf_effect) { return general_wpack_slot_offset(slot, nf_effect); }
+long long pile_general_tape_bytes(int B, int N, int nf_effect) { return bad_dims(B, N) ? -1 : general_tape_bytes(B, N, nf_effect); }
+long long pile_general_scratch_bytes(int B, int N, int nf_effect) {
+  return bad_dims(B, N) ? -1 : general_bwd_scratch_bytes(B, N, nf_effect);
+}
+long long pile_general_grad_offset(int tensor_index, int nf_effect) { return general_grad_offset(tensor_index, nf_effect); }
+
+int pile_general_forward(const float* wpack, int nf_effect, const float* attr, const float* dens,
+                         const int* particle_nums, const float* s_cur, const float* s_delta, float adj_thresh, int B,
+                         int N, void* tape, float* s_pred, void* stream) {
+  if (bad_dims(B, N) || !wpack || !attr || !dens || !s_cur || !s_delta || !tape || !s_pred) return (int)cudaErrorInvalidValue;
+  return launch_general_forward(wpack, nf_effect, attr, dens, particle_nums, s_cur, s_delta, adj_thresh, B, N, tape, s_pred,
+                                (cudaStream_t)stream);
+}
+
+int pile_general_forward_relations(const float* wpack, int nf_effect, const float* attr, const float* dens,
+                                   const float* s_cur, const float* s_delta, const int* rowptr, const int* col,
+                                   const int* row, int B, int N, void* tape, float* s_pred, void* stream) {
+  if (bad_dims(B, N) || !wpack || !attr || !dens || !s_cur || !s_delta || !rowptr || !col || !row || !tape || !s_pred)
+    return (int)cudaErrorInvalidValue;
+  return launch_general_forward_relations(wpack, nf_effect, attr, dens, s_cur, s_delta, rowptr, col, row, B, N, tape,
+                                          s_pred, (cudaStream_t)stream);
+}
+
+int pile_general_backward(const float* wpack, int nf_effect, const float* dens, void* tape, int B, int N,
+                          const float* g_pred, float* g_s_cur, float* g_s_delta, float* grads, void* scratch,
+                          void* stream) {
+  if (bad_dims(B, N) || !wpack || !dens || !tape || !g_pred || !g_s_cur || !g_s_delta || !scratch)
+    return (int)cudaErrorInvalidValue;
+  return launch_general_backward(wpack, nf_effect, dens, tape, B, N, g_pred, g_s_cur, g_s_delta, grads, scratch,
+                                 (cudaStream_t)stream);
+}
+
+int pile_general_relations_view(void* tape, int B, int N, int nf_effect, int** rowptr, int** col, int** row) {
+  if (!tape || bad_dims(B, N)) return (int)cudaErrorInvalidValue;
+  return general_relations_view(tape, B, N, nf_effect, rowptr, col, row);
+}
+
 long long pile_rgr_param_offset(int tensor_index) {
   return (tensor_index < 0 || tensor_index > 20) ? -1 : rgr_param_offset(tensor_index);
 }

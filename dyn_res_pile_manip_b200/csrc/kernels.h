@@ -138,6 +138,21 @@ int launch_train_forward_relations(const float* wpack, const float* attr, const 
 int launch_train_backward(const float* wpack, const float* dens, void* tape, int B, int N, const float* g_pred,
                           float* g_s_cur, float* g_s_delta, float* grads, void* scratch, cudaStream_t st);
 
+// general-width engine (general.cu): any nf_effect <= 256, forward with kept activations + full backward
+long long general_wpack_slot_offset(int slot, int H);
+long long general_tape_bytes(int B, int N, int H);
+long long general_bwd_scratch_bytes(int B, int N, int H);
+long long general_grad_offset(int tensor_index, int H);
+int general_relations_view(void* tape, int B, int N, int H, int** rowptr, int** col, int** row);
+int launch_general_forward(const float* wpack, int H, const float* attr, const float* dens, const int* particle_nums,
+                           const float* s_cur, const float* s_delta, float adj_thresh, int B, int N, void* tape,
+                           float* s_pred, cudaStream_t st);
+int launch_general_forward_relations(const float* wpack, int H, const float* attr, const float* dens, const float* s_cur,
+                                     const float* s_delta, const int* rowptr, const int* col, const int* row, int B,
+                                     int N, void* tape, float* s_pred, cudaStream_t st);
+int launch_general_backward(const float* wpack, int H, const float* dens, void* tape, int B, int N, const float* g_pred,
+                            float* g_s_cur, float* g_s_delta, float* grads, void* scratch, cudaStream_t st);
+
 // resolution regressor (rgr.cu)
 long long rgr_param_offset(int idx);
 long long rgr_workspace_bytes(int B, int H, int W);

@@ -25,7 +25,9 @@ class RolloutEngine:
         self.model_dy, self.planner = model_dy, planner
         self.rows, self.N, self.T = int(rows), int(N), int(T)
         self.device = torch.device(device if device is not None else "cuda")
-        self.use_graph = use_graph
+        # nf_effect != 64 rolls out step by step on the general-width engine (planner.general_rollout): no capture
+        self.general = not model_dy.model.planner_engines
+        self.use_graph = use_graph and not self.general
         dev = self.device
         self.actions = torch.zeros(rows, T, 4, dtype=torch.float32, device=dev)
         self.states = torch.empty(rows, T, N, 3, dtype=torch.float32, device=dev)
@@ -37,7 +39,7 @@ class RolloutEngine:
         self.reward_weight = planner.config['mpc']['mppi']['reward_weight'] if reward_weight is None else reward_weight
         lib = _lib.load()
         self._parts = torch.zeros(lib.pile_mppi_num_chunks(rows), 2 + 4 * T, dtype=torch.float32, device=dev)
-        self.scratch = torch.empty(lib.pile_step_scratch_bytes(rows, N), dtype=torch.uint8, device=dev)
+        self.scratch = None if self.general else torch.empty(lib.pile_step_scratch_bytes(rows, N), dtype=torch.uint8, device=dev)
         self.goal_img = self.goal_coor = None
         if goal is not None:
             self.set_goal(goal, goal_coor)
@@ -86,8 +88,13 @@ class RolloutEngine:
 
     def _enqueue(self):
         p = self.planner
-        ops.rollout_forward_raw(self._wpack, self.attr, self.dens, self.s0, self.actions, p.pusher,
-                                self.model_dy.adj_thresh, self.scratch, None, out=self.states)
+        if self.general:
+            from .planner import general_rollout
+            with torch.no_grad():
+                self.states.copy_(general_rollout(p, self.model_dy, self.s0, self.dens, self.attr, self.actions))
+        else:
+            ops.rollout_forward_raw(self._wpack, self.attr, self.dens, self.s0, self.actions, p.pusher,
+                                    self.model_dy.adj_thresh, self.scratch, None, out=self.states)
         if self.goal_img is not None:
             N, T = self.N, self.T
             last = self.states[:, T - 1]

@@ -148,6 +148,61 @@ def pack_weights(state, device):
     return out
 
 
+GENERAL_SLOTS = WSLOTS[:35]          # the non-tensor-core slots: what the general-width engine reads
+GENERAL_MAX_WIDTH = 256
+
+
+def pack_weights_general(state, device, H):
+    """18 checkpoint tensors of ANY hidden width H <= 256 -> the packed buffer of the general-width engine
+    (csrc/general.cu): the same forward / backward weight images as `pack_weights`, zero-padded to Hp = 64 * ceil(H / 64)
+    so that padded channels stay exactly 0 through every layer."""
+    lib = _lib.load()
+    if not 1 <= H <= GENERAL_MAX_WIDTH:
+        raise _lib.PileLibraryError("nf_effect=%d: the general-width engine takes 1..%d" % (H, GENERAL_MAX_WIDTH))
+    Hp = (H + 63) // 64 * 64
+    g = {k: _f32(v.detach(), device) for k, v in state.items()}
+
+    def w(name):
+        return g[name + ".weight"], g[name + ".bias"]
+    pe0, bpe0 = w(CKPT_KEYS[0]); pe1, bpe1 = w(CKPT_KEYS[1])
+    re0, bre0 = w(CKPT_KEYS[2]); re1, bre1 = w(CKPT_KEYS[3]); re2, bre2 = w(CKPT_KEYS[4])
+    pp, bpp = w(CKPT_KEYS[5]); rp, brp = w(CKPT_KEYS[6])
+    v0, bv0 = w(CKPT_KEYS[7]); v1, bv1 = w(CKPT_KEYS[8])
+    if pe1.shape != (H, H) or rp.shape != (H, 3 * H + 1) or pp.shape != (H, 2 * H + 1):
+        raise _lib.PileLibraryError("checkpoint does not have nf_effect=%d" % H)
+
+    def sq(m):          # [r][c] -> zero-padded [Hp][Hp]
+        return _pad_cols(_pad_rows(m, Hp), Hp)
+
+    def vec(v):
+        out = v.new_zeros(Hp)
+        out[:v.shape[0]] = v
+        return out
+    blocks = {
+        "W_PE0T": _pad_cols(_pad_rows(pe0.t(), 8), Hp), "B_PE0": vec(bpe0), "W_PE1T": sq(pe1.t()), "B_PE1": vec(bpe1),
+        "W_RE0T": _pad_cols(_pad_rows(re0.t(), 8), Hp), "B_RE0": vec(bre0), "W_RE1T": sq(re1.t()), "B_RE1": vec(bre1),
+        "W_RE2T": sq(re2.t()), "B_RE2": vec(bre2),
+        "W_ET": sq(rp[:, 0:H].t()), "W_RT": sq(rp[:, H:2 * H].t()), "W_ST": sq(rp[:, 2 * H:3 * H].t()),
+        "WD_RP": vec(rp[:, 3 * H]), "B_RP": vec(brp),
+        "W_PT": sq(pp[:, 0:H].t()), "W_AT": sq(pp[:, H:2 * H].t()), "WD_PP": vec(pp[:, 2 * H]), "B_PP": vec(bpp),
+        "W_V0T": sq(v0.t()), "B_V0": vec(bv0), "W_V1T": _pad_cols(_pad_rows(v1.t(), Hp), 4),
+        "B_V1": torch.cat([bv1, bv1.new_zeros(1)]),
+        "W_PE0": _pad_cols(_pad_rows(pe0, Hp), 8), "W_PE1": sq(pe1), "W_RE0": _pad_cols(_pad_rows(re0, Hp), 8),
+        "W_RE1": sq(re1), "W_RE2": sq(re2),
+        "W_E": sq(rp[:, 0:H]), "W_R": sq(rp[:, H:2 * H]), "W_S": sq(rp[:, 2 * H:3 * H]), "W_P": sq(pp[:, 0:H]),
+        "W_A": sq(pp[:, H:2 * H]), "W_V0": sq(v0), "W_V1": _pad_cols(_pad_rows(v1, 4), Hp),
+    }
+    total = lib.pile_general_wpack_slot_offset(len(GENERAL_SLOTS), H)
+    out = torch.zeros(total, dtype=torch.float32, device=device)
+    for i, name in enumerate(GENERAL_SLOTS):
+        blk = blocks[name].contiguous().reshape(-1)
+        off, end = lib.pile_general_wpack_slot_offset(i, H), lib.pile_general_wpack_slot_offset(i + 1, H)
+        if blk.numel() != end - off:
+            raise _lib.PileLibraryError("slot %s: %d floats, library expects %d" % (name, blk.numel(), end - off))
+        out[off:end] = blk
+    return out
+
+
 def cam_matrix12(cam_extrinsic):
     """Rows 0..2 of the world->camera(OpenCV) matrix the reference rebuilds per call (planners.py:197-203)."""
     flip = np.diag([1.0, -1.0, -1.0, 1.0])
@@ -350,7 +405,10 @@ def relations_from_buffer(buf, is_tape, B, N):
     """View the relation lists a step left in its scratch / tape / training-tape (is_tape == 2) buffer (no copy)."""
     lib = _lib.load()
     ps = [C.c_void_p() for _ in range(3)]
-    if int(is_tape) == 2:
+    if isinstance(is_tape, tuple):          # ("general", nf_effect): tape of the general-width engine
+        _lib.check(lib.pile_general_relations_view(_lib.ptr(buf), B, N, int(is_tape[1]), *[C.byref(p) for p in ps]),
+                   "pile_general_relations_view")
+    elif int(is_tape) == 2:
         _lib.check(lib.pile_train_relations_view(_lib.ptr(buf), B, N, *[C.byref(p) for p in ps]), "pile_train_relations_view")
     else:
         _lib.check(lib.pile_relations_view(_lib.ptr(buf), int(is_tape), B, N, *[C.byref(p) for p in ps]), "pile_relations_view")
@@ -535,4 +593,31 @@ def train_backward_raw(wpack, dens, tape, B, N, g_pred, grads, scratch):
     _lib.check(_lib.load().pile_train_backward(_lib.ptr(wpack), _lib.ptr(dens), _lib.ptr(tape), B, N, _lib.ptr(g_pred),
                                                _lib.ptr(g_s), _lib.ptr(g_sd), _lib.ptr(grads), _lib.ptr(scratch),
                                                _stream()), "pile_train_backward")
+    return g_s, g_sd
+
+
+def general_forward_raw(wpack, H, attr, dens, s_cur, s_delta, adj_thresh, particle_nums, tape, rel=None):
+    """Model step of the general-width engine (csrc/general.cu, any nf_effect <= 256); relations searched or supplied."""
+    B, N, _ = s_cur.shape
+    out = torch.empty_like(s_cur)
+    lib = _lib.load()
+    if rel is None:
+        _lib.check(lib.pile_general_forward(_lib.ptr(wpack), int(H), _lib.ptr(attr), _lib.ptr(dens), _lib.ptr(particle_nums),
+                                            _lib.ptr(s_cur), _lib.ptr(s_delta), float(adj_thresh), B, N, _lib.ptr(tape),
+                                            _lib.ptr(out), _stream()), "pile_general_forward")
+    else:
+        _lib.check(lib.pile_general_forward_relations(
+            _lib.ptr(wpack), int(H), _lib.ptr(attr), _lib.ptr(dens), _lib.ptr(s_cur), _lib.ptr(s_delta), _lib.ptr(rel.rowptr),
+            _lib.ptr(rel.col), _lib.ptr(rel.row), B, N, _lib.ptr(tape), _lib.ptr(out), _stream()),
+            "pile_general_forward_relations")
+    return out
+
+
+def general_backward_raw(wpack, H, dens, tape, B, N, g_pred, grads, scratch):
+    """-> (g_s_cur, g_s_delta); grads (flat buffer of the 18 tensors) is accumulated into, None = input gradients only."""
+    g_s = torch.empty(B, N, 3, dtype=torch.float32, device=g_pred.device)
+    g_sd = torch.empty_like(g_s)
+    _lib.check(_lib.load().pile_general_backward(_lib.ptr(wpack), int(H), _lib.ptr(dens), _lib.ptr(tape), B, N,
+                                                 _lib.ptr(g_pred), _lib.ptr(g_s), _lib.ptr(g_sd), _lib.ptr(grads),
+                                                 _lib.ptr(scratch), _stream()), "pile_general_backward")
     return g_s, g_sd

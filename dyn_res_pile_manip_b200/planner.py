@@ -27,6 +27,20 @@ def particle_num_to_iter_time(particle_num):
     return max(int(t), 1)
 
 
+def general_rollout(planner, model_dy, s0, dens, attr, act_seqs):
+    """T-step rollout for a model of any width (nf_effect != 64): the reference's own loop (planners.py:341-359) --
+    pusher model, model step -- on the differentiable ops of the general-width engine; gradients reach the action
+    sequences through torch's autograd over those two ops.  No weight gradients (planners.py:674 optimises actions only)."""
+    from .propnet import _GeneralStepFn
+    states = []
+    s = s0
+    for t in range(act_seqs.shape[1]):
+        s_delta = ops.gen_s_delta(s, act_seqs[:, t], planner.pusher)
+        s = _GeneralStepFn.apply(s, s_delta, attr, dens, model_dy.model, None, None)
+        states.append(s)
+    return torch.stack(states, dim=1)
+
+
 class _RolloutFn(torch.autograd.Function):
     """T-step rollout; differentiable w.r.t. the action sequences only (planners.py:674)."""
 
@@ -100,9 +114,12 @@ class _GDLoop:
         self.rew_mean = torch.zeros(n_batch // n_batch1, self.REW_CAP, **f)
         self.rew_std = torch.zeros(n_batch // n_batch1, self.REW_CAP, **f)
         self.iter = torch.zeros(1, **i32)
-        self.scratch = net.workspace.scratch(rows, N, device)
-        self.bwd_scratch = net.workspace.bwd(rows, N, device)
-        self.tape = ops.new_tape(rows, N, T, device)
+        self.general = not net.planner_engines      # nf_effect != 64: rollout through general_rollout + autograd
+        if not self.general:
+            self.scratch = net.workspace.scratch(rows, N, device)
+            self.bwd_scratch = net.workspace.bwd(rows, N, device)
+            self.tape = ops.new_tape(rows, N, T, device)
+        self._graph_states = None
         self.sig = None
         self.g_fwd = self.g_bwd = None
 
@@ -115,8 +132,14 @@ class _GDLoop:
     def _enqueue_fwd(self, c):
         N, T = self.N, self.T
         last = self.states[:, T - 1]                              # view: last-step states, stride T*N*3
-        ops.rollout_forward_raw(c['wpack'], self.attr, self.dens, self.s0, self.acts, c['pusher'], c['adj_thresh'],
-                                self.scratch, self.tape, out=self.states)
+        if self.general:
+            leaf = self.acts.detach().requires_grad_(True)
+            with torch.enable_grad():
+                self._graph_states = (general_rollout(c['planner'], c['model_dy'], self.s0, self.dens, self.attr, leaf), leaf)
+            self.states.copy_(self._graph_states[0].detach())
+        else:
+            ops.rollout_forward_raw(c['wpack'], self.attr, self.dens, self.s0, self.acts, c['pusher'], c['adj_thresh'],
+                                    self.scratch, self.tape, out=self.states)
         # the loss only looks at the last step (reward_seqs = next_r[:, -1], planners.py:438)
         ops.reward_raw(last, self.rows, T * N * 3, N, self.goal_img, self.goal_coor, c['cam'], c['offset'], True,
                        want_argmin=True, out=self.reward, arg=self.argmin)
@@ -134,8 +157,14 @@ class _GDLoop:
             self.g_states[:, :T - 1].zero_()
         ops.reward_backward_raw(last, self.rows, T * N * 3, N, self.goal_img, self.goal_coor, c['cam'], c['offset'],
                                 True, self.g_reward, self.argmin, self.g_states[:, T - 1], T * N * 3, False)
-        ops.rollout_backward_raw(c['wpack'], self.dens, self.s0, self.acts, c['pusher'], self.tape, self.states,
-                                 self.g_states, self.bwd_scratch, out=self.g_act)
+        if self.general:
+            states, leaf = self._graph_states
+            self._graph_states = None
+            (g_leaf,) = torch.autograd.grad([states], [leaf], [self.g_states])
+            self.g_act.copy_(g_leaf)
+        else:
+            ops.rollout_backward_raw(c['wpack'], self.dens, self.s0, self.acts, c['pusher'], self.tape, self.states,
+                                     self.g_states, self.bwd_scratch, out=self.g_act)
         ops.adam_clamp_dev(self.acts, self.g_act, self.exp_avg, self.exp_avg_sq, self.iter, c['lr'], c['lo'], c['hi'])
         ops.counter_add(self.iter, 1)
 
@@ -303,7 +332,10 @@ class PlannerGD(Planner):
         start = torch.cuda.Event(enable_timing=True)
         end = torch.cuda.Event(enable_timing=True)
         start.record()
-        states = _RolloutFn.apply(act_seqs, self, model_dy, s0, dens, attr)
+        if model_dy.model.planner_engines:
+            states = _RolloutFn.apply(act_seqs, self, model_dy, s0, dens, attr)
+        else:
+            states = general_rollout(self, model_dy, s0, dens, attr, ops._f32(act_seqs, dev))
         end.record()
         end.synchronize()          # the reference synchronises after every step (planners.py:357); here once
         return {'model_rollout': {'state_pred': states}, 'rollout_time': start.elapsed_time(end)}
@@ -407,7 +439,8 @@ class PlannerGD(Planner):
         lo, hi = self.action_box(0)
         ctx = {'wpack': net.packed_weights(device), 'pusher': self.pusher, 'adj_thresh': model_dy.adj_thresh,
                'cam': [float(v) for v in self.cam_params], 'offset': self.reward_offset(),
-               'lr': self.config['mpc']['gd']['lr'], 'lo': [float(v) for v in lo], 'hi': [float(v) for v in hi]}
+               'lr': self.config['mpc']['gd']['lr'], 'lo': [float(v) for v in lo], 'hi': [float(v) for v in hi],
+               'planner': self, 'model_dy': model_dy}
         sig = (ctx['wpack'].data_ptr(), _lib.load().pile_get_tensor_cores(), self.pusher.signature(),
                float(model_dy.adj_thresh), tuple(ctx['cam']), ctx['offset'], float(ctx['lr']), tuple(ctx['lo']),
                tuple(ctx['hi']))
@@ -432,7 +465,8 @@ class PlannerGD(Planner):
             # a problem size seen for the first time runs launch by launch (the loop is GPU-bound, the host keeps up);
             # from the second call on the two captured graphs are replayed
             loop.calls += 1
-            graph = self.use_graph and n_iter > 0 and (loop.calls >= 2 or self.capture_first_call)
+            graph = (self.use_graph and n_iter > 0 and (loop.calls >= 2 or self.capture_first_call)
+                     and not loop.general)          # the general-width rollout runs under autograd: no capture
             if graph and loop.ensure_captured(sig, ctx):
                 loop.reset(*inputs)                      # the capture's warm-up iteration moved the actions
             for i in range(n_iter):

@@ -118,6 +118,52 @@ class _TrainStepFn(torch.autograd.Function):
         return (g_s, g_sd, None, None, None, None, None) + tuple(out)
 
 
+class _GeneralStepFn(torch.autograd.Function):
+    """One model step on the general-width engine (any nf_effect <= 256): input gradients always, weight gradients
+    when a parameter requires grad."""
+
+    @staticmethod
+    def forward(ctx, s_cur, s_delta, attr, dens, owner, particle_nums, rel, *params):
+        s_cur_c, s_delta_c = ops._f32(s_cur.detach()), ops._f32(s_delta.detach())
+        ops._require_cuda(s_cur_c, "s_cur")
+        dev = s_cur_c.device
+        B, N, _ = s_cur_c.shape
+        H = owner.nf_effect
+        attr_c, dens_c = ops._f32(attr.detach(), dev), ops._f32(dens.detach(), dev)
+        wpack = owner.packed_weights(dev)
+        nbytes = _lib.load().pile_general_tape_bytes(B, N, H)
+        if nbytes < 0:
+            raise _lib.PileLibraryError("unsupported sizes B=%d N=%d nf_effect=%d" % (B, N, H))
+        tape = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        pn = None
+        if particle_nums is not None:
+            pn = torch.as_tensor(particle_nums).to(device=dev, dtype=torch.int32).contiguous()
+        out = ops.general_forward_raw(wpack, H, attr_c, dens_c, s_cur_c, s_delta_c, owner.adj_thresh, pn, tape, rel)
+        owner.last_relations_buffer = (tape, ("general", H), B, N)
+        ctx.save_for_backward(wpack, dens_c, tape)
+        ctx.dims, ctx.shapes = (B, N, H), [tuple(p.shape) for p in params]
+        ctx.wgrad = any(p.requires_grad for p in params)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        wpack, dens, tape = ctx.saved_tensors
+        B, N, H = ctx.dims
+        g = ops._f32(g)
+        lib = _lib.load()
+        grads = None
+        if ctx.wgrad:
+            grads = torch.zeros(lib.pile_general_grad_offset(len(ctx.shapes), H), dtype=torch.float32, device=g.device)
+        scratch = torch.empty(lib.pile_general_scratch_bytes(B, N, H), dtype=torch.uint8, device=g.device)
+        g_s, g_sd = ops.general_backward_raw(wpack, H, dens, tape, B, N, g, grads, scratch)
+        out = [None] * len(ctx.shapes)
+        if grads is not None:
+            for i, shape in enumerate(ctx.shapes):
+                off, end = lib.pile_general_grad_offset(i, H), lib.pile_general_grad_offset(i + 1, H)
+                out[i] = grads[off:end].view(shape)
+        return (g_s, g_sd, None, None, None, None, None) + tuple(out)
+
+
 class PropModuleDiffDen(nn.Module):
     """Propagation network (reference model/gnn_dyn.py:113-198), weights only + CUDA forward."""
 
@@ -126,6 +172,11 @@ class PropModuleDiffDen(nn.Module):
         self.config = config
         nf = config['train']['particle']['nf_effect']
         self.nf_effect = nf
+        # 64 (config/mpc/config.yaml:91) runs on the planner engines (FP32 tiles / tcgen05); any other width on the
+        # general-width engine (csrc/general.cu)
+        self.planner_engines = nf == 64
+        if not 1 <= nf <= ops.GENERAL_MAX_WIDTH:
+            raise _lib.PileLibraryError("nf_effect=%d: supported widths are 1..%d" % (nf, ops.GENERAL_MAX_WIDTH))
         self.add_delta = config['train']['particle']['add_delta']
         self.use_gpu = use_gpu
         # construction order = reference order, so torch.manual_seed(s) gives identical initial weights
@@ -142,16 +193,20 @@ class PropModuleDiffDen(nn.Module):
     # ---- weights -> packed device buffer, re-packed only when a parameter changed --------------
     def packed_weights(self, device):
         params = list(self.named_parameters())
-        stamp = tuple((p.data_ptr(), p._version) for _, p in params)
+        stamp = (self.planner_engines,) + tuple((p.data_ptr(), p._version) for _, p in params)
         hit = self._packed.get(str(device))
         if hit is None or hit[0] != stamp:
             state = {"model." + k: p for k, p in params}
-            self._packed[str(device)] = (stamp, ops.pack_weights(state, device))
+            packed = (ops.pack_weights(state, device) if self.planner_engines
+                      else ops.pack_weights_general(state, device, self.nf_effect))
+            self._packed[str(device)] = (stamp, packed)
         return self._packed[str(device)][1]
 
     def forward(self, a_cur, s_cur, s_delta, Rr, Rs, particle_dens, verbose=False):
         rel = Rr if isinstance(Rr, ops.Relations) else ops.Relations.from_dense(Rr, Rs)
         params = [p for _, p in self.named_parameters()]
+        if not self.planner_engines:
+            return _GeneralStepFn.apply(s_cur, s_delta, a_cur, particle_dens, self, None, rel, *params)
         wants_wgrad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if wants_wgrad or rel.max_degree > ops.KMAX:
             # training (weight gradients), or relation lists denser than the planner's engines take: general kernels
@@ -167,9 +222,6 @@ class PropNetDiffDenModel(nn.Module):
         self.config = config
         self.adj_thresh = config['train']['particle']['adj_thresh']
         self.model = PropModuleDiffDen(config, use_gpu)
-        if self.model.nf_effect != 64 and _lib.os.path.isfile(_lib.LIB_PATH):
-            if _lib.load().pile_nf_effect() != self.model.nf_effect:
-                raise _lib.PileLibraryError("libpilegnn is compiled for nf_effect=%d" % _lib.load().pile_nf_effect())
 
     def predict_one_step(self, a_cur, s_cur, s_delta, particle_dens, particle_nums=None):
         assert type(a_cur) == torch.Tensor
@@ -179,6 +231,8 @@ class PropNetDiffDenModel(nn.Module):
         assert s_cur.shape == s_delta.shape
         self.model.adj_thresh = self.adj_thresh
         params = [p for _, p in self.model.named_parameters()]
+        if not self.model.planner_engines:
+            return _GeneralStepFn.apply(s_cur, s_delta, a_cur, particle_dens, self.model, particle_nums, None, *params)
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             # training: weight gradients wanted (train/train_gnn_dyn.py:150-199)
             return _TrainStepFn.apply(s_cur, s_delta, a_cur, particle_dens, self.model, particle_nums, None, *params)

@@ -20,10 +20,11 @@
 extern "C" {
 #endif
 
-#define PILE_ABI_VERSION 2
+#define PILE_ABI_VERSION 3
 
 int pile_abi_version(void);
-int pile_nf_effect(void);        /* hidden width compiled in (config train.particle.nf_effect = 64) */
+int pile_nf_effect(void);        /* hidden width the planner engines are compiled for (config train.particle.nf_effect
+                                  * = 64); other widths run on the general-width engine, pile_general_* below */
 int pile_max_relations(void);    /* 10, model/gnn_dyn.py:231 */
 const char* pile_error_string(int code);
 
@@ -215,6 +216,31 @@ int pile_train_forward_relations(const float* wpack, const float* attr, const fl
 int pile_train_backward(const float* wpack, const float* dens, void* train_tape, int B, int N, const float* g_pred,
                         float* g_s_cur, float* g_s_delta, float* grads, void* scratch, void* stream);
 int pile_train_relations_view(void* train_tape, int B, int N, int** rowptr, int** col, int** row);
+
+/* ---- general-width engine: the same model step for ANY hidden width nf_effect <= 256 (model/gnn_dyn.py:119 reads it
+ * from the config; the engines above are compiled for 64).  Feature arrays and weight matrices are zero-padded to a
+ * multiple of 64, the layers are block GEMMs on the CUDA cores.  wpack: the forward ([in][out]) and backward
+ * ([out][in]) images of the 9 layers, padded, in the order of the non-tensor-core weight slots;
+ * pile_general_wpack_slot_offset(slot, nf_effect) = float offset of slot 0..34, slot 35 = total floats.
+ * pile_general_forward leaves every layer input in `tape` (pile_general_tape_bytes); pile_general_backward returns
+ * d/ds_cur, d/ds_delta (overwritten) and, when grads != NULL, ACCUMULATES the 18 weight gradients into `grads`
+ * (state_dict order and shapes, pile_general_grad_offset(i, nf_effect), i = 18: total) -- grads == NULL is the
+ * planner's input-gradient-only case (planners.py:674).  Replaces predict_one_step / forward / their autograd for
+ * checkpoints with nf_effect != 64 in the planner, the MPC loop and the training loop alike. */
+long long pile_general_wpack_slot_offset(int slot, int nf_effect);
+long long pile_general_tape_bytes(int B, int N, int nf_effect);
+long long pile_general_scratch_bytes(int B, int N, int nf_effect);
+long long pile_general_grad_offset(int tensor_index, int nf_effect);
+int pile_general_forward(const float* wpack, int nf_effect, const float* attr, const float* dens,
+                         const int* particle_nums, const float* s_cur, const float* s_delta, float adj_thresh, int B,
+                         int N, void* tape, float* s_pred, void* stream);
+int pile_general_forward_relations(const float* wpack, int nf_effect, const float* attr, const float* dens,
+                                   const float* s_cur, const float* s_delta, const int* rowptr, const int* col,
+                                   const int* row, int B, int N, void* tape, float* s_pred, void* stream);
+int pile_general_backward(const float* wpack, int nf_effect, const float* dens, void* tape, int B, int N,
+                          const float* g_pred, float* g_s_cur, float* g_s_delta, float* grads, void* scratch,
+                          void* stream);
+int pile_general_relations_view(void* tape, int B, int N, int nf_effect, int** rowptr, int** col, int** row);
 
 /* ---- resolution regressor: replaces MPCResRgrNoPool.forward (model/res_regressor.py:106-144), the network that
  * picks the particle count once per MPC step (env/flex_env.py:981-998, 1080-1090).  params: all 20 tensors of the

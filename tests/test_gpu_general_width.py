@@ -1,0 +1,216 @@
+"""General-width engine (csrc/general.cu): checkpoints with nf_effect != 64 (model/gnn_dyn.py:119) through the same
+drop-in API -- predict_one_step, forward(Rr, Rs), training gradients, planner rollout and the GD planner.  Pinned by a
+fixture the REAL reference generated at nf_effect = 96 (tests/golden/make_golden_width.py), by the reference's own
+width-64 training fixture run through the general engine, and by the oracle at widths 150 and 256."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dyn_res_pile_manip_b200 as P
+from dyn_res_pile_manip_b200 import ops, synthetic
+from oracle import pile_oracle as O
+from test_gpu_training import training_loss
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def config_with_width(nf):
+    cfg = copy.deepcopy(synthetic.default_config())
+    cfg['train']['particle']['nf_effect'] = nf
+    return cfg
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def min_abs_preactivation(W, st, sd, dn):
+    """Smallest |ReLU input| of one oracle step (float64).  A value within a few fp32 ulps of zero has an
+    implementation-defined mask; on batches this small one flipped mask moves the weight gradients by percents."""
+    seen, orig = [], torch.relu
+
+    def spy(x):
+        seen.append(float(x.detach().abs().min()))
+        return orig(x)
+    torch.relu = spy
+    try:
+        B, N, _ = st.shape
+        O.predict_one_step({k: v.double() for k, v in W.items()}, 0.08, torch.zeros(B, N, dtype=torch.float64),
+                           torch.tensor(st).double(), torch.tensor(sd).double(), torch.tensor(dn).double())
+    finally:
+        torch.relu = orig
+    return min(seen)
+
+
+def test_width96_loss_predictions_and_all_gradients_vs_reference():
+    g = np.load(os.path.join(HERE, "golden", "golden_width_v1.npz"))
+    nf = int(g["nf_effect"])
+    model = P.PropNetDiffDenModel(config_with_width(nf), True)
+    model.load_state_dict({k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w/")})
+    model = model.to(DEV)
+    assert not model.model.planner_engines
+    st, sd, at, dn = (torch.tensor(g[k]).to(DEV) for k in ("states", "states_delta", "attrs", "dens"))
+    nums = torch.tensor(g["particle_nums"])
+    # predictions of both roll-out steps
+    with torch.no_grad():
+        s = st[:, 0]
+        for t in range(sd.shape[1]):
+            s = model.predict_one_step(at[:, 0], s, sd[:, t], dn, nums)
+            for j, n in enumerate(g["particle_nums"]):
+                np.testing.assert_allclose(s[j, :n].cpu().numpy(), g["preds"][j, t, :n], rtol=0, atol=2e-6)
+    # loss, weight gradients, input gradients
+    s0 = st[:, 0].clone().requires_grad_(True)
+    sdg = sd.clone().requires_grad_(True)
+    states = torch.cat([s0[:, None], st[:, 1:]], dim=1)
+    loss = training_loss(model, states, sdg, at, dn, nums)
+    assert abs(loss.item() - float(g["loss"])) <= 2e-7 + 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    worst = {}
+    for k, p in model.named_parameters():
+        ref = g["g/" + k]
+        assert p.grad is not None and p.grad.shape == ref.shape, k
+        worst[k] = np.abs(p.grad.cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1e-12)
+    print("width 96: 18 weight gradients vs reference autograd (max-abs error / tensor max):")
+    for k, v in worst.items():
+        print("   %-45s %.1e" % (k, v))
+    assert max(worst.values()) <= 2e-5, worst
+    assert rel_l2(s0.grad.cpu().numpy(), g["g_s0"]) <= 1e-5
+    assert rel_l2(sdg.grad.cpu().numpy(), g["g_states_delta"]) <= 1e-5
+
+
+def test_width64_on_the_general_engine_vs_reference_training_fixture(golden_weights):
+    """The reference's width-64 fixture (loss + 18 gradients from its autograd) through the general engine."""
+    g = np.load(os.path.join(HERE, "golden", "golden_train_v1.npz"))
+    model = P.PropNetDiffDenModel(synthetic.default_config(), True)
+    model.load_state_dict(golden_weights)
+    model = model.to(DEV)
+    model.model.planner_engines = False          # route width 64 to csrc/general.cu
+    args = [torch.tensor(g[k]).to(DEV) for k in ("states", "states_delta", "attrs", "dens")]
+    loss = training_loss(model, *args, torch.tensor(g["particle_nums"]))
+    assert abs(loss.item() - float(g["loss"])) <= 2e-7 + 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    for k, p in model.named_parameters():
+        ref = g["g/" + k]
+        err = np.abs(p.grad.cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1e-12)
+        assert err <= (4e-3 if "relation_encoder" in k else 5e-6), (k, err)      # knife-edge ReLU: test_gpu_training.py
+    # and it agrees with the width-64 training kernels (csrc/train.cu)
+    grads_general = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.model.planner_engines = True
+    model.zero_grad()
+    training_loss(model, *args, torch.tensor(g["particle_nums"])).backward()
+    for k, p in model.named_parameters():
+        scale = float(p.grad.abs().max())
+        assert float((p.grad - grads_general[k]).abs().max()) <= (4e-3 if "relation_encoder" in k else 5e-6) * scale, k
+
+
+@pytest.mark.parametrize("nf,N,B", [(150, 60, 3), (256, 33, 2), (8, 20, 2)])
+def test_rollout_and_action_gradient_vs_oracle(nf, N, B):
+    cfg, env = config_with_width(nf), synthetic.FakeEnv()
+    torch.manual_seed(1)
+    model = P.PropNetDiffDenModel(cfg, True).to(DEV)
+    planner = P.PlannerGD(cfg, env)
+    n_sample, T = 2, 3
+    st, dn = synthetic.make_pile_batch(B, N, seed=nf)
+    acts_np = synthetic.random_actions(n_sample * B, T, seed=nf)
+    planner.particle_num = N
+    acts = torch.tensor(acts_np, device=DEV, requires_grad=True)
+    out = planner.ptcl_model_rollout(torch.tensor(st).to(DEV), torch.tensor(dn).to(DEV), torch.zeros(B, N, device=DEV),
+                                     model, acts)
+    pred = out["model_rollout"]["state_pred"]
+    W = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    acts_o = torch.tensor(acts_np, requires_grad=True)
+    ref = O.rollout(W, 0.08, env.get_cam_extrinsics(), synthetic.GLOBAL_SCALE, torch.tensor(st), torch.tensor(dn),
+                    torch.zeros(B, N), acts_o)
+    assert rel_l2(pred.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(0))
+    (pred * w.to(DEV)).sum().backward()
+    (ref * w).sum().backward()
+    assert rel_l2(acts.grad.cpu().numpy(), acts_o.grad.numpy()) < 2e-3
+    # relation sets of the last step: bit-exact against the oracle's adjacency on the same states
+    rel = model.relations_of_last_step().edge_sets()
+    s_prev = ref[:, T - 2].detach()
+    sd = O.gen_s_delta(env.get_cam_extrinsics(), synthetic.GLOBAL_SCALE, s_prev, torch.tensor(acts_np[:, T - 1]))
+    adj = O.adjacency(s_prev, sd, 0.08)
+    for b in range(n_sample * B):
+        want = np.argwhere(adj[b].numpy() > 0)
+        got = rel[b]
+        if not np.array_equal(got, want):         # a flipped neighbour after 2 free-running steps is a rounding tie
+            assert len(set(map(tuple, got)) ^ set(map(tuple, want))) <= 2
+
+
+def test_dense_relation_entry_and_weight_gradients_width150():
+    """model.forward(a_cur, s_cur, s_delta, Rr, Rs, dens) with dense one-hot Rr / Rs at width 150 vs the oracle."""
+    nf, B, N = 150, 2, 30
+    torch.manual_seed(2)
+    model = P.PropNetDiffDenModel(config_with_width(nf), True).to(DEV)
+    Wd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    for seed in range(3, 40):          # first inputs without a ReLU sitting on the fence (see min_abs_preactivation)
+        st, dn = synthetic.make_pile_batch(B, N, seed=seed)
+        sd = (np.random.RandomState(seed).normal(0, 0.01, st.shape)).astype(np.float32)
+        if min_abs_preactivation(Wd, st, sd, dn) > 4e-7:
+            break
+    adj = O.adjacency(torch.tensor(st), torch.tensor(sd), 0.08)
+    Rr, Rs = O.one_hot_relations(adj)
+    W = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref = O.propnet_forward(W, torch.zeros(B, N), torch.tensor(st), torch.tensor(sd), Rr, Rs, torch.tensor(dn))
+    out = model.model.forward(torch.zeros(B, N, device=DEV), torch.tensor(st).to(DEV), torch.tensor(sd).to(DEV),
+                              Rr.to(DEV), Rs.to(DEV), torch.tensor(dn).to(DEV))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=0, atol=3e-6)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    (out * w.to(DEV)).sum().backward()
+    (ref * w).sum().backward()
+    for k, p in model.named_parameters():
+        gref = W[k].grad.numpy()
+        err = np.abs(p.grad.cpu().numpy() - gref).max() / max(np.abs(gref).max(), 1e-12)
+        print("   %-45s %.1e" % (k, err))
+        assert err <= 2e-5, k
+
+
+def test_gd_planner_width150_matches_oracle_adam_loop():
+    """Three Adam iterations of the reference's MPC entry with a width-150 model == the oracle + autograd loop."""
+    nf = 150
+    cfg, env = config_with_width(nf), synthetic.FakeEnv()
+    torch.manual_seed(4)
+    model = P.PropNetDiffDenModel(cfg, True).to(DEV)
+    planner = P.PlannerGD(cfg, env)
+    n_batch, n_sample, N, T, iters = 2, 3, 40, 2, 3
+    st, dn = synthetic.make_pile_batch(n_batch, N, seed=5)
+    act0 = synthetic.random_actions(n_sample, T, seed=5).transpose(1, 0, 2).copy()
+    goal = synthetic.make_goal("bar")
+    res = planner.trajectory_optimization_ptcl_multi_traj(
+        st, dn, np.zeros((n_batch, N), np.float32), goal, model, act0.astype(np.float64), np.zeros(T), n_sample, T, iters,
+        None, None, use_gpu=True, rollout_best_action_sequence=True)
+    assert res["iter_num"] == iters - 1
+    W = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    acts = torch.tensor(np.repeat(act0.transpose(1, 0, 2)[:, :, None, :], n_batch, axis=0), dtype=torch.float,
+                        requires_grad=True)
+    opt = torch.optim.Adam([acts], lr=0.05, betas=(0.9, 0.999))
+    coords = np.argwhere(goal < 0.5)[:, ::-1].astype(np.float32)
+    coor, _ = synthetic.fps_np(coords, min(5 * N, len(coords)), 0)
+    lo, hi = O.action_box(env.cvx_region)
+    means = []
+    for _ in range(iters):
+        pred = O.rollout(W, 0.08, env.get_cam_extrinsics(), synthetic.GLOBAL_SCALE, torch.tensor(st), torch.tensor(dn),
+                         torch.zeros(n_batch, N), acts[:, :, 0, :])
+        obs = pred.reshape(n_sample * n_batch, 1, T, N, 3).permute(0, 2, 1, 3, 4)
+        reward, _ = O.evaluate_traj(obs, torch.from_numpy(goal), env.get_cam_params(), torch.from_numpy(coor))
+        means.append(float(reward.reshape(n_sample, n_batch)[:, 0].mean()))
+        opt.zero_grad()
+        torch.sum(-reward).backward()
+        opt.step()
+        with torch.no_grad():
+            acts.data[:, :, 0, :] = torch.minimum(torch.maximum(acts.data[:, :, 0, :], torch.tensor(lo).float()),
+                                                  torch.tensor(hi).float())
+    np.testing.assert_allclose(res["rew_mean"][0, :iters], means, rtol=1e-4)
+    np.testing.assert_allclose(res["action_full"], acts.detach().numpy()[:, 0, 0, :], rtol=0, atol=2e-3)
+    assert res["observation_sequence"].shape == (T, N, 3)
+
+
+def test_width_limits():
+    with pytest.raises(P._lib.PileLibraryError):
+        P.PropNetDiffDenModel(config_with_width(257), True)

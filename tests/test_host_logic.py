@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pile_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.pile_abi_version() == _lib.ABI_VERSION == 3
     assert lib.pile_nf_effect() == 64 and lib.pile_max_relations() == 10
 
 
@@ -39,6 +39,31 @@ def test_argument_validation_without_gpu(lib):
     assert lib.pile_tape_step_bytes(4, 100) > 0
     assert lib.pile_predict_step(None, None, None, None, None, None, 0.08, 4, 100, None, None, None, None) != 0
     assert lib.pile_mppi_num_chunks(1000) == 8
+
+
+def test_general_width_weight_pack_layout(lib):
+    """Packed buffer of the general-width engine (csrc/general.cu): every matrix zero-padded to 64 * ceil(H / 64),
+    forward images transposed, backward images in checkpoint layout; offsets come from the library."""
+    from oracle import pile_oracle as O
+    for H in (96, 150, 64):
+        Hp = (H + 63) // 64 * 64
+        W = O.weights_from_seed(3, nf=H)
+        pack = ops.pack_weights_general(W, torch.device("cpu"), H)
+        off = {n: lib.pile_general_wpack_slot_offset(i, H) for i, n in enumerate(ops.GENERAL_SLOTS)}
+        assert pack.numel() == lib.pile_general_wpack_slot_offset(len(ops.GENERAL_SLOTS), H)
+        rp = W["model.relation_propagator.linear.weight"]
+        blk = pack[off["W_ST"]:off["W_ST"] + Hp * Hp].view(Hp, Hp)
+        assert torch.equal(blk[:H, :H], rp[:, 2 * H:3 * H].t())
+        assert float(blk[H:].abs().sum()) == 0 and float(blk[:, H:].abs().sum()) == 0
+        assert torch.equal(pack[off["W_S"]:off["W_S"] + Hp * Hp].view(Hp, Hp)[:H, :H], rp[:, 2 * H:3 * H])
+        assert torch.equal(pack[off["WD_RP"]:off["WD_RP"] + H], rp[:, 3 * H])
+        pe0 = W["model.particle_encoder.model.0.weight"]
+        assert torch.equal(pack[off["W_PE0T"]:off["W_PE0T"] + 8 * Hp].view(8, Hp)[:5, :H], pe0.t())
+        v1 = W["model.particle_predictor.linear_1.weight"]
+        assert torch.equal(pack[off["W_V1"]:off["W_V1"] + 4 * Hp].view(4, Hp)[:3, :H], v1)
+    assert lib.pile_general_wpack_slot_offset(0, 300) == -1 and lib.pile_general_tape_bytes(2, 50, 300) == -1
+    assert lib.pile_general_grad_offset(18, 150) == sum(v.numel() for v in O.weights_from_seed(0, nf=150).values())
+    assert lib.pile_general_forward(None, 150, None, None, None, None, None, 0.08, 2, 50, None, None, None) != 0
 
 
 def test_weight_pack_layout(lib, golden_weights):
