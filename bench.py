@@ -422,6 +422,22 @@ def main():
                         if mode else "FP32 CUDA-core tile GEMM engine (parity anchor)")
 
         extras = world == 1 and not args.no_extras
+        # BASELINE config 3 is a resolution SWEEP (the regressor's output range): the other particle counts, device-timed
+        # the same way (L2 flushed, CUDA events, K steps after W warm-ups)
+        sweep = None
+        if extras and args.workload == "cfg3_n300":
+            sweep = {}
+            for wl in ("cfg3_n50", "cfg3_n100", "cfg3_n200"):
+                s_w, n_w, t_w = WORKLOADS[wl]
+                st_w, dn_w = synthetic.make_pile_batch(1, n_w, seed=0)
+                a_w = Arm(s_w, n_w, t_w, 7000 + n_w, K + Wm, (st_w, dn_w))
+                for i in range(Wm):
+                    a_w.step_device(i)
+                ms_w, _, _ = timed_loop(lambda i: a_w.step_device(Wm + i), K)
+                launches += K * a_w.launches_per_step()
+                sweep[wl] = {"value": s_w * n_w * t_w * K / (ms_w * 1e-3), "unit": UNIT, "ms_per_step": ms_w / K,
+                             "kernel_ms": profile_kernels(a_w)}
+                del a_w
         parity = parity_report(model, planner, dev) if extras else None
         plan = plan_latency(model, planner, env, goal, dev, args) if extras else None
         cpu = None
@@ -457,6 +473,8 @@ def main():
                         "d2h_bytes_per_step": samples * 4 + (2 + 4 * T) * 4},
                 "gpu_launches": launches,
                 "clocks": clocks, "roofline": roof}
+        if sweep:
+            line["resolution_sweep"] = sweep
         if strong:
             line["strong"] = strong
         if cfg5:
@@ -679,6 +697,37 @@ def plan_latency(model, planner, env, goal, dev, args):
                              "workload": "32 samples x <=300 particles (padded, particle_nums), 3 roll-out steps: forward + "
                                          "per-sample MSE + backward (18 weight gradients) + torch Adam, through predict_one_step"}
     del tmodel, opt
+
+    # a checkpoint with another hidden width (model/gnn_dyn.py:119; north_star: "hidden ~150") runs on the general-width
+    # engine (csrc/general.cu, FP32 CUDA-core block GEMMs): one model step of config 2's batch, forward only and
+    # forward + input/weight gradients
+    import copy
+    cfg_w = copy.deepcopy(synthetic.default_config())
+    cfg_w['train']['particle']['nf_effect'] = 150
+    torch.manual_seed(0)
+    wmodel = PropNetDiffDenModel(cfg_w, True).to(dev)
+    s8 = torch.tensor(st2).to(dev).repeat(s2, 1, 1)
+    sd8 = (0.01 * torch.randn(s8.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(8)))
+    a8, d8 = torch.zeros(s2, n2, device=dev), torch.tensor(dn2).to(dev).repeat(s2)
+    fw, fb = [], []
+    for i in range(8):
+        torch.cuda.synchronize()
+        t_a = time.perf_counter()
+        with torch.no_grad():
+            wmodel.predict_one_step(a8, s8, sd8, d8)
+        torch.cuda.synchronize()
+        fw.append((time.perf_counter() - t_a) * 1e3)
+        t_a = time.perf_counter()
+        wmodel.zero_grad()
+        wmodel.predict_one_step(a8, s8, sd8, d8).square().sum().backward()
+        torch.cuda.synchronize()
+        fb.append((time.perf_counter() - t_a) * 1e3)
+    plan["general_width"] = {"nf_effect": 150, "forward_ms": sorted(fw[2:])[len(fw[2:]) // 2],
+                             "forward_backward_ms": sorted(fb[2:])[len(fb[2:]) // 2],
+                             "particle_steps_per_s": s2 * n2 / (sorted(fw[2:])[len(fw[2:]) // 2] * 1e-3),
+                             "workload": "one model step, 256 samples x 100 particles, nf_effect = 150 (padded to 192) on the "
+                                         "general-width engine: forward; forward + backward with all 18 weight gradients"}
+    del wmodel
 
     # the other planner-side piece of an MPC step: RGB-D observation -> 30 particle
     # re-samplings (env/flex_env.py:933-951), host observation in -> host particles out

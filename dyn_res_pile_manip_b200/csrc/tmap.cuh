@@ -33,14 +33,15 @@ inline EncodeTiledFn tmap_encoder() {
 }
 
 // byte tensor [n2][n1][inner] (inner contiguous; stride1 / stride2 in bytes, multiples of 16), box [1][box1][inner]
+// (or [box2][box1][inner])
 // with the swizzle that matches `inner` (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B).  Returns 0 or a cudaError.
 inline int tmap_encode_rows(CUtensorMap* out, void* base, uint32_t inner, uint64_t n1, uint64_t stride1, uint64_t n2,
-                            uint64_t stride2, uint32_t box1) {
+                            uint64_t stride2, uint32_t box1, uint32_t box2 = 1) {
   EncodeTiledFn enc = tmap_encoder();
   if (enc == nullptr) return (int)cudaErrorNotSupported;
   const cuuint64_t dims[3] = {inner, n1, n2};
   const cuuint64_t strides[2] = {stride1, stride2};
-  const cuuint32_t box[3] = {inner, box1, 1};
+  const cuuint32_t box[3] = {inner, box1, box2};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUtensorMapSwizzle sw = inner == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                              : (inner == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);

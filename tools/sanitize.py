@@ -55,5 +55,25 @@ from dyn_res_pile_manip_b200 import MPCResRgrNoPool
 rg = MPCResRgrNoPool({"train_res_cls": {"state_h": 224, "state_w": 224, "res_dim": 6}})
 y = rg.forward(torch.rand(2, 6, 224, 224).cuda())
 assert torch.isfinite(y).all()
+# general-width engine (csrc/general.cu): width 150 (padded to 192, streamed weight blocks) and 96: training step with
+# weight gradients on a padded batch, planner rollout with action gradients
+import copy
+for nf in (150, 96):
+    cfg_w = copy.deepcopy(cfg)
+    cfg_w['train']['particle']['nf_effect'] = nf
+    torch.manual_seed(0)
+    wm = PropNetDiffDenModel(cfg_w, True).cuda()
+    st, dn = synthetic.make_pile_batch(3, 45, seed=2)
+    s = torch.tensor(st).cuda()
+    out = wm.predict_one_step(torch.zeros(3, 45).cuda(), s, sd, torch.tensor(dn).cuda(), torch.tensor([45, 31, 20]))
+    (out ** 2).mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in wm.parameters())
+    planner.particle_num = 37
+    st, dn = synthetic.make_pile_batch(1, 37, seed=1)
+    acts = torch.tensor(synthetic.random_actions(5, 2, seed=2), device="cuda", requires_grad=True)
+    pred = planner.ptcl_model_rollout(torch.tensor(st).cuda(), torch.tensor(dn).cuda(), torch.zeros(1, 37, device="cuda"),
+                                      wm, acts)["model_rollout"]["state_pred"]
+    pred.sum().backward()
+    assert torch.isfinite(acts.grad).all()
 torch.cuda.synchronize()
 print("round-2 paths ok")
