@@ -223,7 +223,9 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
   constexpr unsigned FULL = 0xffffffffu;
   const int R = B * N;                                   // 32-bit: 64-bit div/mod is emulated
   const int nhw = (int)gridDim.x * (int)(blockDim.x >> 4);
-  if (l16 == 0) tc::mbar_init(bar, 1);
+  // arrivals per phase: lane 0's arrive.expect_tx (the C_e bulk copy) + one asynchronous arrive per lane (its cp.async
+  // pieces of the P_s rows have landed)
+  if (l16 == 0) tc::mbar_init(bar, 17);
   tc::mbar_init_fence();
   __syncthreads();
   uint32_t phase = 0;
@@ -253,13 +255,30 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
     const int cntw = max(cnt, __shfl_xor_sync(FULL, cnt, 16));
     // all rows of this receiver
     if (l16 == 0) {
-      tc::mbar_expect_tx(bar, (uint32_t)(cnt * EDGE_BYTES));
+      tc::mbar_expect_tx(bar, (uint32_t)(cnt * CE_ROW));
       if (cnt > 0) tc::bulk_g2s(slab_ce, reinterpret_cast<const unsigned char*>(Ce) + slot * CE_ROW, (uint32_t)(cnt * CE_ROW), bar);
     }
     __syncwarp();
-    if (l16 < cnt)
-      tc::bulk_g2s(slab_ps + l16 * PS_ROW, reinterpret_cast<const unsigned char*>(Ps) + ((long long)cur.b * N + mycol) * PS_ROW,
-                   PS_ROW, bar);
+    // the gathered P_s rows: 16-byte cp.async pieces, lane l16 takes pieces l16, l16 + 16, ... of the receiver's
+    // cnt x (PS_ROW / 16) pieces (a per-row bulk copy needs uniform registers, i.e. one serialised
+    // elect / broadcast / UBLKCP round per row: a quarter of the kernel's instructions and stall samples)
+    {
+      constexpr int CH = PS_ROW / 16;
+      const unsigned char* ps_base = reinterpret_cast<const unsigned char*>(Ps) + (long long)cur.b * N * PS_ROW;
+      const uint32_t slab_ps_u32 = tc::smem_u32(slab_ps);
+      const int npieces = cnt * CH;
+#pragma unroll 1
+      for (int i0 = 0; i0 < cntw * CH; i0 += 16) {          // warp-uniform trip count (the shuffle needs all lanes)
+        const int i = i0 + l16;
+        const int rowk = i / CH, ch = i - rowk * CH;
+        const int c = __shfl_sync(FULL, mycol, (threadIdx.x & 16) + min(rowk, KMAX - 1));
+        if (i < npieces)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slab_ps_u32 + (uint32_t)(rowk * PS_ROW + ch * 16)),
+                       "l"(ps_base + (long long)c * PS_ROW + ch * 16)
+                       : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+    }
     // prefetch for the next two receivers of this half-warp while the rows are on their way
     const int n1 = node + nhw;
     int mycol1 = 0;

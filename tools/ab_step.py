@@ -13,6 +13,11 @@ model = PropNetDiffDenModel(cfg, True).cuda()
 planner = PlannerGD(cfg, env)
 eng = RolloutEngine(model, planner, B, N, 2, use_graph=False)
 st, dn = synthetic.make_pile_batch(1, N, seed=0)
+if os.environ.get("AB_SORT"):          # particles in a spatially coherent index order (8 x 8 cells, row-major)
+    import numpy as np
+    p = st[0]
+    q = np.floor((p[:, :2] - p[:, :2].min(0)) / (np.ptp(p[:, :2], axis=0) + 1e-9) * 8).clip(0, 7).astype(int)
+    st = st[:, np.lexsort((q[:, 0], q[:, 1]))]
 eng.load_state(st, dn)
 eng.actions.copy_(torch.from_numpy(synthetic.random_actions(B, 2, seed=1)))
 lib = _lib.load()
