@@ -222,19 +222,20 @@ __global__ void k_g_mask(const float* __restrict__ g, int g_gather, const float*
                          int N, int Hp) {
   const int q4 = Hp / 4;
   if (EDGE) {
-    const int b = blockIdx.y;
-    const int ne = rowptr[(long long)b * (N + 1) + N];
-    const long long slot0 = (long long)b * KMAX * N;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long long)ne * q4;
-         idx += (long long)gridDim.x * blockDim.x) {
-      const int e = (int)(idx / q4), c = (int)(idx - (long long)e * q4) * 4;
-      const long long gr = g_gather ? (long long)b * N + row[slot0 + e] : slot0 + e;
-      float4 v = ld4(g + gr * Hp + c);
-      if (ymask) {
-        const float4 y = ld4(ymask + (slot0 + e) * Hp + c);
-        v.x = y.x > 0.f ? v.x : 0.f; v.y = y.y > 0.f ? v.y : 0.f; v.z = y.z > 0.f ? v.z : 0.f; v.w = y.w > 0.f ? v.w : 0.f;
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+      const int ne = rowptr[(long long)b * (N + 1) + N];
+      const long long slot0 = (long long)b * KMAX * N;
+      for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long long)ne * q4;
+           idx += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(idx / q4), c = (int)(idx - (long long)e * q4) * 4;
+        const long long gr = g_gather ? (long long)b * N + row[slot0 + e] : slot0 + e;
+        float4 v = ld4(g + gr * Hp + c);
+        if (ymask) {
+          const float4 y = ld4(ymask + (slot0 + e) * Hp + c);
+          v.x = y.x > 0.f ? v.x : 0.f; v.y = y.y > 0.f ? v.y : 0.f; v.z = y.z > 0.f ? v.z : 0.f; v.w = y.w > 0.f ? v.w : 0.f;
+        }
+        st4(Gm + (slot0 + e) * Hp + c, v);
       }
-      st4(Gm + (slot0 + e) * Hp + c, v);
     }
   } else {
     const long long total = (long long)B * N * q4;
@@ -424,15 +425,16 @@ __global__ void k_g_node_in(const float* __restrict__ s_delta, const float* __re
 __global__ void k_g_edge_in(const float* __restrict__ attr, const float* __restrict__ dens, const float* __restrict__ s_cur,
                             const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ row,
                             float* __restrict__ Y0, int B, int N) {
-  const int b = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= rowptr[(long long)b * (N + 1) + N]) return;
-  const long long slot = (long long)b * KMAX * N + e;
-  const int r = row[slot], c = col[slot];
-  const float* pr = s_cur + ((long long)b * N + r) * 3;
-  const float* ps = s_cur + ((long long)b * N + c) * 3;
-  st4(Y0 + slot * 8, make_float4(attr[(long long)b * N + r], attr[(long long)b * N + c], pr[0] - ps[0], pr[1] - ps[1]));
-  st4(Y0 + slot * 8 + 4, make_float4(pr[2] - ps[2], dens[b] / 5000.f, 0.f, 0.f));
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    if (e >= rowptr[(long long)b * (N + 1) + N]) continue;
+    const long long slot = (long long)b * KMAX * N + e;
+    const int r = row[slot], c = col[slot];
+    const float* pr = s_cur + ((long long)b * N + r) * 3;
+    const float* ps = s_cur + ((long long)b * N + c) * 3;
+    st4(Y0 + slot * 8, make_float4(attr[(long long)b * N + r], attr[(long long)b * N + c], pr[0] - ps[0], pr[1] - ps[1]));
+    st4(Y0 + slot * 8 + 4, make_float4(pr[2] - ps[2], dens[b] / 5000.f, 0.f, 0.f));
+  }
 }
 
 // out[i] (+)= base[i] + sum_{e in row i} A[e] + sum_{k in trow i} Bs[tedge k]   ([*, Hp] rows; one thread per float4)
@@ -536,27 +538,28 @@ __global__ void k_g_dx8(const float* __restrict__ Gm, const float* __restrict__ 
   extern __shared__ __align__(16) float w8_sh[];
   for (int i = threadIdx.x; i < Hp * 8; i += blockDim.x) w8_sh[i] = w8[i];
   __syncthreads();
-  long long r;
-  if (edge) {
-    const int b = blockIdx.y;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= rowptr[(long long)b * (N + 1) + N]) return;
-    r = (long long)b * KMAX * N + e;
-  } else {
-    r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= (long long)B * N) return;
-  }
-  float o8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int k = 0; k < Hp; k += 4) {
-    const float4 gv = ld4(Gm + r * Hp + k);
-    const float g4[4] = {gv.x, gv.y, gv.z, gv.w};
+  for (int b = blockIdx.y; b < (edge ? B : 1); b += gridDim.y) {
+    long long r;
+    if (edge) {
+      const int e = blockIdx.x * blockDim.x + threadIdx.x;
+      if (e >= rowptr[(long long)b * (N + 1) + N]) continue;
+      r = (long long)b * KMAX * N + e;
+    } else {
+      r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+      if (r >= (long long)B * N) continue;
+    }
+    float o8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < Hp; k += 4) {
+      const float4 gv = ld4(Gm + r * Hp + k);
+      const float g4[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o8[j] = fmaf(g4[u], w8_sh[(k + u) * 8 + j], o8[j]);
+        for (int j = 0; j < 8; ++j) o8[j] = fmaf(g4[u], w8_sh[(k + u) * 8 + j], o8[j]);
+    }
+    st4(dx8 + r * 8, make_float4(o8[0], o8[1], o8[2], o8[3]));
+    st4(dx8 + r * 8 + 4, make_float4(o8[4], o8[5], o8[6], o8[7]));
   }
-  st4(dx8 + r * 8, make_float4(o8[0], o8[1], o8[2], o8[3]));
-  st4(dx8 + r * 8 + 4, make_float4(o8[4], o8[5], o8[6], o8[7]));
 }
 
 // g_s_cur[i] = g_pred[i] + sum_{e in row i} dY0[e][2:5] - sum_{e: sender = i} dY0[e][2:5];  g_s_delta[i] = dX0[i][0:3]
@@ -716,7 +719,7 @@ int lin(LinArgs a, cudaStream_t st) {
 template <bool EDGE>
 int mask(const float* g, int g_gather, const float* ymask, const Csr& csr, float* Gm, int B, int N, int Hp, cudaStream_t st) {
   if (EDGE) {
-    const dim3 grid((unsigned)(((long long)KMAX * N * (Hp / 4) + 255) / 256), B);
+    const dim3 grid((unsigned)(((long long)KMAX * N * (Hp / 4) + 255) / 256), B < 65535 ? B : 65535);
     k_g_mask<true><<<grid, 256, 0, st>>>(g, g_gather, ymask, csr.rowptr, csr.row, Gm, B, N, Hp);
   } else {
     const long long total = (long long)B * N * (Hp / 4);
@@ -891,7 +894,7 @@ int launch_general_forward_relations(const float* wpack, int H, const float* att
   if ((ce = cudaMemcpyAsync(t.csr.col, col, sizeof(int) * E, cudaMemcpyDeviceToDevice, st))) return (int)ce;
   if ((ce = cudaMemcpyAsync(t.csr.row, row, sizeof(int) * E, cudaMemcpyDeviceToDevice, st))) return (int)ce;
   if ((e = launch_transpose_relations(t.csr, B, N, st))) return e;
-  const dim3 fgrid((KMAX * N + 255) / 256, B);
+  const dim3 fgrid((KMAX * N + 255) / 256, B < 65535 ? B : 65535);
   k_g_edge_in<<<fgrid, 256, 0, st>>>(attr, dens, s_cur, t.csr.rowptr, t.csr.col, t.csr.row, t.Y0, B, N);
   PILE_CHECK_LAUNCH();
   return forward_body(wpack, Hp, attr, dens, s_cur, s_delta, B, N, t, s_pred, st);
@@ -1008,7 +1011,7 @@ int launch_general_backward(const float* wpack, int H, const float* dens, void* 
       if ((e = wgrad<true>(B, N, nb, H, t.csr, s.gmE, 1, src, nullptr, nullptr, s.partial, f, st))) return e;
     }
     if ((e = mask<true>(s.dZr, 0, t.R1, t.csr, s.gmE, B, N, Hp, st))) return e;
-    const dim3 egrid((KMAX * N + 127) / 128, B);
+    const dim3 egrid((KMAX * N + 127) / 128, B < 65535 ? B : 65535);
     k_g_dx8<<<egrid, 128, Hp * 8 * sizeof(float), st>>>(s.gmE, W(W_RE0), t.csr.rowptr, s.dY0, B, N, Hp, 1);
     PILE_CHECK_LAUNCH();
     if (wg) {
