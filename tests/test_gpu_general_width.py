@@ -211,6 +211,36 @@ def test_gd_planner_width150_matches_oracle_adam_loop():
     assert res["observation_sequence"].shape == (T, N, 3)
 
 
+def test_mppi_planner_width150_matches_oracle_composition():
+    """trajectory_optimization_mppi with a width-150 model (RolloutEngine on the general-width engine) == the oracle
+    composition with the same numpy seed (planners.py:69-190, 302-370, 549-561)."""
+    cfg, env = config_with_width(150), synthetic.FakeEnv()
+    torch.manual_seed(6)
+    model = P.PropNetDiffDenModel(cfg, True).to(DEV)
+    planner = P.PlannerGD(cfg, env)
+    N, T, NS, iters = 50, 3, 32, 2
+    st, dn = synthetic.make_pile_batch(1, N, seed=12)
+    goal = synthetic.make_goal("bar")
+    mean0 = synthetic.random_actions(1, T, seed=12, lim=3.0)[0]
+    got = planner.trajectory_optimization_mppi(st, dn, np.zeros((1, N), np.float32), goal, model, mean0, n_sample=NS,
+                                               n_update_iter=iters, seed=4)
+    W = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    coords = np.argwhere(goal < 0.5)[:, ::-1].astype(np.float32)
+    coor, _ = synthetic.fps_np(coords, min(5 * N, len(coords)), 0)
+    np.random.seed(4)
+    mean = np.asarray(mean0, dtype=np.float64).reshape(T, 1, 4)
+    for _ in range(iters):
+        sampled = O.sample_action_sequences(mean, NS, cfg["mpc"]["sigma"] * synthetic.GLOBAL_SCALE / 12.0,
+                                            cfg["mpc"]["mppi"]["beta_filter"], env.cvx_region)
+        with torch.no_grad():
+            pred = O.rollout(W, 0.08, env.get_cam_extrinsics(), synthetic.GLOBAL_SCALE, torch.tensor(st), torch.tensor(dn),
+                             torch.zeros(1, N), torch.tensor(sampled[:, :, 0, :], dtype=torch.float))
+            rew = O.reward_ptcl(pred[:, -1], torch.from_numpy(goal), env.get_cam_params(), torch.from_numpy(coor))
+        mean = O.mppi_optimize_action(sampled, rew.numpy()[:, None].astype(np.float64), cfg["mpc"]["mppi"]["reward_weight"])
+    np.testing.assert_allclose(got["reward"], rew.numpy(), rtol=2e-4)
+    np.testing.assert_allclose(got["action_sequence"], mean[:, 0, :], rtol=0, atol=1e-4)
+
+
 def test_width_limits():
     with pytest.raises(P._lib.PileLibraryError):
         P.PropNetDiffDenModel(config_with_width(257), True)
