@@ -280,8 +280,39 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
     const float4 pi = pos[ic];
     const float xi = pi.x, yi = pi.y, zi = pi.z;
     const uint64_t X2 = pack2(xi, xi), Y2 = pack2(yi, yi), Z2 = pack2(zi, zi);
+    // Warm start of the admission bound from whatever the output lists hold on entry -- in a rollout the relations of
+    // the step before, in the planner's loop those of the iteration before: ANY ten distinct candidates are at most
+    // D = max of their current distances away, so the tenth smallest distance is <= D and no candidate with d > D can be
+    // selected.  Candidates with d == D still can (ties go to the lower index), hence the bound is the next float above
+    // D.  The selected set is unchanged; the sorted insertion runs ~10 + few times per receiver instead of
+    // ~10 (1 + ln(in-radius / 10)) times.  The old list is validated (ten strictly ascending indices in range), so
+    // stale or uninitialised memory is harmless; a sample's old lists are read here, its new ones written after the
+    // barrier below by the same CTA.
+    float lim0 = thr;
+    if (active) {
+      const int* prp = rowptr + (size_t)b * (N + 1) + i;
+      const int plo = prp[0];
+      if (prp[1] - plo == KMAX && plo >= 0 && plo <= KMAX * N - KMAX) {
+        const int* pc = col + (size_t)b * KMAX * N + plo;
+        int c[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) c[k] = pc[k];
+        bool ok = c[0] >= 0 && c[KMAX - 1] < N;
+#pragma unroll
+        for (int k = 1; k < KMAX; ++k) ok = ok && c[k - 1] < c[k];
+        if (ok) {
+          float D = 0.f;
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            const float4 pj = pos[c[k]];
+            D = fmaxf(D, sqdist_rn(xi, yi, zi, pj.x, pj.y, pj.z));
+          }
+          lim0 = fminf(thr, __int_as_float(__float_as_int(D) + 1));
+        }
+      }
+    }
     // admission bound; -1 keeps lanes without a receiver out (d >= 0)
-    float lim = active ? thr : -1.f;
+    float lim = active ? lim0 : -1.f;
     for (int jb = 0; jb < NP; jb += NBR_BLOCK) {
       unsigned m = 0;
 #pragma unroll
@@ -313,7 +344,7 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
               bd[s] = nd; id[s] = ni;
             }
             if (d < bd[0]) { bd[0] = d; id[0] = j; }
-            lim = fminf(thr, bd[KMAX - 1]);
+            lim = fminf(lim0, bd[KMAX - 1]);
           }
         }
       }

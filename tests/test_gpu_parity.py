@@ -118,6 +118,52 @@ def test_sender_major_transpose(N, B):
         assert np.array_equal(np.diff(trp[b]), np.bincount(col[b, :ne], minlength=N))
 
 
+@pytest.mark.parametrize("garbage", ["valid_lists", "duplicates", "out_of_range", "negative_offsets", "stale_step"])
+def test_relation_search_warm_start_never_changes_the_result(garbage):
+    """The search takes its first admission bound from whatever the output lists hold on entry (the relations of the
+    rollout step / planner iteration before).  Any ten distinct in-range candidates give a valid bound; anything else must
+    be ignored: the result is the cold-start result (empty lists on entry) whatever the buffers contained -- including
+    sample 0, where 15 coincident points tie at the tenth place of many receivers (lower index wins; torch.topk's own
+    choice among such ties is unspecified, so only the tie-free samples are also compared with the oracle)."""
+    from dyn_res_pile_manip_b200 import _lib
+    B, N = 3, 77
+    rng = np.random.RandomState(5)
+    s = rng.uniform(-.12, .12, (B, N, 3)).astype(np.float32)
+    s[0, 5:19] = s[0, 4]                                     # coincident points: ties at the tenth place
+    want = O.adjacency(torch.tensor(s), torch.zeros(B, N, 3), 0.08)
+    rowptr = torch.arange(N + 1, dtype=torch.int32, device=DEV).repeat(B, 1) * 10
+    col = torch.zeros(B, 10 * N, dtype=torch.int32, device=DEV)
+    if garbage == "valid_lists":          # ten distinct random candidates per receiver, ascending: a (loose) valid bound
+        col = torch.tensor(np.stack([np.concatenate([np.sort(rng.choice(N, 10, replace=False)) for _ in range(N)])
+                                     for _ in range(B)]).astype(np.int32), device=DEV)
+    elif garbage == "duplicates":         # in range but not distinct: would give a bound that is too tight
+        col = torch.tensor(rng.randint(0, 3, (B, 10 * N)).astype(np.int32), device=DEV)
+    elif garbage == "out_of_range":
+        col = torch.tensor(rng.randint(-5 * N, 5 * N, (B, 10 * N)).astype(np.int32), device=DEV)
+    elif garbage == "negative_offsets":
+        rowptr = torch.tensor(rng.randint(-2 ** 31, 2 ** 31 - 1, (B, N + 1), dtype=np.int64).astype(np.int32), device=DEV)
+    elif garbage == "stale_step":         # the lists of a different configuration of the same pile
+        other = ops.build_relations(cuda(s[:, ::-1].copy()), cuda(np.zeros_like(s)), 0.08)
+        rowptr, col = other.rowptr.clone(), other.col.clone()
+    row = torch.zeros(B, 10 * N, dtype=torch.int32, device=DEV)
+    sc, sd = cuda(s), cuda(np.zeros_like(s))
+    _lib.check(_lib.load().pile_build_relations(_lib.ptr(sc), _lib.ptr(sd), None, B, N, 0.08, _lib.ptr(rowptr), _lib.ptr(col),
+                                                _lib.ptr(row), None, None, None, ops._stream()), "pile_build_relations")
+    got = ops.Relations(rowptr, col, row).edge_sets()
+    cold_rp = torch.zeros(B, N + 1, dtype=torch.int32, device=DEV)          # every old list empty: no warm start
+    cold_col, cold_row = torch.zeros_like(col), torch.zeros_like(row)
+    _lib.check(_lib.load().pile_build_relations(_lib.ptr(sc), _lib.ptr(sd), None, B, N, 0.08, _lib.ptr(cold_rp),
+                                                _lib.ptr(cold_col), _lib.ptr(cold_row), None, None, None, ops._stream()),
+               "pile_build_relations")
+    cold = ops.Relations(cold_rp, cold_col, cold_row).edge_sets()
+    for b in range(B):
+        assert np.array_equal(got[b], cold[b]), (garbage, b)
+        if b > 0:
+            assert np.array_equal(got[b], np.argwhere(want[b].numpy() > 0)), (garbage, b)
+    inside = got[0][got[0][:, 0] == 11, 1]                   # a receiver inside the coincident group keeps the lowest ten
+    assert list(inside) == list(range(4, 14))
+
+
 def test_relations_duplicate_points_lowest_index_wins():
     # 14 coincident particles: every distance ties at 0 -> the 10 lowest sender indices must be kept
     s = np.zeros((1, 14, 3), dtype=np.float32)
