@@ -180,24 +180,28 @@ __device__ __forceinline__ void stage_flush(const uint8_t* stage, int t, float* 
   }
 }
 // ---- packed C_e rows (tensor engine 2) ------------------------------------------------------------------
-// k_edge_agg re-reads C_e once per propagation step and sits on the HBM roofline, so the tensor engine stores the
-// rows as 24-bit words (fp32 rounded to 15 explicit mantissa bits: relative error <= 2^-16, the same as the bf16
-// hi/lo operands of the products that made them): per row 64 x 16-bit upper halves (128 bytes) followed by
-// 64 x 8-bit third bytes (64 bytes) = 192 bytes instead of 256.
+// k_edge_agg re-reads C_e once per propagation step, so the tensor engine stores the rows as 24-bit words: per row
+// 64 x 16-bit upper halves (128 bytes) followed by 64 x 8-bit third bytes (64 bytes) = 192 bytes instead of 256.
+// The reader rebuilds a float with ONE byte permute per value and no mask: [upper half | b | b], i.e. the low 16
+// mantissa bits become 257 * b.  The writer therefore stores b = round(low16 / 257) (multiply-high by 2^24 / 257):
+// |257 b - low16| <= 128.5, a relative error <= 2^-16 like the bf16 hi/lo operands of the products that made the
+// row -- the same bound as rounding to 24 bits, without the reader's AND.
 constexpr int CE_PACKED_ROW = 192;
+__device__ __forceinline__ uint32_t third_byte_scaled(float x) {          // byte 3 of the result = b
+  return (__float_as_uint(x) & 0xffffu) * 65281u + 0x800000u;              // <= 65535 * 65281 + 2^23 < 2^32
+}
 __device__ __forceinline__ void pack24(const float4& v, uint2& hi, uint32_t& lo) {
-  const uint32_t a = __float_as_uint(v.x) + 0x80u, b = __float_as_uint(v.y) + 0x80u;
-  const uint32_t c = __float_as_uint(v.z) + 0x80u, d = __float_as_uint(v.w) + 0x80u;
-  hi.x = __byte_perm(a, b, 0x7632);                                         // [a.2 a.3 b.2 b.3]
-  hi.y = __byte_perm(c, d, 0x7632);
-  lo = __byte_perm(__byte_perm(a, b, 0x0051), __byte_perm(c, d, 0x0051), 0x5410);   // [a.1 b.1 c.1 d.1]
+  hi.x = __byte_perm(__float_as_uint(v.x), __float_as_uint(v.y), 0x7632);                  // [x.2 x.3 y.2 y.3]
+  hi.y = __byte_perm(__float_as_uint(v.z), __float_as_uint(v.w), 0x7632);
+  lo = __byte_perm(__byte_perm(third_byte_scaled(v.x), third_byte_scaled(v.y), 0x0073),
+                   __byte_perm(third_byte_scaled(v.z), third_byte_scaled(v.w), 0x0073), 0x5410);   // [bx by bz bw]
 }
 __device__ __forceinline__ float4 unpack24(const uint2& hi, uint32_t lo) {
   float4 v;
-  v.x = __uint_as_float(__byte_perm(hi.x, lo, 0x1044) & 0xffffff00u);       // [junk lo.0 hi.0 hi.1] & mask
-  v.y = __uint_as_float(__byte_perm(hi.x, lo, 0x3254) & 0xffffff00u);
-  v.z = __uint_as_float(__byte_perm(hi.y, lo, 0x1064) & 0xffffff00u);
-  v.w = __uint_as_float(__byte_perm(hi.y, lo, 0x3274) & 0xffffff00u);
+  v.x = __uint_as_float(__byte_perm(hi.x, lo, 0x1044));       // [lo.0 lo.0 hi.0 hi.1]
+  v.y = __uint_as_float(__byte_perm(hi.x, lo, 0x3255));
+  v.z = __uint_as_float(__byte_perm(hi.y, lo, 0x1066));
+  v.w = __uint_as_float(__byte_perm(hi.y, lo, 0x3277));
   return v;
 }
 // all 256 threads of the group: staging tile -> packed rows [row0, row_end) (row_end - row0 <= 128)
