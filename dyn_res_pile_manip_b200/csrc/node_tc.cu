@@ -186,6 +186,24 @@ k_node_encode_tc(const float* __restrict__ wpack, const float* __restrict__ attr
 // ------------------------------------------------------------------------------------------------
 // receiver-segmented sum of the relation effects (memory-bound; no weights, high occupancy)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 add2x2(const float4& a, const float4& b) {
+  float4 r;
+  asm("{\n\t"
+      ".reg .b64 a01, a23, b01, b23;\n\t"
+      "mov.b64 a01, {%4, %5};\n\t"
+      "mov.b64 a23, {%6, %7};\n\t"
+      "mov.b64 b01, {%8, %9};\n\t"
+      "mov.b64 b23, {%10, %11};\n\t"
+      "add.rn.f32x2 a01, a01, b01;\n\t"
+      "add.rn.f32x2 a23, a23, b23;\n\t"
+      "mov.b64 {%0, %1}, a01;\n\t"
+      "mov.b64 {%2, %3}, a23;\n\t"
+      "}\n"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+      : "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w));
+  return r;
+}
+
 constexpr int AGG_THREADS = 256;
 template <bool PACKED>
 __host__ __device__ constexpr int agg_edge_bytes(bool packed_ps) {      // C_e row + P_s row
@@ -310,8 +328,9 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
           ps = unpack24(*reinterpret_cast<const uint2*>(pe + l16 * 8), *reinterpret_cast<const uint32_t*>(pe + 128 + l16 * 4));
         else
           ps = *reinterpret_cast<const float4*>(pe + l16 * 16);
-        v = make_float4(ce.x + pr.x + ps.x, ce.y + pr.y + ps.y, ce.z + pr.z + ps.z, ce.w + pr.w + ps.w);
-        sum.x += fmaxf(v.x, 0.f); sum.y += fmaxf(v.y, 0.f); sum.z += fmaxf(v.z, 0.f); sum.w += fmaxf(v.w, 0.f);
+        // packed fp32x2 adds (sm_100 FADD2: two IEEE round-to-nearest sums per instruction, same values as scalar adds)
+        v = add2x2(add2x2(ce, pr), ps);
+        sum = add2x2(sum, make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f)));
       }
       if (RECORD) {          // sign bits of 8 channels per byte: even lanes collect their right neighbour's nibble
         const unsigned m4 = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
