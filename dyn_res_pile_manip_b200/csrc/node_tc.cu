@@ -247,15 +247,15 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
   tc::mbar_init_fence();
   __syncthreads();
   uint32_t phase = 0;
-  struct Seg { int b, e_lo, cnt; };
+  struct Seg { int b, e_lo, e_hi; };          // e_hi stays raw: its subtraction would wait for the prefetching load
   auto load_seg = [&](int nd) {
     Seg s;
-    s.b = 0; s.e_lo = 0; s.cnt = 0;
+    s.b = 0; s.e_lo = 0; s.e_hi = 0;
     if (nd < R) {
       s.b = nd / N;
       const int* rp = rowptr + (long long)s.b * (N + 1) + (nd - s.b * N);
       s.e_lo = __ldg(rp);
-      s.cnt = __ldg(rp + 1) - s.e_lo;
+      s.e_hi = __ldg(rp + 1);
     }
     return s;
   };
@@ -264,11 +264,11 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
   int mycol = 0;
   float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
   if (node < R) {
-    if (l16 < cur.cnt) mycol = __ldg(col + (long long)cur.b * KMAX * N + cur.e_lo + l16);
+    if (l16 < cur.e_hi - cur.e_lo) mycol = __ldg(col + (long long)cur.b * KMAX * N + cur.e_lo + l16);
     pr = ld4(Pr + (long long)node * H + 4 * l16);
   }
   while (__any_sync(FULL, node < R)) {
-    const int cnt = cur.cnt;
+    const int cnt = cur.e_hi - cur.e_lo;
     const long long slot = (long long)cur.b * KMAX * N + cur.e_lo;
     const int cntw = max(cnt, __shfl_xor_sync(FULL, cnt, 16));
     // all rows of this receiver
@@ -277,22 +277,22 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
       if (cnt > 0) tc::bulk_g2s(slab_ce, reinterpret_cast<const unsigned char*>(Ce) + slot * CE_ROW, (uint32_t)(cnt * CE_ROW), bar);
     }
     __syncwarp();
-    // the gathered P_s rows: 16-byte cp.async pieces, lane l16 takes pieces l16, l16 + 16, ... of the receiver's
-    // cnt x (PS_ROW / 16) pieces (a per-row bulk copy needs uniform registers, i.e. one serialised
-    // elect / broadcast / UBLKCP round per row: a quarter of the kernel's instructions and stall samples)
+    // the gathered P_s rows as 16-byte cp.async pieces: lane l16 (< PS_ROW / 16) takes piece l16 of every row, so the
+    // only per-row work is the sender's index from the lane that holds it and one 64-bit multiply-add (a per-row bulk
+    // copy needs uniform registers, i.e. one serialised elect / broadcast / UBLKCP round per row: a quarter of the
+    // kernel's instructions and stall samples)
     {
       constexpr int CH = PS_ROW / 16;
-      const unsigned char* ps_base = reinterpret_cast<const unsigned char*>(Ps) + (long long)cur.b * N * PS_ROW;
-      const uint32_t slab_ps_u32 = tc::smem_u32(slab_ps);
-      const int npieces = cnt * CH;
-#pragma unroll 1
-      for (int i0 = 0; i0 < cntw * CH; i0 += 16) {          // warp-uniform trip count (the shuffle needs all lanes)
-        const int i = i0 + l16;
-        const int rowk = i / CH, ch = i - rowk * CH;
-        const int c = __shfl_sync(FULL, mycol, (threadIdx.x & 16) + min(rowk, KMAX - 1));
-        if (i < npieces)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slab_ps_u32 + (uint32_t)(rowk * PS_ROW + ch * 16)),
-                       "l"(ps_base + (long long)c * PS_ROW + ch * 16)
+      const unsigned char* ps_lane = reinterpret_cast<const unsigned char*>(Ps) + (long long)cur.b * N * PS_ROW + l16 * 16;
+      const uint32_t slab_lane = tc::smem_u32(slab_ps) + (uint32_t)(l16 * 16);
+      const int src_lane = threadIdx.x & 16;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k >= cntw) break;          // warp-uniform (the shuffle needs all lanes)
+        const int c = __shfl_sync(FULL, mycol, src_lane + k);
+        if (k < cnt && l16 < CH)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slab_lane + (uint32_t)(k * PS_ROW)),
+                       "l"(ps_lane + (long long)c * PS_ROW)
                        : "memory");
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
@@ -302,7 +302,7 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
     int mycol1 = 0;
     float4 pr1 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n1 < R) {
-      if (l16 < nxt.cnt) mycol1 = __ldg(col + (long long)nxt.b * KMAX * N + nxt.e_lo + l16);
+      if (l16 < nxt.e_hi - nxt.e_lo) mycol1 = __ldg(col + (long long)nxt.b * KMAX * N + nxt.e_lo + l16);
       pr1 = ld4(Pr + (long long)n1 * H + 4 * l16);
     }
     const Seg nn = load_seg(n1 + nhw);
