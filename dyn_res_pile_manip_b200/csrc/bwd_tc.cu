@@ -77,11 +77,34 @@ k_bwd_edge_tc(const float* __restrict__ wpack, const int* __restrict__ rowptr, c
   const int ntiles = B * tps;
   tc::mbar_wait(&S.w_bar, 0);
 
-  for (int tile = (int)blockIdx.x * TC_GROUPS + g; tile < ntiles; tile += (int)gridDim.x * TC_GROUPS) {
+  // The chain  row index -> rows of g_agg  is the kernel's longest wait (the ncu source page shows half of all stall
+  // samples on it), so the receiver index and the three relation-mask words of a group's NEXT tile are fetched while
+  // its current tile runs through the layers.
+  const uint8_t* mp[3] = {me0, me1, me2};
+  struct Pre { int node; uint32_t bits[3]; int ne; };
+  auto prefetch = [&](int tile) {
+    Pre p;
+    p.node = 0; p.bits[0] = p.bits[1] = p.bits[2] = 0u; p.ne = 0;
+    if (tile < ntiles) {
+      const int b = tile / tps;
+      const int e0 = (tile - b * tps) * TILE;
+      p.ne = rowptr[(long long)b * (N + 1) + N];
+      if (e0 + r < p.ne) {
+        const long long slot = (long long)b * KMAX * N + e0 + r;
+        p.node = b * N + row[slot];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) p.bits[q] = *reinterpret_cast<const uint32_t*>(mp[q] + slot * 8 + half * 4);
+      }
+    }
+    return p;
+  };
+  const int tstride = (int)gridDim.x * TC_GROUPS;
+  Pre cur = prefetch((int)blockIdx.x * TC_GROUPS + g);
+  for (int tile = (int)blockIdx.x * TC_GROUPS + g; tile < ntiles; tile += tstride) {
     const int b = tile / tps;
     const int e0 = (tile - b * tps) * TILE;
-    const int ne = rowptr[(long long)b * (N + 1) + N];
-    if (e0 >= ne) continue;                                // group-uniform
+    const int ne = cur.ne;
+    if (e0 >= ne) { cur = prefetch(tile + tstride); continue; }          // group-uniform
     const int nrows = min(TILE, ne - e0);
     const long long slot0 = (long long)b * KMAX * N + e0;
     const bool valid = r < nrows;
@@ -95,12 +118,11 @@ k_bwd_edge_tc(const float* __restrict__ wpack, const int* __restrict__ rowptr, c
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
       if (valid) {
-        const long long node = (long long)b * N + row[slot0 + r];
+        const long long node = cur.node;
         const float* gp[3] = {ga0, ga1, ga2};
-        const uint8_t* mp[3] = {me0, me1, me2};
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
-          const uint32_t bits = *reinterpret_cast<const uint32_t*>(mp[p] + mrow);
+          const uint32_t bits = cur.bits[p];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float v[8];
@@ -113,13 +135,15 @@ k_bwd_edge_tc(const float* __restrict__ wpack, const int* __restrict__ rowptr, c
 #pragma unroll
       for (int j = 0; j < 4; ++j) store_chunk(a_hi, a_lo, row_off + (half * 4 + j) * A_LBO, acc[j]);
     }
+    cur = prefetch(tile + tstride);
     // three 64x64 dgrad layers, each followed by the recorded ReLU mask of the layer below
 #pragma unroll 1
     for (int layer = 0; layer < 3; ++layer) {
       const uint32_t wl = w + layer * BE_W64;
-      run_gemm(c, [&](uint32_t el) { issue_gemm<64, 4, false>(el, c.tmem_d, c.a_hi, c.a_lo, 0, 0, 0, wl, wl + BE_W64 / 2); });
+      // the recorded ReLU bits of the layer below are fetched before the GEMM is handed over: the load overlaps the MMAs
       const uint8_t* mk = layer == 0 ? m_re2 : (layer == 1 ? m_re1 : m_re0);
       const uint32_t bits = valid ? *reinterpret_cast<const uint32_t*>(mk + mrow) : 0u;
+      run_gemm(c, [&](uint32_t el) { issue_gemm<64, 4, false>(el, c.tmem_d, c.a_hi, c.a_lo, 0, 0, 0, wl, wl + BE_W64 / 2); });
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         float v[16];
