@@ -283,7 +283,10 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
     // kernel's instructions and stall samples)
     {
       constexpr int CH = PS_ROW / 16;
-      const unsigned char* ps_lane = reinterpret_cast<const unsigned char*>(Ps) + (long long)cur.b * N * PS_ROW + l16 * 16;
+      // 32-bit byte offsets into P_s (the launcher checks rows * 256 < 2^32): one multiply-add per row instead of a
+      // 64-bit multiply chain
+      const unsigned char* ps_bytes = reinterpret_cast<const unsigned char*>(Ps);
+      const uint32_t row0_off = (uint32_t)(cur.b * N) * (uint32_t)PS_ROW + (uint32_t)(l16 * 16);
       const uint32_t slab_lane = tc::smem_u32(slab_ps) + (uint32_t)(l16 * 16);
       const int src_lane = threadIdx.x & 16;
 #pragma unroll
@@ -292,7 +295,7 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
         const int c = __shfl_sync(FULL, mycol, src_lane + k);
         if (k < cnt && l16 < CH)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slab_lane + (uint32_t)(k * PS_ROW)),
-                       "l"(ps_lane + (long long)c * PS_ROW)
+                       "l"(ps_bytes + (row0_off + (uint32_t)c * (uint32_t)PS_ROW))
                        : "memory");
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
@@ -526,6 +529,7 @@ int launch_propagate_tc(const float* wpack, const Csr& csr, const StepScratch& w
   const int in = p & 1, out = in ^ 1;
   const long long R = (long long)B * N;
   const long long ntiles = (R + TILE - 1) / TILE;
+  if (R * 256 >= (1ll << 32)) return (int)cudaErrorInvalidValue;          // 32-bit byte offsets in k_edge_agg
   const int agg_blocks = (int)((R + 15) / 16 < 3 * NSM ? (R + 15) / 16 : 3 * NSM);      // 3 resident blocks per SM: one wave
   // tensor engine 2 (edge_tmem.cu) writes packed C_e rows, engine 1 (edge_tc.cu) plain fp32 rows
   const bool packed = g_use_tensor_cores == 2;
