@@ -15,7 +15,7 @@ import torch
 
 from . import _lib, ops
 from .propnet import PropNetDiffDenModel
-from .rewards import GoalCache, config_reward_ptcl
+from .rewards import GoalCache, config_reward_ptcl, goal_content_hash
 from .synthetic import fps_np
 
 DEBUG = False
@@ -417,7 +417,8 @@ class PlannerGD(Planner):
         state_cur_tensor = torch.tensor(state_cur_np, device=device, dtype=torch.float)
         attr_cur_tensor = torch.tensor(np.concatenate(attr_cur_list, axis=0), device=device, dtype=torch.float)
         obs_goal_tensor = torch.tensor(obs_goal, device=device, dtype=torch.float)
-        obs_goal_coor_tensor = self.goal_coordinates(obs_goal, device)
+        goal_hash = goal_content_hash(obs_goal)          # one pass over the image for both goal caches
+        obs_goal_coor_tensor = self.goal_coordinates(obs_goal, device, goal_hash)
         state_param_tensor = torch.from_numpy(np.concatenate(state_param_list, axis=0)).to(device=device, dtype=torch.float)
 
         n_act = act_seq.shape[0]
@@ -457,7 +458,7 @@ class PlannerGD(Planner):
                     self._gd_loops.popitem(last=False)
                 loop = _GDLoop(key, net, device)
             self._gd_loops[key] = loop
-            goal_img = self.goals.shaped_np(obs_goal, obs_goal_tensor)
+            goal_img = self.goals.shaped_np(obs_goal, obs_goal_tensor, goal_hash)
             inputs = (state_cur_tensor.repeat(traj_num, 1, 1), state_param_tensor.repeat(traj_num),
                       attr_cur_tensor.repeat(traj_num, 1), act_seqs_tensor.view(rows, T, 4), goal_img,
                       obs_goal_coor_tensor)
@@ -566,11 +567,11 @@ class PlannerGD(Planner):
         return results
 
     # ---- helpers -----------------------------------------------------------------------------------------
-    def goal_coordinates(self, obs_goal, device):
+    def goal_coordinates(self, obs_goal, device, content_hash=None):
         """FPS-thinned (col,row) pixels of the goal region (planners.py:620-624).  On a CUDA device the
         sampling runs in libpilegnn (`pile_fps`, same picks as utils.fps_np); results are cached per goal."""
         g = np.asarray(obs_goal)
-        key = (g.shape, self.particle_num, str(device), hash(g.tobytes()))
+        key = (g.shape, self.particle_num, str(device), goal_content_hash(g) if content_hash is None else content_hash)
         hit = self._goal_coor_cache.get(key)
         if hit is not None:
             return hit

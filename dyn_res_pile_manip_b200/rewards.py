@@ -39,16 +39,23 @@ class GoalCache:
         self._np_key = None
         return self._img
 
-    def shaped_np(self, goal_np, goal_tensor):
+    def shaped_np(self, goal_np, goal_tensor, content_hash=None):
         """Planner entry: the goal arrives as a numpy array, so the key is a hash of its bytes (as
-        PlannerGD.goal_coordinates does); `goal_tensor` is the same image already on the device."""
+        PlannerGD.goal_coordinates does; `content_hash` = goal_content_hash(goal_np) when the caller already has it);
+        `goal_tensor` is the same image already on the device."""
         g = np.ascontiguousarray(goal_np)
-        key = (g.shape, str(g.dtype), str(goal_tensor.device), hash(g.tobytes()))
+        key = (g.shape, str(g.dtype), str(goal_tensor.device), goal_content_hash(g) if content_hash is None else content_hash)
         if self._img is None or key != self._np_key:
             self._img = shape_goal_image(goal_tensor)
             self._np_key = key
             self._ref, self._version, self._copy = goal_tensor, goal_tensor._version, goal_tensor.detach().clone()
         return self._img
+
+
+def goal_content_hash(goal_np):
+    """Hash of the goal image's bytes: the cache key of everything derived from a goal (0.45 ms for 720 x 720 floats, so a
+    planner call computes it once and hands it to both users)."""
+    return hash(np.ascontiguousarray(goal_np).tobytes())
 
 
 def shape_goal_image(goal):
