@@ -204,6 +204,12 @@ __device__ __forceinline__ float4 add2x2(const float4& a, const float4& b) {
   return r;
 }
 
+// A/B switch (tools/ab_step.py with a variant library): -DPILE_PS_FP32 keeps the gathered P_s rows in fp32 on inference runs too
+#ifdef PILE_PS_FP32
+constexpr bool PS_PACK_OK = false;
+#else
+constexpr bool PS_PACK_OK = true;
+#endif
 constexpr int AGG_THREADS = 256;
 template <bool PACKED>
 __host__ __device__ constexpr int agg_edge_bytes(bool packed_ps) {      // C_e row + P_s row
@@ -229,7 +235,7 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
   __shared__ uint64_t bars[AGG_THREADS / 16];
   // P_s rows are packed like C_e when no tape is recorded; with a tape (gradient runs) they stay fp32, because the
   // extra rounding in front of the ReLU flips sign bits and triples the gradient noise (5.9e-3 vs 2e-3 relative)
-  constexpr bool PS_PACKED = PACKED && !RECORD;
+  constexpr bool PS_PACKED = PACKED && !RECORD && PS_PACK_OK;
   constexpr int CE_ROW = PACKED ? CE_PACKED_ROW : H * 4;
   constexpr int PS_ROW = PS_PACKED ? CE_PACKED_ROW : H * 4;
   constexpr int EDGE_BYTES = agg_edge_bytes<PACKED>(PS_PACKED);
@@ -515,10 +521,10 @@ int launch_node_encode_tc(const float* wpack, const float* attr, const float* de
   const long long ntiles = ((long long)B * N + TILE - 1) / TILE;
   if (mk)
     k_node_encode_tc<true><<<tc_grid(ntiles), TC_THREADS, sizeof(NodeEncSmemTc), st>>>(
-        wpack, attr, dens, s_delta, mk->pe0, mk->pe1, ws.Cp, ws.eff, ws.Pr[0], ws.Ps[0], B, N, g_use_tensor_cores == 2 && mk == nullptr);
+        wpack, attr, dens, s_delta, mk->pe0, mk->pe1, ws.Cp, ws.eff, ws.Pr[0], ws.Ps[0], B, N, PS_PACK_OK && g_use_tensor_cores == 2 && mk == nullptr);
   else
     k_node_encode_tc<false><<<tc_grid(ntiles), TC_THREADS, sizeof(NodeEncSmemTc), st>>>(
-        wpack, attr, dens, s_delta, nullptr, nullptr, ws.Cp, ws.eff, ws.Pr[0], ws.Ps[0], B, N, g_use_tensor_cores == 2 && mk == nullptr);
+        wpack, attr, dens, s_delta, nullptr, nullptr, ws.Cp, ws.eff, ws.Pr[0], ws.Ps[0], B, N, PS_PACK_OK && g_use_tensor_cores == 2 && mk == nullptr);
   PILE_CHECK_LAUNCH();
   return 0;
 }
@@ -536,7 +542,7 @@ int launch_propagate_tc(const float* wpack, const Csr& csr, const StepScratch& w
   uint8_t* me = mk ? mk->edge[p] : nullptr;
   auto agg_kernel = mk ? (packed ? k_edge_agg<true, true> : k_edge_agg<true, false>)
                        : (packed ? k_edge_agg<false, true> : k_edge_agg<false, false>);
-  const int agg_smem = packed ? agg_smem_bytes<true>(mk == nullptr) : agg_smem_bytes<false>(false);
+  const int agg_smem = packed ? agg_smem_bytes<true>(PS_PACK_OK && mk == nullptr) : agg_smem_bytes<false>(false);
   agg_kernel<<<agg_blocks, AGG_THREADS, agg_smem, st>>>(csr.rowptr, csr.col, ws.Ce, ws.Pr[in], ws.Ps[in], me, ws.agg, B, N);
   PILE_CHECK_LAUNCH();
   if (mid) cudaEventRecord(mid, st);
@@ -545,17 +551,17 @@ int launch_propagate_tc(const float* wpack, const Csr& csr, const StepScratch& w
   if (p < PSTEP - 1) {
     if (mk)
       k_node_update_tc<false, true><<<grid, TC_THREADS, sm, st>>>(wpack, ws.agg, ws.Cp, ws.eff, ws.Pr[out], ws.Ps[out],
-                                                                  mk->eff[p], nullptr, s_cur, s_stride, s_out, o_stride, B, N, packed && mk == nullptr);
+                                                                  mk->eff[p], nullptr, s_cur, s_stride, s_out, o_stride, B, N, PS_PACK_OK && packed && mk == nullptr);
     else
       k_node_update_tc<false, false><<<grid, TC_THREADS, sm, st>>>(wpack, ws.agg, ws.Cp, ws.eff, ws.Pr[out], ws.Ps[out],
-                                                                   nullptr, nullptr, s_cur, s_stride, s_out, o_stride, B, N, packed && mk == nullptr);
+                                                                   nullptr, nullptr, s_cur, s_stride, s_out, o_stride, B, N, PS_PACK_OK && packed && mk == nullptr);
   } else {
     if (mk)
       k_node_update_tc<true, true><<<grid, TC_THREADS, sm, st>>>(wpack, ws.agg, ws.Cp, ws.eff, nullptr, nullptr, mk->eff[p],
-                                                                 mk->q, s_cur, s_stride, s_out, o_stride, B, N, packed && mk == nullptr);
+                                                                 mk->q, s_cur, s_stride, s_out, o_stride, B, N, PS_PACK_OK && packed && mk == nullptr);
     else
       k_node_update_tc<true, false><<<grid, TC_THREADS, sm, st>>>(wpack, ws.agg, ws.Cp, ws.eff, nullptr, nullptr, nullptr,
-                                                                  nullptr, s_cur, s_stride, s_out, o_stride, B, N, packed && mk == nullptr);
+                                                                  nullptr, s_cur, s_stride, s_out, o_stride, B, N, PS_PACK_OK && packed && mk == nullptr);
   }
   PILE_CHECK_LAUNCH();
   return 0;

@@ -39,13 +39,17 @@ class GoalCache:
         self._np_key = None
         return self._img
 
-    def shaped_np(self, goal_np, goal_tensor, content_hash=None):
+    def shaped_np(self, goal_np, goal_tensor, content_hash=None, device=None):
         """Planner entry: the goal arrives as a numpy array, so the key is a hash of its bytes (as
         PlannerGD.goal_coordinates does; `content_hash` = goal_content_hash(goal_np) when the caller already has it);
-        `goal_tensor` is the same image already on the device."""
+        `goal_tensor` is the same image already on the device, or None with `device` given: the image is then copied
+        to the device only on a miss (2 MB for a 720 x 720 goal, every call otherwise)."""
         g = np.ascontiguousarray(goal_np)
-        key = (g.shape, str(g.dtype), str(goal_tensor.device), goal_content_hash(g) if content_hash is None else content_hash)
+        dev = goal_tensor.device if goal_tensor is not None else torch.device(device)
+        key = (g.shape, str(g.dtype), str(dev), goal_content_hash(g) if content_hash is None else content_hash)
         if self._img is None or key != self._np_key:
+            if goal_tensor is None:
+                goal_tensor = torch.as_tensor(g, dtype=torch.float32).to(dev)
             self._img = shape_goal_image(goal_tensor)
             self._np_key = key
             self._ref, self._version, self._copy = goal_tensor, goal_tensor._version, goal_tensor.detach().clone()

@@ -19,8 +19,10 @@ from oracle import pile_oracle as O
 N, T, NS = 30, 3, 8
 
 
-def _install_doubles(pl, W, env):
-    def evaluate(s0, dens, attr, model_dy, acts, obs_goal, goal_t, coor, w):
+def _install_doubles(pl, W, env, goal):
+    goal_t = torch.tensor(goal, dtype=torch.float)
+
+    def evaluate(s0, dens, attr, model_dy, acts, goal_img, coor, w):
         pred = O.rollout(W, 0.08, env.get_cam_extrinsics(), synthetic.GLOBAL_SCALE, s0, dens, attr, acts)
         rew = O.reward_ptcl(pred[:, -1], goal_t, env.get_cam_params(), coor)
         return rew, torch.from_numpy(O.mppi_record(rew.numpy(), acts.numpy(), w)).float()
@@ -38,9 +40,10 @@ def _plan(world, rank, port, out):
     cfg, env = synthetic.default_config(), synthetic.FakeEnv()
     pl = P.PlannerGD(cfg, env)
     W = O.weights_from_seed(0)
-    _install_doubles(pl, W, env)
+    goal = synthetic.make_goal("disc")
+    _install_doubles(pl, W, env, goal)
     st, dn = synthetic.make_pile_batch(1, N, seed=2)
-    res = pl.trajectory_optimization_mppi(st, dn, np.zeros((1, N), np.float32), synthetic.make_goal("disc"), None,
+    res = pl.trajectory_optimization_mppi(st, dn, np.zeros((1, N), np.float32), goal, None,
                                           synthetic.random_actions(1, T, seed=2)[0], n_sample=NS, n_update_iter=2, seed=5)
     if rank == 0:
         np.save(out, res["action_sequence"])
