@@ -514,7 +514,7 @@ int launch_node_encode_tc(const float* wpack, const float* attr, const float* de
     if ((e = set_smem_tc(k_node_update_tc<true, true>, sizeof(NodeUpdSmemTc)))) return e;
     if ((e = set_smem_tc(k_edge_agg<false, false>, agg_smem_bytes<false>(false)))) return e;
     if ((e = set_smem_tc(k_edge_agg<true, false>, agg_smem_bytes<false>(false)))) return e;
-    if ((e = set_smem_tc(k_edge_agg<false, true>, agg_smem_bytes<true>(true)))) return e;
+    if ((e = set_smem_tc(k_edge_agg<false, true>, agg_smem_bytes<true>(PS_PACK_OK)))) return e;
     if ((e = set_smem_tc(k_edge_agg<true, true>, agg_smem_bytes<true>(false)))) return e;
     once.done(once_dev);
   }
