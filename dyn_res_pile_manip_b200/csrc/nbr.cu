@@ -148,7 +148,8 @@ __device__ __forceinline__ uint64_t mul2_rn(uint64_t a, uint64_t b) { uint64_t r
 constexpr int NBR_BLOCK = 32;     // candidates per admission mask
 
 // One CTA per sample.  Optional fused s_delta (action != nullptr).
-// dynamic smem: pos[N] (float4) | cutd[N] | cuti[N] | deg[N] | roff[N+1] | sel[N*KMAX] | perm[N] | xs[NP] | ys[NP] | zs[NP]
+// dynamic smem: pos[N] (float4) | cutd[N] | cuti[N] | deg[N] | roff[N+1] | sel[N*KMAX] | perm[N] | xs[NP] | ys[NP] | zs[NP] |
+// cur[N] (float4: un-pushed position + attribute, for the relation-encoder input rows) | transposed lists (tape runs)
 // (NP = N rounded up to a multiple of 32; the tail of xs holds +inf so that padded candidates are never admitted)
 __global__ void __launch_bounds__(NBR_THREADS)
 k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* __restrict__ s_delta_in,
@@ -170,6 +171,7 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
   float* xs = smem + (19 * N + 1 + 3) / 4 * 4;
   float* ys = xs + NP;
   float* zs = ys + NP;
+  float4* cur = reinterpret_cast<float4*>(zs + NP);      // (s_cur, attr): the epilogue reads no global memory
   __shared__ int warp_sums[NBR_THREADS / 32];
   __shared__ int total_s;
   __shared__ float box[6];
@@ -196,6 +198,7 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
     const float px = __fadd_rn(x, dx), py = __fadd_rn(y, dy), pz = __fadd_rn(z, dz);
     pos[i] = make_float4(px, py, pz, 0.f);
     xs[i] = px; ys[i] = py; zs[i] = pz;
+    cur[i] = make_float4(x, y, z, efeat != nullptr ? attr[base + i] : 0.f);
   }
   for (int i = N + threadIdx.x; i < NP; i += blockDim.x) { xs[i] = __int_as_float(0x7f800000); ys[i] = 0.f; zs[i] = 0.f; }
   __syncthreads();
@@ -392,11 +395,10 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
     // optional: the relation encoder's input rows (attr_r, attr_s, s_cur_r - s_cur_s, density; gnn_dyn.py:164-172)
     // for the tensor engine, the same values k_edge_features (edge_tc.cu) writes
     if (efeat != nullptr) {
-      const float* pr = s_cur + (long long)b * s_stride + i * 3;
-      const float* ps = s_cur + (long long)b * s_stride + c * 3;
+      const float4 pr = cur[i], ps = cur[c];
       float* out = efeat + e * 8;
-      *reinterpret_cast<float4*>(out) = make_float4(attr[base + i], attr[base + c], pr[0] - ps[0], pr[1] - ps[1]);
-      *reinterpret_cast<float4*>(out + 4) = make_float4(pr[2] - ps[2], dn, 0.f, 0.f);
+      *reinterpret_cast<float4*>(out) = make_float4(pr.w, ps.w, pr.x - ps.x, pr.y - ps.y);
+      *reinterpret_cast<float4*>(out + 4) = make_float4(pr.z - ps.z, dn, 0.f, 0.f);
     }
   }
 
@@ -405,7 +407,7 @@ k_nbr_search(const float* __restrict__ s_cur, long long s_stride, const float* _
   // the receiver lists by a counting sort in shared memory (O(E) shared-memory atomics) instead of a second O(N^2)
   // distance scan per sender; the atomics fill a sender's segment in arbitrary order, so every segment is then sorted
   // by receiver (each receiver appears at most once per sender): the result is deterministic.
-  int* tre = reinterpret_cast<int*>(zs + NP);      // [KMAX*N] receiver of transposed slot (tape runs only)
+  int* tre = reinterpret_cast<int*>(cur + N);      // [KMAX*N] receiver of transposed slot (tape runs only)
   int* ted = tre + KMAX * N;                       // [KMAX*N] edge id
   __syncthreads();
   for (int j = threadIdx.x; j < N; j += blockDim.x) deg[j] = 0;       // reuse as in-degree / fill cursor
@@ -611,7 +613,7 @@ int launch_gen_s_delta(const float* s_cur, long long s_stride, const float* acti
 
 static size_t nbr_smem_bytes_mode(int N, bool transpose) {
   const size_t NP = (size_t)(N + NBR_BLOCK - 1) / NBR_BLOCK * NBR_BLOCK;
-  size_t words = (size_t)(19 * N + 1 + 3) / 4 * 4 + 3 * NP;      // 4N pos + 15N + 1 words, then xs | ys | zs
+  size_t words = (size_t)(19 * N + 1 + 3) / 4 * 4 + 3 * NP + 4 * (size_t)N;      // 4N pos + 15N + 1 words, then xs | ys | zs | cur
   if (transpose) words += 2 * (size_t)KMAX * N;                 // + the transposed lists being sorted
   return sizeof(float) * words;
 }
