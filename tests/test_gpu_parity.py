@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import dyn_res_pile_manip_b200 as P
-from dyn_res_pile_manip_b200 import ops, synthetic
+from dyn_res_pile_manip_b200 import _lib, ops, synthetic
 from oracle import pile_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -95,6 +95,26 @@ def test_relation_search_block_borders_and_padding_mask(N, B):
     adj = O.adjacency(torch.from_numpy(s), torch.from_numpy(sd), 0.08, nums)
     rel = ops.build_relations(cuda(s), cuda(sd), 0.08, nums)
     assert np.array_equal(coo_from_relations(rel), adj.nonzero().to(torch.int16).numpy())
+
+
+def test_largest_sample_and_one_past_it():
+    """The relation search keeps a whole sample in 200 KB of shared memory (184 bytes per particle): 1112 particles is
+    the largest sample it takes -- checked against the oracle, with and without the transposed lists -- and 1113 is
+    refused loudly instead of launching with too little shared memory."""
+    N = 1112
+    rng = np.random.RandomState(3)
+    s = rng.uniform(-.25, .25, (2, N, 3)).astype(np.float32)
+    s[..., 2] = 0.74 + 0.02 * rng.uniform(size=(2, N)).astype(np.float32)
+    sd = (rng.normal(0, 0.02, size=s.shape) * (rng.uniform(size=s.shape[:2] + (1,)) < 0.3)).astype(np.float32)
+    adj = O.adjacency(torch.from_numpy(s), torch.from_numpy(sd), 0.08)
+    want = adj.nonzero().to(torch.int16).numpy()
+    rel = ops.build_relations(cuda(s), cuda(sd), 0.08)
+    assert np.array_equal(coo_from_relations(rel), want)
+    rel_t, _ = ops.build_relations(cuda(s), cuda(sd), 0.08, with_transpose=True)
+    assert np.array_equal(coo_from_relations(rel_t), want)
+    big = np.zeros((1, N + 1, 3), np.float32)
+    with pytest.raises(_lib.PileLibraryError):
+        ops.build_relations(cuda(big), cuda(big), 0.08)
 
 
 @pytest.mark.parametrize("N,B", [(7, 2), (40, 3), (100, 4), (300, 3), (341, 2)])
