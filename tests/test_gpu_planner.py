@@ -207,6 +207,28 @@ def test_gd_planner_sees_a_changed_goal(setup):
     assert not np.array_equal(r[0], r[1])
 
 
+def test_mppi_planner_sees_changed_goal_and_state(setup):
+    """The MPPI entry keeps one captured engine per problem size and reloads its goal / start-state buffers only when
+    they changed: a sequence of calls that alternates goals and start states (same shapes, so the same engine) must
+    give, call by call, what a fresh planner gives."""
+    cfg, env, model, planner = setup
+    N, T, NS = 50, 3, 32
+    mean0 = synthetic.random_actions(1, T, seed=21, lim=3.0)[0]
+    piles = [synthetic.make_pile_batch(1, N, seed=s) for s in (30, 31)]
+    seen = {}
+    for step, (kind, which) in enumerate([("bar", 0), ("bar", 0), ("disc", 0), ("disc", 1), ("bar", 1), ("bar", 0)]):
+        st, dn = piles[which]
+        args = (st, dn, np.zeros((1, N), np.float32), synthetic.make_goal(kind), model, mean0)
+        got = planner.trajectory_optimization_mppi(*args, n_sample=NS, n_update_iter=2, seed=9)
+        fresh = P.PlannerGD(cfg, env).trajectory_optimization_mppi(*args, n_sample=NS, n_update_iter=2, seed=9)
+        assert np.array_equal(got["reward"], fresh["reward"]), (step, kind, which)
+        assert np.array_equal(got["action_sequence"], fresh["action_sequence"]), (step, kind, which)
+        seen[(kind, which)] = got["reward"]
+    assert len(planner._mppi_engines) >= 1
+    assert not np.array_equal(seen[("bar", 0)], seen[("disc", 0)])
+    assert not np.array_equal(seen[("bar", 0)], seen[("bar", 1)])
+
+
 def test_mppi_planner_matches_oracle_composition(setup):
     """trajectory_optimization_mppi == sample_action_sequences -> rollout -> last-step reward -> softmax-weighted mean
     written with the oracle pieces (reference planners.py:69-190, 302-370, 549-561), same numpy seed."""
