@@ -172,7 +172,9 @@ k_bwd_gather(const int* __restrict__ rowptr, const int* __restrict__ trowptr, co
              const int* __restrict__ tedge, const uint8_t* __restrict__ m_edge, const float* __restrict__ gagg_p,
              float* __restrict__ gpr_out, float* __restrict__ gps_out, int B, int N) {
   const int l16 = threadIdx.x & 15;
-  const int mb = l16 >> 1, msh = (l16 & 1) * 4;
+  // a lane's four channels are one nibble of mask byte l16 / 2 of a relation's row: the low one on even lanes
+  const unsigned odd = (unsigned)l16 & 1u;
+  const unsigned sel_nib = odd ? 0xf0u : 0x0fu, sel_cnt = odd ? 0x10101010u : 0x01010101u, sh = odd * 4u;
   const int R = B * N;
   const int nhw = (int)gridDim.x * (int)(blockDim.x >> 4);
   for (int node = (int)blockIdx.x * (int)(blockDim.x >> 4) + (int)(threadIdx.x >> 4); node < R; node += nhw) {
@@ -182,27 +184,49 @@ k_bwd_gather(const int* __restrict__ rowptr, const int* __restrict__ trowptr, co
     const int* tp = trowptr + (long long)b * (N + 1) + i;
     const int e0 = rp[0], e1 = rp[1], k0 = tp[0], k1 = tp[1];
     const float4 ga = ld4(gagg_p + (long long)node * H + 4 * l16);
-    float4 gpr = make_float4(0.f, 0.f, 0.f, 0.f), gps = gpr;
-    for (int e = e0; e < e1; ++e) {
-      const unsigned nib = (m_edge[(slot + e) * 8 + mb] >> msh) & 15u;
-      const float4 v = mask4(ga, nib);
-      gpr.x += v.x; gpr.y += v.y; gpr.z += v.z; gpr.w += v.w;
+    // per-sample base pointers once; everything below is a 32-bit index on top of them
+    const uint8_t* msample = m_edge + slot * 8 + (l16 >> 1);
+    const float* gsample = gagg_p + (long long)b * N * H + 4 * l16;
+    const int* tr = trecv + slot;
+    const int* te = tedge + slot;
+    // (kept opaque: ptxas otherwise re-derives every address from the kernel parameters, three instructions per load)
+    asm volatile("" : "+l"(msample), "+l"(gsample), "+l"(tr), "+l"(te));
+    // Receiver side: every relation of the row carries the SAME gradient row ga, so the masked sum is ga times the number
+    // of relations whose sign bit is set, per channel.  The four bits of the lane's nibble are spread to the four bytes of
+    // a word (multiplier 1 + 2^7 + 2^14 + 2^21: bit k of the nibble lands on bit 8k, the copies do not overlap) and the
+    // words are added: four counters (<= 10) in one register.
+    unsigned cnt4 = 0;
+    {
+      const uint8_t* mp = msample + (unsigned)e0 * 8u;
+      asm volatile("" : "+l"(mp));
+      const int cnt = e1 - e0;
+#pragma unroll
+      for (int q = 0; q < KMAX; ++q)
+        if (q < cnt) cnt4 += (((unsigned)__ldg(mp + q * 8) & sel_nib) * 0x00204081u) & sel_cnt;
+#pragma unroll 1
+      for (int q = KMAX; q < cnt; ++q)          // denser caller-provided lists never reach this kernel; kept for safety
+        cnt4 += (((unsigned)__ldg(mp + q * 8) & sel_nib) * 0x00204081u) & sel_cnt;
     }
+    const float4 gpr = make_float4(ga.x * (float)((cnt4 >> sh) & 15u), ga.y * (float)((cnt4 >> (8u + sh)) & 15u),
+                                   ga.z * (float)((cnt4 >> (16u + sh)) & 15u), ga.w * (float)((cnt4 >> (24u + sh)) & 15u));
+    float4 gps = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k = k0; k < k1; k += 4) {          // four independent gathers in flight
       float4 g[4];
       unsigned nib[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int kk = min(k + u, k1 - 1);
-        const int rc = trecv[slot + kk], e = tedge[slot + kk];
-        nib[u] = (m_edge[(slot + e) * 8 + mb] >> msh) & 15u;
-        g[u] = ld4(gagg_p + ((long long)b * N + rc) * H + 4 * l16);
+        const unsigned rc = (unsigned)__ldg(tr + kk), e = (unsigned)__ldg(te + kk);
+        nib[u] = (unsigned)__ldg(msample + e * 8u) >> sh;
+        g[u] = __ldg(reinterpret_cast<const float4*>(gsample + rc * (unsigned)H));
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (k + u < k1) {
-          const float4 v = mask4(g[u], nib[u]);
-          gps.x += v.x; gps.y += v.y; gps.z += v.z; gps.w += v.w;
+          if (nib[u] & 1u) gps.x += g[u].x;
+          if (nib[u] & 2u) gps.y += g[u].y;
+          if (nib[u] & 4u) gps.z += g[u].z;
+          if (nib[u] & 8u) gps.w += g[u].w;
         }
       }
     }
