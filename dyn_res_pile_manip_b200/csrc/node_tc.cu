@@ -224,13 +224,13 @@ k_edge_agg(const int* __restrict__ rowptr, const int* __restrict__ col, const fl
            const float* __restrict__ Pr, const float* __restrict__ Ps, uint8_t* __restrict__ m_edge,
            float* __restrict__ agg, int B, int N) {
   // A half-warp owns one receiver at a time; lane l16 owns channels 4*l16 .. 4*l16+3.  The kernel streams C_e once
-  // and gathers one P_s row per relation; what bounds it is how many of those row reads an SM keeps in flight and
-  // how many instructions it spends to issue them.  So the rows do not pass through registers: per receiver ONE
-  // bulk copy (TMA, cp.async.bulk) brings its contiguous C_e rows and one bulk copy per relation (issued by the
-  // lane that holds that relation's sender index) its P_s row into the half-warp's shared-memory slab, completion
-  // counted on the half-warp's mbarrier; then the rows are summed from the slab.  The first two levels of the
-  // dependent chain rowptr -> col -> rows are prefetched (rowptr two receivers ahead, col and P_r one ahead).
-  // All loop bounds are warp-uniform so that the two half-warps stay converged.
+  // and gathers one P_s row per relation.  The rows do not pass through registers: per receiver ONE bulk copy (TMA,
+  // cp.async.bulk) brings its contiguous C_e rows into the half-warp's shared-memory slab, and the P_s rows of its
+  // relations follow as 16-byte cp.async pieces (lane l16 copies piece l16 of every row; the sender indices go round by
+  // shuffle); completion of both is counted on the half-warp's mbarrier, then the rows are summed from the slab.  The
+  // first two levels of the dependent chain rowptr -> col -> rows are prefetched (rowptr two receivers ahead, col and
+  // P_r one ahead).  All loop bounds are warp-uniform so that the two half-warps stay converged.  Variants that were
+  // measured and lost (fewer instructions, register-fed rows, L2 prefetch, other occupancies): DESIGN.md section 6.
   extern __shared__ __align__(128) unsigned char agg_smem[];
   __shared__ uint64_t bars[AGG_THREADS / 16];
   // P_s rows are packed like C_e when no tape is recorded; with a tape (gradient runs) they stay fp32, because the

@@ -2,8 +2,8 @@
 
 The reference synchronises the host after every horizon step (planners.py:357) and builds
 data-dependent shapes (`n_rel.item()`, gnn_dyn.py:243).  Here every buffer is sized by
-(rows, N, T) up front (CSR with a fixed 10N edge capacity), so the T*6+3 kernel launches of one
-planner evaluation are captured once with `torch.cuda.CUDAGraph` and replayed per iteration.
+(rows, N, T) up front (CSR with a fixed 10N edge capacity), so the T*9+3 kernel launches of one
+planner evaluation (T*6+3 on the FP32 engine) are captured once with `torch.cuda.CUDAGraph` and replayed per iteration.
 """
 import numpy as np
 import torch
