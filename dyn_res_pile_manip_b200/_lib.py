@@ -79,6 +79,7 @@ SIGNATURES = {
     "pile_general_scratch_bytes": (_LL, [_I, _I, _I]),
     "pile_general_grad_offset": (_LL, [_I, _I]),
     "pile_general_forward": (_I, [_P, _I, _P, _P, _P, _P, _P, _F, _I, _I, _P, _P, _P]),
+    "pile_general_forward_inference": (_I, [_P, _I, _P, _P, _P, _P, _P, _F, _I, _I, _P, _P, _P]),
     "pile_general_forward_relations": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "pile_general_backward": (_I, [_P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "pile_general_relations_view": (_I, [_P, _I, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
@@ -90,7 +91,7 @@ SIGNATURES = {
     "pile_mppi_combine": (_I, [_P, _I, _I, _P, _P]),
 }
 
-ABI_VERSION = 3          # PILE_ABI_VERSION of include/pile_gnn.h
+ABI_VERSION = 4          # PILE_ABI_VERSION of include/pile_gnn.h
 _lib = None
 
 

@@ -501,6 +501,14 @@ int pile_general_forward(const float* wpack, int nf_effect, const float* attr, c
                                 (cudaStream_t)stream);
 }
 
+int pile_general_forward_inference(const float* wpack, int nf_effect, const float* attr, const float* dens,
+                                   const int* particle_nums, const float* s_cur, const float* s_delta, float adj_thresh,
+                                   int B, int N, void* tape, float* s_pred, void* stream) {
+  if (bad_dims(B, N) || !wpack || !attr || !dens || !s_cur || !s_delta || !tape || !s_pred) return (int)cudaErrorInvalidValue;
+  return launch_general_forward(wpack, nf_effect, attr, dens, particle_nums, s_cur, s_delta, adj_thresh, B, N, tape, s_pred,
+                                (cudaStream_t)stream, true);
+}
+
 int pile_general_forward_relations(const float* wpack, int nf_effect, const float* attr, const float* dens,
                                    const float* s_cur, const float* s_delta, const int* rowptr, const int* col,
                                    const int* row, int B, int N, void* tape, float* s_pred, void* stream) {

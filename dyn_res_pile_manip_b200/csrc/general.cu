@@ -468,6 +468,34 @@ __global__ void k_g_gather_nodes(const int* __restrict__ rowptr, const int* __re
   st4(o, s);
 }
 
+// hoisted relation propagator (inference): agg[i] = sum_{e in row i} ReLU(Ce[e] + Pr[i] + Ps[col e])   (one thread per float4)
+// with Ce = W_e r3 + w_d d + b per relation (once per model step) and (Pr, Ps) = (W_r, W_s) eff per PARTICLE -- the same
+// regrouping of Linear([r3, eff_r, eff_s, d]) the width-64 planner engines use
+__global__ void k_g_agg_hoisted(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ Ce,
+                                const float* __restrict__ Pr, const float* __restrict__ Ps, float* __restrict__ out, int B,
+                                int N, int Hp) {
+  const int q4 = Hp / 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * N * q4) return;
+  const long long node = idx / q4;
+  const int c = (int)(idx - node * q4) * 4;
+  const int b = (int)(node / N), i = (int)(node - (long long)b * N);
+  const long long slot = (long long)b * KMAX * N;
+  const float4 pr = ld4(Pr + node * Hp + c);
+  const float* ps_b = Ps + (long long)b * N * Hp + c;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int* rp = rowptr + (long long)b * (N + 1) + i;
+  for (int e = rp[0]; e < rp[1]; ++e) {
+    const float4 ce = ld4(Ce + (slot + e) * Hp + c);
+    const float4 ps = ld4(ps_b + (long long)col[slot + e] * Hp);
+    s.x += fmaxf(ce.x + pr.x + ps.x, 0.f);
+    s.y += fmaxf(ce.y + pr.y + ps.y, 0.f);
+    s.z += fmaxf(ce.z + pr.z + ps.z, 0.f);
+    s.w += fmaxf(ce.w + pr.w + ps.w, 0.f);
+  }
+  st4(out + node * Hp + c, s);
+}
+
 // s_pred = Q V1^T + b + s_cur   (gnn_dyn.py:196-198); V1T [Hp][4], b [4]
 __global__ void k_g_predict(const float* __restrict__ Q, const float* __restrict__ v1t, const float* __restrict__ b1,
                             const float* __restrict__ s_cur, float* __restrict__ s_out, int B, int N, int Hp) {
@@ -777,8 +805,11 @@ GradOff grad_offsets(int H) {
   return g;
 }
 
+// hoisted: inference only -- the relation propagator in its regrouped form (k_g_agg_hoisted); the tape then holds the
+// relation lists and the particle-side arrays but NOT the relation-side layer inputs M[p] a backward pass would need
+// (M[0] = Ce, the head of M[1] / M[2] = Pr / Ps)
 int forward_body(const float* wpack, int Hp, const float* attr, const float* dens, const float* s_cur,
-                 const float* s_delta, int B, int N, const Tape& t, float* s_pred, cudaStream_t st) {
+                 const float* s_delta, int B, int N, const Tape& t, float* s_pred, cudaStream_t st, bool hoisted = false) {
   int e = 0;
   const int nb = Hp / BW;
   const long long R = (long long)B * N;
@@ -804,9 +835,29 @@ int forward_body(const float* wpack, int Hp, const float* attr, const float* den
     if ((e = lin<true>(a, st))) return e;
   }
   const unsigned node4 = (unsigned)((R * (Hp / 4) + 255) / 256);
+  if (hoisted) {          // Ce = W_e r3 + w_d d + b
+    LinArgs a = lin_base(B, N, nb, t.csr);
+    a.nsrc = 1; a.src[0] = {t.R3, W(W_ET), 0}; a.dens = dens; a.wd = W(WD_RP); a.bias = W(B_RP); a.y = t.M[0]; a.relu = 0;
+    if ((e = lin<true>(a, st))) return e;
+  }
   for (int p = 0; p < PSTEP; ++p) {
     const float* eff_in = p == 0 ? t.P : t.eff[p - 1];
     LinArgs a = lin_base(B, N, nb, t.csr);
+    if (hoisted) {
+      a.nsrc = 1; a.src[0] = {eff_in, W(W_RT), 0}; a.y = t.M[1]; a.relu = 0;
+      if ((e = lin<false>(a, st))) return e;
+      a.src[0] = {eff_in, W(W_ST), 0}; a.y = t.M[2];
+      if ((e = lin<false>(a, st))) return e;
+      k_g_agg_hoisted<<<node4, 256, 0, st>>>(t.csr.rowptr, t.csr.col, t.M[0], t.M[1], t.M[2], t.agg[p], B, N, Hp);
+      PILE_CHECK_LAUNCH();
+      a = lin_base(B, N, nb, t.csr);
+      a.nsrc = 2;
+      a.src[0] = {t.P, W(W_PT), 0};
+      a.src[1] = {t.agg[p], W(W_AT), 0};
+      a.dens = dens; a.wd = W(WD_PP); a.bias = W(B_PP); a.res = eff_in; a.y = t.eff[p]; a.relu = 1;
+      if ((e = lin<false>(a, st))) return e;
+      continue;
+    }
     a.nsrc = 3;
     a.src[0] = {t.R3, W(W_ET), 0};
     a.src[1] = {eff_in, W(W_RT), 1};
@@ -865,7 +916,7 @@ int general_relations_view(void* tape, int B, int N, int H, int** rowptr, int** 
 
 int launch_general_forward(const float* wpack, int H, const float* attr, const float* dens, const int* particle_nums,
                            const float* s_cur, const float* s_delta, float adj_thresh, int B, int N, void* tape,
-                           float* s_pred, cudaStream_t st) {
+                           float* s_pred, cudaStream_t st, bool hoisted) {
   if (bad_width(H)) return (int)cudaErrorInvalidValue;
   int e = configure();
   if (e) return e;
@@ -875,7 +926,7 @@ int launch_general_forward(const float* wpack, int H, const float* attr, const f
   e = launch_nbr_search(s_cur, (long long)N * 3, s_delta, nullptr, 0, none, nullptr, particle_nums, B, N,
                         adj_thresh * adj_thresh, t.csr, st, attr, dens, t.Y0);
   if (e) return e;
-  return forward_body(wpack, Hp, attr, dens, s_cur, s_delta, B, N, t, s_pred, st);
+  return forward_body(wpack, Hp, attr, dens, s_cur, s_delta, B, N, t, s_pred, st, hoisted);
 }
 
 // the same step on caller-provided relation lists (receiver-grouped CSR, any number of relations per receiver as long

@@ -146,7 +146,7 @@ long long general_grad_offset(int tensor_index, int H);
 int general_relations_view(void* tape, int B, int N, int H, int** rowptr, int** col, int** row);
 int launch_general_forward(const float* wpack, int H, const float* attr, const float* dens, const int* particle_nums,
                            const float* s_cur, const float* s_delta, float adj_thresh, int B, int N, void* tape,
-                           float* s_pred, cudaStream_t st);
+                           float* s_pred, cudaStream_t st, bool hoisted = false);
 int launch_general_forward_relations(const float* wpack, int H, const float* attr, const float* dens, const float* s_cur,
                                      const float* s_delta, const int* rowptr, const int* col, const int* row, int B,
                                      int N, void* tape, float* s_pred, cudaStream_t st);

@@ -596,15 +596,18 @@ def train_backward_raw(wpack, dens, tape, B, N, g_pred, grads, scratch):
     return g_s, g_sd
 
 
-def general_forward_raw(wpack, H, attr, dens, s_cur, s_delta, adj_thresh, particle_nums, tape, rel=None):
-    """Model step of the general-width engine (csrc/general.cu, any nf_effect <= 256); relations searched or supplied."""
+def general_forward_raw(wpack, H, attr, dens, s_cur, s_delta, adj_thresh, particle_nums, tape, rel=None, inference=False):
+    """Model step of the general-width engine (csrc/general.cu, any nf_effect <= 256); relations searched or supplied.
+    inference: no backward pass will follow -- the regrouped (hoisted) relation propagator, searched relations only."""
     B, N, _ = s_cur.shape
     out = torch.empty_like(s_cur)
     lib = _lib.load()
     if rel is None:
-        _lib.check(lib.pile_general_forward(_lib.ptr(wpack), int(H), _lib.ptr(attr), _lib.ptr(dens), _lib.ptr(particle_nums),
-                                            _lib.ptr(s_cur), _lib.ptr(s_delta), float(adj_thresh), B, N, _lib.ptr(tape),
-                                            _lib.ptr(out), _stream()), "pile_general_forward")
+        fn, name = (lib.pile_general_forward_inference, "pile_general_forward_inference") if inference else \
+            (lib.pile_general_forward, "pile_general_forward")
+        _lib.check(fn(_lib.ptr(wpack), int(H), _lib.ptr(attr), _lib.ptr(dens), _lib.ptr(particle_nums),
+                      _lib.ptr(s_cur), _lib.ptr(s_delta), float(adj_thresh), B, N, _lib.ptr(tape),
+                      _lib.ptr(out), _stream()), name)
     else:
         _lib.check(lib.pile_general_forward_relations(
             _lib.ptr(wpack), int(H), _lib.ptr(attr), _lib.ptr(dens), _lib.ptr(s_cur), _lib.ptr(s_delta), _lib.ptr(rel.rowptr),

@@ -31,12 +31,12 @@ def general_rollout(planner, model_dy, s0, dens, attr, act_seqs):
     """T-step rollout for a model of any width (nf_effect != 64): the reference's own loop (planners.py:341-359) --
     pusher model, model step -- on the differentiable ops of the general-width engine; gradients reach the action
     sequences through torch's autograd over those two ops.  No weight gradients (planners.py:674 optimises actions only)."""
-    from .propnet import _GeneralStepFn
+    from .propnet import general_step
     states = []
     s = s0
     for t in range(act_seqs.shape[1]):
         s_delta = ops.gen_s_delta(s, act_seqs[:, t], planner.pusher)
-        s = _GeneralStepFn.apply(s, s_delta, attr, dens, model_dy.model, None, None)
+        s = general_step(s, s_delta, attr, dens, model_dy.model, None, None)
         states.append(s)
     return torch.stack(states, dim=1)
 

@@ -138,7 +138,12 @@ class _GeneralStepFn(torch.autograd.Function):
         pn = None
         if particle_nums is not None:
             pn = torch.as_tensor(particle_nums).to(device=dev, dtype=torch.int32).contiguous()
-        out = ops.general_forward_raw(wpack, H, attr_c, dens_c, s_cur_c, s_delta_c, owner.adj_thresh, pn, tape, rel)
+        # nothing asks for a gradient (torch.no_grad(): MPPI rollouts, plain predictions): the hoisted forward, whose tape
+        # keeps the relation lists but not what a backward pass would read (decided by general_step: inside forward the
+        # grad mode is already off and needs_input_grad ignores it)
+        infer = rel is None and bool(getattr(owner, "_general_infer", False))
+        out = ops.general_forward_raw(wpack, H, attr_c, dens_c, s_cur_c, s_delta_c, owner.adj_thresh, pn, tape, rel,
+                                      inference=infer)
         owner.last_relations_buffer = (tape, ("general", H), B, N)
         ctx.save_for_backward(wpack, dens_c, tape)
         ctx.dims, ctx.shapes = (B, N, H), [tuple(p.shape) for p in params]
@@ -162,6 +167,17 @@ class _GeneralStepFn(torch.autograd.Function):
                 off, end = lib.pile_general_grad_offset(i, H), lib.pile_general_grad_offset(i + 1, H)
                 out[i] = grads[off:end].view(shape)
         return (g_s, g_sd, None, None, None, None, None) + tuple(out)
+
+
+def general_step(s_cur, s_delta, attr, dens, owner, particle_nums, rel, *params):
+    """_GeneralStepFn with the inference decision made where the grad mode is still visible."""
+    wants = torch.is_grad_enabled() and any(isinstance(x, torch.Tensor) and x.requires_grad
+                                            for x in (s_cur, s_delta, attr, dens) + tuple(params))
+    owner._general_infer = not wants
+    try:
+        return _GeneralStepFn.apply(s_cur, s_delta, attr, dens, owner, particle_nums, rel, *params)
+    finally:
+        owner._general_infer = False
 
 
 class PropModuleDiffDen(nn.Module):
@@ -206,7 +222,7 @@ class PropModuleDiffDen(nn.Module):
         rel = Rr if isinstance(Rr, ops.Relations) else ops.Relations.from_dense(Rr, Rs)
         params = [p for _, p in self.named_parameters()]
         if not self.planner_engines:
-            return _GeneralStepFn.apply(s_cur, s_delta, a_cur, particle_dens, self, None, rel, *params)
+            return general_step(s_cur, s_delta, a_cur, particle_dens, self, None, rel, *params)
         wants_wgrad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if wants_wgrad or rel.max_degree > ops.KMAX:
             # training (weight gradients), or relation lists denser than the planner's engines take: general kernels
@@ -232,7 +248,7 @@ class PropNetDiffDenModel(nn.Module):
         self.model.adj_thresh = self.adj_thresh
         params = [p for _, p in self.model.named_parameters()]
         if not self.model.planner_engines:
-            return _GeneralStepFn.apply(s_cur, s_delta, a_cur, particle_dens, self.model, particle_nums, None, *params)
+            return general_step(s_cur, s_delta, a_cur, particle_dens, self.model, particle_nums, None, *params)
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             # training: weight gradients wanted (train/train_gnn_dyn.py:150-199)
             return _TrainStepFn.apply(s_cur, s_delta, a_cur, particle_dens, self.model, particle_nums, None, *params)

@@ -242,6 +242,32 @@ def test_mppi_planner_width150_matches_oracle_composition():
     np.testing.assert_allclose(got["action_sequence"], mean[:, 0, :], rtol=0, atol=5e-4)     # softmax-weighted mean of them
 
 
+@pytest.mark.parametrize("nf,N,B", [(8, 20, 3), (96, 50, 4), (150, 100, 5), (256, 33, 2)])
+def test_inference_forward_equals_training_forward(nf, N, B):
+    """Without a gradient in sight predict_one_step takes pile_general_forward_inference (the regrouped relation
+    propagator: one relation-side GEMM per step instead of three wide ones); it must give the training forward's
+    prediction up to the summation order, on a ragged batch, with the same relation lists."""
+    torch.manual_seed(nf)
+    model = P.PropNetDiffDenModel(config_with_width(nf), True).to(DEV)
+    st, dn = synthetic.make_pile_batch(B, N, seed=nf)
+    rng = np.random.RandomState(nf)
+    sd = (rng.normal(0, 0.02, size=st.shape) * (rng.uniform(size=st.shape[:2] + (1,)) < 0.3)).astype(np.float32)
+    nums = torch.tensor([N] + [max(2, N - 3 * b) for b in range(1, B)])
+    args = (torch.zeros(B, N, device=DEV), torch.tensor(st).to(DEV), torch.tensor(sd).to(DEV), torch.tensor(dn).to(DEV), nums)
+    with torch.no_grad():
+        fast = model.predict_one_step(*args)
+        rel_fast = [e.copy() for e in model.relations_of_last_step().edge_sets()]
+    s_req = args[1].clone().requires_grad_(True)          # a gradient is wanted: the taped (un-hoisted) forward
+    slow = model.predict_one_step(args[0], s_req, *args[2:])
+    rel_slow = model.relations_of_last_step().edge_sets()
+    assert all(np.array_equal(a, b) for a, b in zip(rel_fast, rel_slow))
+    moved = (slow.detach() - args[1]).cpu().numpy()
+    err = np.abs((fast - slow.detach()).cpu().numpy()).max() / max(np.abs(moved).max(), 1e-30)
+    assert err < 5e-6, err
+    slow.sum().backward()                                   # and the taped one still backpropagates
+    assert torch.isfinite(s_req.grad).all()
+
+
 def test_width_limits():
     with pytest.raises(P._lib.PileLibraryError):
         P.PropNetDiffDenModel(config_with_width(257), True)

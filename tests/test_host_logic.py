@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pile_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.pile_abi_version() == _lib.ABI_VERSION == 4
     assert lib.pile_nf_effect() == 64 and lib.pile_max_relations() == 10
 
 
