@@ -824,21 +824,44 @@ int forward_body(const float* wpack, int Hp, const float* attr, const float* den
     a.nsrc = 1; a.src[0] = {t.H0, W(W_PE1T), 0}; a.bias = W(B_PE1); a.y = t.P; a.relu = 1;
     if ((e = lin<false>(a, st))) return e;
   }
+  // Inference with the tensor-core GEMM engine selected (pile_set_tensor_cores != 0) and enough relation rows to fill the
+  // GPU: the three wide relation-side layers run on tcgen05 (general_tc.cu).  Their bf16 hi / lo weight images are built here,
+  // into the tape space behind P_r (the head of M[1]; M[1] / M[2] hold nothing else in an inference step).
+  const size_t E_cap = (size_t)B * KMAX * N;
+  const bool tc = hoisted && g_use_tensor_cores != 0 && E_cap >= 4096 &&
+                  E_cap * Hp >= (size_t)R * Hp + 3 * tc_image_floats(Hp);
+  float* img[3] = {nullptr, nullptr, nullptr};
+  if (tc) {
+    const int wslot[3] = {W_RE1T, W_RE2T, W_ET};
+    for (int i = 0; i < 3; ++i) {
+      img[i] = t.M[1] + (size_t)R * Hp + i * tc_image_floats(Hp);
+      if ((e = launch_tc_image(W(wslot[i]), Hp, img[i], st))) return e;
+    }
+  }
   {  // relation encoder
     LinArgs a = lin_base(B, N, nb, t.csr);
     a.x8 = t.Y0; a.w8 = W(W_RE0T); a.bias = W(B_RE0); a.y = t.R1; a.relu = 1;
     if ((e = lin<true>(a, st))) return e;
-    a = lin_base(B, N, nb, t.csr);
-    a.nsrc = 1; a.src[0] = {t.R1, W(W_RE1T), 0}; a.bias = W(B_RE1); a.y = t.R2; a.relu = 1;
-    if ((e = lin<true>(a, st))) return e;
-    a.src[0] = {t.R2, W(W_RE2T), 0}; a.bias = W(B_RE2); a.y = t.R3;
-    if ((e = lin<true>(a, st))) return e;
+    if (tc) {
+      if ((e = launch_lin_tc_edge(t.R1, img[0], W(B_RE1), nullptr, nullptr, 1, t.R2, t.csr.rowptr, B, N, Hp, st))) return e;
+      if ((e = launch_lin_tc_edge(t.R2, img[1], W(B_RE2), nullptr, nullptr, 1, t.R3, t.csr.rowptr, B, N, Hp, st))) return e;
+    } else {
+      a = lin_base(B, N, nb, t.csr);
+      a.nsrc = 1; a.src[0] = {t.R1, W(W_RE1T), 0}; a.bias = W(B_RE1); a.y = t.R2; a.relu = 1;
+      if ((e = lin<true>(a, st))) return e;
+      a.src[0] = {t.R2, W(W_RE2T), 0}; a.bias = W(B_RE2); a.y = t.R3;
+      if ((e = lin<true>(a, st))) return e;
+    }
   }
   const unsigned node4 = (unsigned)((R * (Hp / 4) + 255) / 256);
   if (hoisted) {          // Ce = W_e r3 + w_d d + b
-    LinArgs a = lin_base(B, N, nb, t.csr);
-    a.nsrc = 1; a.src[0] = {t.R3, W(W_ET), 0}; a.dens = dens; a.wd = W(WD_RP); a.bias = W(B_RP); a.y = t.M[0]; a.relu = 0;
-    if ((e = lin<true>(a, st))) return e;
+    if (tc) {
+      if ((e = launch_lin_tc_edge(t.R3, img[2], W(B_RP), W(WD_RP), dens, 0, t.M[0], t.csr.rowptr, B, N, Hp, st))) return e;
+    } else {
+      LinArgs a = lin_base(B, N, nb, t.csr);
+      a.nsrc = 1; a.src[0] = {t.R3, W(W_ET), 0}; a.dens = dens; a.wd = W(WD_RP); a.bias = W(B_RP); a.y = t.M[0]; a.relu = 0;
+      if ((e = lin<true>(a, st))) return e;
+    }
   }
   for (int p = 0; p < PSTEP; ++p) {
     const float* eff_in = p == 0 ? t.P : t.eff[p - 1];

@@ -1,0 +1,214 @@
+// General-width engine, inference: the three wide relation-side layers (RE1, RE2 and the hoisted C_e = W_e r3 + w_d d + b;
+// reference model/gnn_dyn.py:95-111, 186-187 at any nf_effect, model/gnn_dyn.py:119) on the tensor cores.
+//
+//   y[E, Hp] = act(x[E, Hp] W^T + bias + d w_d)          Hp = 64 NB, NB = 1..4 (nf_effect <= 256 zero-padded)
+//
+// Same arithmetic as the width-64 planner engines (tc.cuh): every fp32 operand is split into bf16 hi + lo, a product is
+// three tcgen05.mma passes accumulated in fp32 in tensor memory.  One 256-thread CTA per 128-row tile, two CTAs per SM
+// (while one waits for its MMAs or streams rows the other one works).  Per tile and 64-wide K block: the rows' block is
+// loaded with whole 128-byte lines, split and written as the canonical K-major A tile (32 KB); the K block's weight
+// rows for ALL Hp outputs ([Hp x 64] hi | lo, <= 64 KB) arrive by one TMA bulk copy; 12 MMAs of M = 128, N = Hp, K = 16
+// accumulate into Hp TMEM columns.  After the last K block the accumulator leaves through the (dead) A tile as a
+// row-swizzled staging buffer so that the global stores are whole lines.
+//
+// The bf16 weight images are built on the device from the engine's fp32 [in][out] images (k_g_tc_image) into free tape
+// space at the start of every inference step: no change to the packed-weights layout or to the ABI.
+#include "kernels.h"
+#include "tc_tile.cuh"
+
+namespace pile {
+namespace general {
+
+constexpr int GT_THREADS = 256;
+
+struct GtHdr {
+  uint64_t mma_bar, w_bar;
+  uint32_t tmem_base;
+};
+
+__host__ __device__ constexpr uint32_t gt_wpart(int Hp) { return (uint32_t)Hp * 128u; }          // [Hp x 64] bf16
+__host__ __device__ constexpr uint32_t gt_smem(int Hp) { return 2 * A_BYTES + 2 * gt_wpart(Hp) + 128; }
+
+// Wt: fp32 [Hp in][Hp out] (the forward image of general.cu) -> per K block kb: hi then lo canonical image of the B operand
+// [N = Hp outputs x K = 64 inputs]: bf16 index (k / 8) * (8 Hp) + (n / 8) * 64 + (n % 8) * 8 + (k % 8)
+__global__ void k_g_tc_image(const float* __restrict__ Wt, int Hp, __nv_bfloat16* __restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Hp * Hp) return;
+  const int kin = idx / Hp, n = idx - kin * Hp;
+  const float w = Wt[idx];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+  const int kb = kin >> 6, k = kin & 63;
+  const size_t off = (size_t)kb * (2 * Hp * 64) + (size_t)(k >> 3) * (8 * Hp) + (n >> 3) * 64 + (n & 7) * 8 + (k & 7);
+  img[off] = hi;
+  img[off + (size_t)Hp * 64] = lo;
+}
+
+// rows [row0, row0 + nrows) x columns [col0, col0 + 64) of a row-major [*, ld] array -> hi/lo A tile (rows past nrows are
+// zero).  A warp instruction covers 8 rows x 128 bytes (whole lines); conflict-free on the shared-memory side.
+__device__ __forceinline__ void load_block_to_tile(const float* __restrict__ x, long long row0, int nrows, int ld, int col0,
+                                                   int t, uint8_t* a_hi, uint8_t* a_lo) {
+  const int w = t >> 5, lane = t & 31;
+  float o[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = w * 16 + (j >> 1) * 8 + (lane & 7), kc = (j & 1) * 4 + (lane >> 3);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[j][i] = 0.f;
+    if (row < nrows) ld8(x + (row0 + row) * ld + col0 + kc * 8, o[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = w * 16 + (j >> 1) * 8 + (lane & 7), kc = (j & 1) * 4 + (lane >> 3);
+    store_chunk(a_hi, a_lo, (row >> 3) * A_SBO + (row & 7) * 16 + kc * A_LBO, o[j]);
+  }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(GT_THREADS, 2)
+k_g_lin_tc(const float* __restrict__ x, const uint8_t* __restrict__ img, const float* __restrict__ bias,
+           const float* __restrict__ wd, const float* __restrict__ dens, int relu, float* __restrict__ y,
+           const int* __restrict__ rowptr, int B, int N) {
+  constexpr int Hp = 64 * NB;
+  constexpr uint32_t WPART = gt_wpart(Hp), WROW = 2 * WPART;
+  constexpr uint32_t TCOLS = NB == 1 ? 64u : (NB == 2 ? 128u : 256u);
+  constexpr uint32_t BL = b_lbo(Hp);
+  constexpr uint32_t idesc = tc::make_idesc_bf16(TILE, Hp);
+  extern __shared__ __align__(128) unsigned char sm[];
+  uint8_t* const a_hi = sm;
+  uint8_t* const a_lo = sm + A_BYTES;
+  uint8_t* const w_sm = sm + 2 * A_BYTES;
+  GtHdr* const hdr = reinterpret_cast<GtHdr*>(w_sm + WROW);
+  const int t = threadIdx.x, wig = t >> 5, lane = t & 31;
+  const int r = (wig & 3) * 32 + lane, half = wig >> 2;
+
+  if (t < 32) tc::tmem_alloc(&hdr->tmem_base, TCOLS);
+  if (t == 0) {
+    tc::mbar_init(&hdr->mma_bar, 1);
+    tc::mbar_init(&hdr->w_bar, 1);
+    tc::mbar_init_fence();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_d = hdr->tmem_base;
+  const uint32_t taddr = tmem_d + ((uint32_t)((wig & 3) * 32) << 16);
+  const uint32_t sa_hi = tc::smem_u32(a_hi), sa_lo = tc::smem_u32(a_lo);
+  const uint32_t sw_hi = tc::smem_u32(w_sm), sw_lo = sw_hi + WPART;
+  uint32_t mph = 0, wph = 0;
+
+  // relation rows are tiled per sample (the slots of a sample are contiguous, its last tile is partial)
+  const int tps = (KMAX * N + TILE - 1) / TILE;
+  const int ntiles = B * tps;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b = tile / tps;
+    const int e0 = (tile - b * tps) * TILE;
+    const int nrows = min(TILE, rowptr[(long long)b * (N + 1) + N] - e0);
+    if (nrows <= 0) continue;          // CTA-uniform
+    const long long row0 = (long long)b * KMAX * N + e0;
+#pragma unroll 1
+    for (int kb = 0; kb < NB; ++kb) {
+      // the previous MMAs have completed (waited below): both operand buffers are free
+      if (t == 0) {
+        tc::mbar_expect_tx(&hdr->w_bar, WROW);
+        tc::bulk_g2s(w_sm, img + (size_t)kb * WROW, WROW, &hdr->w_bar);
+      }
+      load_block_to_tile(x, row0, nrows, Hp, kb * 64, t, a_hi, a_lo);
+      tc::fence_async_smem();
+      tc::fence_before_sync();          // this thread's tcgen05.ld of the previous tile are complete
+      __syncthreads();
+      tc::mbar_wait(&hdr->w_bar, wph);
+      wph ^= 1;
+      if (wig == 0) {
+        tc::fence_after_sync();
+        const uint32_t el = tc::elect_one();
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a = pass == 1 ? sa_lo : sa_hi;
+          const uint32_t w = pass == 2 ? sw_lo : sw_hi;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc::mma_bf16_if(el, tmem_d, tc::make_desc(a + k * 2 * A_LBO, A_LBO, A_SBO),
+                            tc::make_desc(w + k * 2 * BL, BL, B_SBO), idesc, (kb | pass | k) != 0 ? 1u : 0u);
+        }
+        if (el) tc::mma_commit(&hdr->mma_bar);
+        __syncwarp();
+      }
+      tc::mbar_wait(&hdr->mma_bar, mph);
+      mph ^= 1;
+      tc::fence_after_sync();
+    }
+    // epilogue: + bias + d w_d, activation, out through the staging tile (the A tile: its MMAs are done)
+    const float d = dens ? dens[b] / 5000.f : 0.f;          // gnn_dyn.py:158
+#pragma unroll 1
+    for (int ob = 0; ob < NB; ++ob) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float v[16];
+        tc::tmem_ld16(taddr + ob * 64 + half * 32 + q * 16, v);
+        tc::tmem_ld_wait();
+        const int c0 = ob * 64 + half * 32 + q * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float add = bias ? __ldg(bias + c0 + j) : 0.f;
+          if (wd) add = fmaf(d, __ldg(wd + c0 + j), add);
+          v[j] += add;
+          if (relu) v[j] = fmaxf(v[j], 0.f);
+        }
+        stage_put16(a_hi, r, half * 32 + q * 16, v);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int idx = it * GT_THREADS + t;
+        const int row = idx >> 4, slot = idx & 15;
+        const float4 v = *reinterpret_cast<const float4*>(a_hi + stage_off(row, slot));
+        if (row < nrows) st4(y + (row0 + row) * Hp + ob * 64 + slot * 4, v);
+      }
+      __syncthreads();
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (t < 32) tc::tmem_dealloc(hdr->tmem_base, TCOLS);
+}
+
+size_t tc_image_floats(int Hp) { return (size_t)Hp * Hp; }          // hi + lo bf16 per weight = one float's worth
+
+int launch_tc_image(const float* Wt, int Hp, float* img, cudaStream_t st) {
+  k_g_tc_image<<<(Hp * Hp + 255) / 256, 256, 0, st>>>(Wt, Hp, reinterpret_cast<__nv_bfloat16*>(img));
+  PILE_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int NB>
+static int launch_lin_tc_nb(const float* x, const float* img, const float* bias, const float* wd, const float* dens, int relu,
+                            float* y, const int* rowptr, int B, int N, cudaStream_t st) {
+  static DeviceOnce once;
+  const int dev = once.pending();
+  if (dev >= 0) {
+    cudaError_t e = cudaFuncSetAttribute(k_g_lin_tc<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem(64 * NB));
+    if (e != cudaSuccess) return (int)e;
+    once.done(dev);
+  }
+  const long long ntiles = (long long)B * ((KMAX * N + TILE - 1) / TILE);
+  const int grid = (int)(ntiles < 2 * NSM ? ntiles : 2 * NSM);
+  k_g_lin_tc<NB><<<grid, GT_THREADS, gt_smem(64 * NB), st>>>(x, reinterpret_cast<const uint8_t*>(img), bias, wd, dens, relu, y,
+                                                             rowptr, B, N);
+  PILE_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_lin_tc_edge(const float* x, const float* img, const float* bias, const float* wd, const float* dens, int relu,
+                       float* y, const int* rowptr, int B, int N, int Hp, cudaStream_t st) {
+  switch (Hp / 64) {
+    case 1: return launch_lin_tc_nb<1>(x, img, bias, wd, dens, relu, y, rowptr, B, N, st);
+    case 2: return launch_lin_tc_nb<2>(x, img, bias, wd, dens, relu, y, rowptr, B, N, st);
+    case 3: return launch_lin_tc_nb<3>(x, img, bias, wd, dens, relu, y, rowptr, B, N, st);
+    case 4: return launch_lin_tc_nb<4>(x, img, bias, wd, dens, relu, y, rowptr, B, N, st);
+  }
+  return (int)cudaErrorInvalidValue;
+}
+
+}  // namespace general
+}  // namespace pile

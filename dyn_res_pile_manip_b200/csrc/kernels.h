@@ -147,6 +147,13 @@ int general_relations_view(void* tape, int B, int N, int H, int** rowptr, int** 
 int launch_general_forward(const float* wpack, int H, const float* attr, const float* dens, const int* particle_nums,
                            const float* s_cur, const float* s_delta, float adj_thresh, int B, int N, void* tape,
                            float* s_pred, cudaStream_t st, bool hoisted = false);
+// tensor-core form of the wide relation-side layers of the general-width engine (general_tc.cu), inference only
+namespace general {
+size_t tc_image_floats(int Hp);
+int launch_tc_image(const float* Wt, int Hp, float* img, cudaStream_t st);
+int launch_lin_tc_edge(const float* x, const float* img, const float* bias, const float* wd, const float* dens, int relu,
+                       float* y, const int* rowptr, int B, int N, int Hp, cudaStream_t st);
+}  // namespace general
 int launch_general_forward_relations(const float* wpack, int H, const float* attr, const float* dens, const float* s_cur,
                                      const float* s_delta, const int* rowptr, const int* col, const int* row, int B,
                                      int N, void* tape, float* s_pred, cudaStream_t st);

@@ -32,6 +32,11 @@ def set_tensor_cores(mode):
     return int(_lib.load().pile_set_tensor_cores(int(mode)))
 
 
+def get_tensor_cores():
+    """The GEMM engine currently selected (see set_tensor_cores)."""
+    return int(_lib.load().pile_get_tensor_cores())
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -242,7 +242,9 @@ def test_mppi_planner_width150_matches_oracle_composition():
     np.testing.assert_allclose(got["action_sequence"], mean[:, 0, :], rtol=0, atol=5e-4)     # softmax-weighted mean of them
 
 
-@pytest.mark.parametrize("nf,N,B", [(8, 20, 3), (96, 50, 4), (150, 100, 5), (256, 33, 2)])
+# the last four have >= 4096 relation slots: their wide relation-side layers run on tcgen05 (general_tc.cu), one case per
+# number of 64-wide blocks (nf_effect 40 / 96 / 150 / 256 -> 1 / 2 / 3 / 4)
+@pytest.mark.parametrize("nf,N,B", [(8, 20, 3), (96, 50, 4), (256, 33, 2), (40, 60, 8), (96, 60, 8), (150, 100, 5), (256, 60, 8)])
 def test_inference_forward_equals_training_forward(nf, N, B):
     """Without a gradient in sight predict_one_step takes pile_general_forward_inference (the regrouped relation
     propagator: one relation-side GEMM per step instead of three wide ones); it must give the training forward's
@@ -266,6 +268,21 @@ def test_inference_forward_equals_training_forward(nf, N, B):
     assert err < 5e-6, err
     slow.sum().backward()                                   # and the taped one still backpropagates
     assert torch.isfinite(s_req.grad).all()
+    # the GEMM-engine selector: FP32 CUDA cores (0) must agree with the tensor cores, and where the batch is large
+    # enough for the tensor-core layers the two results must not be the same bits (i.e. that path really ran)
+    keep = ops.get_tensor_cores()
+    try:
+        ops.set_tensor_cores(0)
+        with torch.no_grad():
+            fp32 = model.predict_one_step(*args)
+    finally:
+        ops.set_tensor_cores(keep)
+    err32 = np.abs((fast - fp32).cpu().numpy()).max() / max(np.abs(moved).max(), 1e-30)
+    assert err32 < 5e-6, err32
+    if keep != 0 and B * 10 * N >= 4096:
+        assert not torch.equal(fast, fp32)
+    else:
+        assert torch.equal(fast, fp32)
 
 
 def test_width_limits():

@@ -75,5 +75,12 @@ for nf in (150, 96):
                                       wm, acts)["model_rollout"]["state_pred"]
     pred.sum().backward()
     assert torch.isfinite(acts.grad).all()
+    # inference (no gradient): hoisted relation propagator, wide relation-side layers on tcgen05 (csrc/general_tc.cu;
+    # 4500 relation slots, ragged)
+    st, dn = synthetic.make_pile_batch(10, 45, seed=3)
+    with torch.no_grad():
+        out = wm.predict_one_step(torch.zeros(10, 45).cuda(), torch.tensor(st).cuda(), 0.01 * torch.randn(10, 45, 3).cuda(),
+                                  torch.tensor(dn).cuda(), torch.tensor([45, 31, 20, 45, 45, 2, 45, 44, 45, 45]))
+    assert torch.isfinite(out).all()
 torch.cuda.synchronize()
 print("round-2 paths ok")
