@@ -816,26 +816,32 @@ int forward_body(const float* wpack, int Hp, const float* attr, const float* den
   k_g_node_in<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(s_delta, attr, dens, t.X0, B, N);
   PILE_CHECK_LAUNCH();
   auto W = [&](int slot) { return wpack + slot_offset(slot, Hp); };
-  {  // particle encoder
-    LinArgs a = lin_base(B, N, nb, t.csr);
-    a.x8 = t.X0; a.w8 = W(W_PE0T); a.bias = W(B_PE0); a.y = t.H0; a.relu = 1;
-    if ((e = lin<false>(a, st))) return e;
-    a = lin_base(B, N, nb, t.csr);
-    a.nsrc = 1; a.src[0] = {t.H0, W(W_PE1T), 0}; a.bias = W(B_PE1); a.y = t.P; a.relu = 1;
-    if ((e = lin<false>(a, st))) return e;
-  }
   // Inference with the tensor-core GEMM engine selected (pile_set_tensor_cores != 0) and enough relation rows to fill the
   // GPU: the three wide relation-side layers run on tcgen05 (general_tc.cu).  Their bf16 hi / lo weight images are built here,
   // into the tape space behind P_r (the head of M[1]; M[1] / M[2] hold nothing else in an inference step).
   const size_t E_cap = (size_t)B * KMAX * N;
+  enum { I_RE1, I_RE2, I_E, I_PE1, I_R, I_S, I_P, I_A, I_V0, NIMG };
   const bool tc = hoisted && g_use_tensor_cores != 0 && E_cap >= 4096 &&
-                  E_cap * Hp >= (size_t)R * Hp + 3 * tc_image_floats(Hp);
-  float* img[3] = {nullptr, nullptr, nullptr};
+                  E_cap * Hp >= (size_t)R * Hp + NIMG * tc_image_floats(Hp);
+  float* img[NIMG] = {};
   if (tc) {
-    const int wslot[3] = {W_RE1T, W_RE2T, W_ET};
-    for (int i = 0; i < 3; ++i) {
+    const int wslot[NIMG] = {W_RE1T, W_RE2T, W_ET, W_PE1T, W_RT, W_ST, W_PT, W_AT, W_V0T};
+    for (int i = 0; i < NIMG; ++i) {
       img[i] = t.M[1] + (size_t)R * Hp + i * tc_image_floats(Hp);
       if ((e = launch_tc_image(W(wslot[i]), Hp, img[i], st))) return e;
+    }
+  }
+  {  // particle encoder
+    LinArgs a = lin_base(B, N, nb, t.csr);
+    a.x8 = t.X0; a.w8 = W(W_PE0T); a.bias = W(B_PE0); a.y = t.H0; a.relu = 1;
+    if ((e = lin<false>(a, st))) return e;
+    if (tc) {
+      if ((e = launch_lin_tc_node(t.H0, img[I_PE1], nullptr, nullptr, W(B_PE1), nullptr, nullptr, nullptr, 1, t.P, B, N, Hp, st)))
+        return e;
+    } else {
+      a = lin_base(B, N, nb, t.csr);
+      a.nsrc = 1; a.src[0] = {t.H0, W(W_PE1T), 0}; a.bias = W(B_PE1); a.y = t.P; a.relu = 1;
+      if ((e = lin<false>(a, st))) return e;
     }
   }
   {  // relation encoder
@@ -843,8 +849,8 @@ int forward_body(const float* wpack, int Hp, const float* attr, const float* den
     a.x8 = t.Y0; a.w8 = W(W_RE0T); a.bias = W(B_RE0); a.y = t.R1; a.relu = 1;
     if ((e = lin<true>(a, st))) return e;
     if (tc) {
-      if ((e = launch_lin_tc_edge(t.R1, img[0], W(B_RE1), nullptr, nullptr, 1, t.R2, t.csr.rowptr, B, N, Hp, st))) return e;
-      if ((e = launch_lin_tc_edge(t.R2, img[1], W(B_RE2), nullptr, nullptr, 1, t.R3, t.csr.rowptr, B, N, Hp, st))) return e;
+      if ((e = launch_lin_tc_edge(t.R1, img[I_RE1], W(B_RE1), nullptr, nullptr, 1, t.R2, t.csr.rowptr, B, N, Hp, st))) return e;
+      if ((e = launch_lin_tc_edge(t.R2, img[I_RE2], W(B_RE2), nullptr, nullptr, 1, t.R3, t.csr.rowptr, B, N, Hp, st))) return e;
     } else {
       a = lin_base(B, N, nb, t.csr);
       a.nsrc = 1; a.src[0] = {t.R1, W(W_RE1T), 0}; a.bias = W(B_RE1); a.y = t.R2; a.relu = 1;
@@ -856,7 +862,7 @@ int forward_body(const float* wpack, int Hp, const float* attr, const float* den
   const unsigned node4 = (unsigned)((R * (Hp / 4) + 255) / 256);
   if (hoisted) {          // Ce = W_e r3 + w_d d + b
     if (tc) {
-      if ((e = launch_lin_tc_edge(t.R3, img[2], W(B_RP), W(WD_RP), dens, 0, t.M[0], t.csr.rowptr, B, N, Hp, st))) return e;
+      if ((e = launch_lin_tc_edge(t.R3, img[I_E], W(B_RP), W(WD_RP), dens, 0, t.M[0], t.csr.rowptr, B, N, Hp, st))) return e;
     } else {
       LinArgs a = lin_base(B, N, nb, t.csr);
       a.nsrc = 1; a.src[0] = {t.R3, W(W_ET), 0}; a.dens = dens; a.wd = W(WD_RP); a.bias = W(B_RP); a.y = t.M[0]; a.relu = 0;
@@ -867,12 +873,24 @@ int forward_body(const float* wpack, int Hp, const float* attr, const float* den
     const float* eff_in = p == 0 ? t.P : t.eff[p - 1];
     LinArgs a = lin_base(B, N, nb, t.csr);
     if (hoisted) {
-      a.nsrc = 1; a.src[0] = {eff_in, W(W_RT), 0}; a.y = t.M[1]; a.relu = 0;
-      if ((e = lin<false>(a, st))) return e;
-      a.src[0] = {eff_in, W(W_ST), 0}; a.y = t.M[2];
-      if ((e = lin<false>(a, st))) return e;
+      if (tc) {
+        if ((e = launch_lin_tc_node(eff_in, img[I_R], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, t.M[1], B, N, Hp, st)))
+          return e;
+        if ((e = launch_lin_tc_node(eff_in, img[I_S], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, t.M[2], B, N, Hp, st)))
+          return e;
+      } else {
+        a.nsrc = 1; a.src[0] = {eff_in, W(W_RT), 0}; a.y = t.M[1]; a.relu = 0;
+        if ((e = lin<false>(a, st))) return e;
+        a.src[0] = {eff_in, W(W_ST), 0}; a.y = t.M[2];
+        if ((e = lin<false>(a, st))) return e;
+      }
       k_g_agg_hoisted<<<node4, 256, 0, st>>>(t.csr.rowptr, t.csr.col, t.M[0], t.M[1], t.M[2], t.agg[p], B, N, Hp);
       PILE_CHECK_LAUNCH();
+      if (tc) {
+        if ((e = launch_lin_tc_node(t.P, img[I_P], t.agg[p], img[I_A], W(B_PP), W(WD_PP), dens, eff_in, 1, t.eff[p], B, N, Hp, st)))
+          return e;
+        continue;
+      }
       a = lin_base(B, N, nb, t.csr);
       a.nsrc = 2;
       a.src[0] = {t.P, W(W_PT), 0};
@@ -896,7 +914,10 @@ int forward_body(const float* wpack, int Hp, const float* attr, const float* den
     a.dens = dens; a.wd = W(WD_PP); a.bias = W(B_PP); a.res = eff_in; a.y = t.eff[p]; a.relu = 1;
     if ((e = lin<false>(a, st))) return e;
   }
-  {
+  if (tc) {
+    if ((e = launch_lin_tc_node(t.eff[PSTEP - 1], img[I_V0], nullptr, nullptr, W(B_V0), nullptr, nullptr, nullptr, 1, t.Q, B, N, Hp, st)))
+      return e;
+  } else {
     LinArgs a = lin_base(B, N, nb, t.csr);
     a.nsrc = 1; a.src[0] = {t.eff[PSTEP - 1], W(W_V0T), 0}; a.bias = W(B_V0); a.y = t.Q; a.relu = 1;
     if ((e = lin<false>(a, st))) return e;

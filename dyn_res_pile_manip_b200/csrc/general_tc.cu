@@ -1,7 +1,8 @@
-// General-width engine, inference: the three wide relation-side layers (RE1, RE2 and the hoisted C_e = W_e r3 + w_d d + b;
-// reference model/gnn_dyn.py:95-111, 186-187 at any nf_effect, model/gnn_dyn.py:119) on the tensor cores.
+// General-width engine, inference: every Hp-wide layer of the hoisted model step on the tensor cores -- relation side RE1,
+// RE2 and C_e = W_e r3 + w_d d + b, particle side PE1, (P_r, P_s) = (W_r, W_s) eff, the particle propagator and V0 (reference
+// model/gnn_dyn.py:62-111, 174-198 at any nf_effect, model/gnn_dyn.py:119).
 //
-//   y[E, Hp] = act(x[E, Hp] W^T + bias + d w_d)          Hp = 64 NB, NB = 1..4 (nf_effect <= 256 zero-padded)
+//   y[rows, Hp] = act(sum_s x_s[rows, Hp] W_s^T + bias + d w_d + res)     Hp = 64 NB, NB = 1..4 (nf_effect <= 256 zero-padded)
 //
 // Same arithmetic as the width-64 planner engines (tc.cuh): every fp32 operand is split into bf16 hi + lo, a product is
 // three tcgen05.mma passes accumulated in fp32 in tensor memory.  One 256-thread CTA per 128-row tile, two CTAs per SM
@@ -64,11 +65,21 @@ __device__ __forceinline__ void load_block_to_tile(const float* __restrict__ x, 
   }
 }
 
-template <int NB>
-__global__ void __launch_bounds__(GT_THREADS, 2)
-k_g_lin_tc(const float* __restrict__ x, const uint8_t* __restrict__ img, const float* __restrict__ bias,
-           const float* __restrict__ wd, const float* __restrict__ dens, int relu, float* __restrict__ y,
-           const int* __restrict__ rowptr, int B, int N) {
+struct LinTcArgs {
+  int nsrc;                 // 1 or 2 sources
+  const float* x[2];        // [rows, Hp]
+  const uint8_t* img[2];    // weight images (k_g_tc_image)
+  const float* bias;        // [Hp] or nullptr
+  const float* wd;          // [Hp] density column or nullptr
+  const float* dens;        // [B]
+  const float* res;         // residual rows [rows, Hp] added before the activation, or nullptr
+  float* y;
+  const int* rowptr;        // EDGE: relation rows, tiled per sample
+  int relu, B, N;
+};
+
+template <int NB, bool EDGE>
+__global__ void __launch_bounds__(GT_THREADS, 2) k_g_lin_tc(const LinTcArgs a) {
   constexpr int Hp = 64 * NB;
   constexpr uint32_t WPART = gt_wpart(Hp), WROW = 2 * WPART;
   constexpr uint32_t TCOLS = NB == 1 ? 64u : (NB == 2 ? 128u : 256u);
@@ -81,6 +92,7 @@ k_g_lin_tc(const float* __restrict__ x, const uint8_t* __restrict__ img, const f
   GtHdr* const hdr = reinterpret_cast<GtHdr*>(w_sm + WROW);
   const int t = threadIdx.x, wig = t >> 5, lane = t & 31;
   const int r = (wig & 3) * 32 + lane, half = wig >> 2;
+  const int B = a.B, N = a.N;
 
   if (t < 32) tc::tmem_alloc(&hdr->tmem_base, TCOLS);
   if (t == 0) {
@@ -97,65 +109,100 @@ k_g_lin_tc(const float* __restrict__ x, const uint8_t* __restrict__ img, const f
   const uint32_t sw_hi = tc::smem_u32(w_sm), sw_lo = sw_hi + WPART;
   uint32_t mph = 0, wph = 0;
 
-  // relation rows are tiled per sample (the slots of a sample are contiguous, its last tile is partial)
+  // relation rows are tiled per sample (the slots of a sample are contiguous, its last tile is partial); particle rows
+  // are one contiguous range
   const int tps = (KMAX * N + TILE - 1) / TILE;
-  const int ntiles = B * tps;
+  const long long R = (long long)B * N;
+  const int ntiles = EDGE ? B * tps : (int)((R + TILE - 1) / TILE);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int b = tile / tps;
-    const int e0 = (tile - b * tps) * TILE;
-    const int nrows = min(TILE, rowptr[(long long)b * (N + 1) + N] - e0);
-    if (nrows <= 0) continue;          // CTA-uniform
-    const long long row0 = (long long)b * KMAX * N + e0;
-#pragma unroll 1
-    for (int kb = 0; kb < NB; ++kb) {
-      // the previous MMAs have completed (waited below): both operand buffers are free
-      if (t == 0) {
-        tc::mbar_expect_tx(&hdr->w_bar, WROW);
-        tc::bulk_g2s(w_sm, img + (size_t)kb * WROW, WROW, &hdr->w_bar);
-      }
-      load_block_to_tile(x, row0, nrows, Hp, kb * 64, t, a_hi, a_lo);
-      tc::fence_async_smem();
-      tc::fence_before_sync();          // this thread's tcgen05.ld of the previous tile are complete
-      __syncthreads();
-      tc::mbar_wait(&hdr->w_bar, wph);
-      wph ^= 1;
-      if (wig == 0) {
-        tc::fence_after_sync();
-        const uint32_t el = tc::elect_one();
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a = pass == 1 ? sa_lo : sa_hi;
-          const uint32_t w = pass == 2 ? sw_lo : sw_hi;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc::mma_bf16_if(el, tmem_d, tc::make_desc(a + k * 2 * A_LBO, A_LBO, A_SBO),
-                            tc::make_desc(w + k * 2 * BL, BL, B_SBO), idesc, (kb | pass | k) != 0 ? 1u : 0u);
-        }
-        if (el) tc::mma_commit(&hdr->mma_bar);
-        __syncwarp();
-      }
-      tc::mbar_wait(&hdr->mma_bar, mph);
-      mph ^= 1;
-      tc::fence_after_sync();
+    int nrows, b = 0;
+    long long row0;
+    if (EDGE) {
+      b = tile / tps;
+      const int e0 = (tile - b * tps) * TILE;
+      nrows = min(TILE, a.rowptr[(long long)b * (N + 1) + N] - e0);
+      row0 = (long long)b * KMAX * N + e0;
+    } else {
+      row0 = (long long)tile * TILE;
+      nrows = (int)min((long long)TILE, R - row0);
     }
-    // epilogue: + bias + d w_d, activation, out through the staging tile (the A tile: its MMAs are done)
-    const float d = dens ? dens[b] / 5000.f : 0.f;          // gnn_dyn.py:158
+    if (nrows <= 0) continue;          // CTA-uniform
+    int step = 0;
+#pragma unroll 1
+    for (int s = 0; s < a.nsrc; ++s) {
+#pragma unroll 1
+      for (int kb = 0; kb < NB; ++kb, ++step) {
+        // the previous MMAs have completed (waited below): both operand buffers are free
+        if (t == 0) {
+          tc::mbar_expect_tx(&hdr->w_bar, WROW);
+          tc::bulk_g2s(w_sm, a.img[s] + (size_t)kb * WROW, WROW, &hdr->w_bar);
+        }
+        load_block_to_tile(a.x[s], row0, nrows, Hp, kb * 64, t, a_hi, a_lo);
+        tc::fence_async_smem();
+        tc::fence_before_sync();          // this thread's tcgen05.ld of the previous tile are complete
+        __syncthreads();
+        tc::mbar_wait(&hdr->w_bar, wph);
+        wph ^= 1;
+        if (wig == 0) {
+          tc::fence_after_sync();
+          const uint32_t el = tc::elect_one();
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t pa = pass == 1 ? sa_lo : sa_hi;
+            const uint32_t pw = pass == 2 ? sw_lo : sw_hi;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc::mma_bf16_if(el, tmem_d, tc::make_desc(pa + k * 2 * A_LBO, A_LBO, A_SBO),
+                              tc::make_desc(pw + k * 2 * BL, BL, B_SBO), idesc, (step | pass | k) != 0 ? 1u : 0u);
+          }
+          if (el) tc::mma_commit(&hdr->mma_bar);
+          __syncwarp();
+        }
+        tc::mbar_wait(&hdr->mma_bar, mph);
+        mph ^= 1;
+        tc::fence_after_sync();
+      }
+    }
+    // epilogue: + bias + d w_d + residual, activation, out through the staging tile (the A tile: its MMAs are done)
+    float d = 0.f;
+    if (a.dens) {
+      const long long node = EDGE ? 0 : min(row0 + r, R - 1);
+      d = a.dens[EDGE ? b : (int)(node / N)] / 5000.f;          // gnn_dyn.py:158
+    }
 #pragma unroll 1
     for (int ob = 0; ob < NB; ++ob) {
+      if (a.res) {          // the residual block, whole lines -> staging tile
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int idx = it * GT_THREADS + t;
+          const int row = idx >> 4, slot = idx & 15;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < nrows) v = ld4(a.res + (row0 + row) * Hp + ob * 64 + slot * 4);
+          *reinterpret_cast<float4*>(a_hi + stage_off(row, slot)) = v;
+        }
+        __syncthreads();
+      }
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         float v[16];
         tc::tmem_ld16(taddr + ob * 64 + half * 32 + q * 16, v);
         tc::tmem_ld_wait();
         const int c0 = ob * 64 + half * 32 + q * 16;
+        if (a.res) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 u = *reinterpret_cast<const float4*>(a_hi + stage_off(r, ((half * 32 + q * 16) >> 2) + i));
+            v[4 * i] += u.x; v[4 * i + 1] += u.y; v[4 * i + 2] += u.z; v[4 * i + 3] += u.w;
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float add = bias ? __ldg(bias + c0 + j) : 0.f;
-          if (wd) add = fmaf(d, __ldg(wd + c0 + j), add);
+          float add = a.bias ? __ldg(a.bias + c0 + j) : 0.f;
+          if (a.wd) add = fmaf(d, __ldg(a.wd + c0 + j), add);
           v[j] += add;
-          if (relu) v[j] = fmaxf(v[j], 0.f);
+          if (a.relu) v[j] = fmaxf(v[j], 0.f);
         }
-        stage_put16(a_hi, r, half * 32 + q * 16, v);
+        stage_put16(a_hi, r, half * 32 + q * 16, v);          // the slots this thread just read
       }
       __syncthreads();
 #pragma unroll
@@ -163,7 +210,7 @@ k_g_lin_tc(const float* __restrict__ x, const uint8_t* __restrict__ img, const f
         const int idx = it * GT_THREADS + t;
         const int row = idx >> 4, slot = idx & 15;
         const float4 v = *reinterpret_cast<const float4*>(a_hi + stage_off(row, slot));
-        if (row < nrows) st4(y + (row0 + row) * Hp + ob * 64 + slot * 4, v);
+        if (row < nrows) st4(a.y + (row0 + row) * Hp + ob * 64 + slot * 4, v);
       }
       __syncthreads();
     }
@@ -181,33 +228,51 @@ int launch_tc_image(const float* Wt, int Hp, float* img, cudaStream_t st) {
   return 0;
 }
 
-template <int NB>
-static int launch_lin_tc_nb(const float* x, const float* img, const float* bias, const float* wd, const float* dens, int relu,
-                            float* y, const int* rowptr, int B, int N, cudaStream_t st) {
+template <int NB, bool EDGE>
+static int launch_lin_tc_nb(const LinTcArgs& a, cudaStream_t st) {
   static DeviceOnce once;
   const int dev = once.pending();
   if (dev >= 0) {
-    cudaError_t e = cudaFuncSetAttribute(k_g_lin_tc<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem(64 * NB));
+    cudaError_t e = cudaFuncSetAttribute(k_g_lin_tc<NB, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem(64 * NB));
     if (e != cudaSuccess) return (int)e;
     once.done(dev);
   }
-  const long long ntiles = (long long)B * ((KMAX * N + TILE - 1) / TILE);
-  const int grid = (int)(ntiles < 2 * NSM ? ntiles : 2 * NSM);
-  k_g_lin_tc<NB><<<grid, GT_THREADS, gt_smem(64 * NB), st>>>(x, reinterpret_cast<const uint8_t*>(img), bias, wd, dens, relu, y,
-                                                             rowptr, B, N);
+  const long long ntiles = EDGE ? (long long)a.B * ((KMAX * a.N + TILE - 1) / TILE) : ((long long)a.B * a.N + TILE - 1) / TILE;
+  const int grid = (int)(ntiles < 1 ? 1 : (ntiles < 2 * NSM ? ntiles : 2 * NSM));
+  k_g_lin_tc<NB, EDGE><<<grid, GT_THREADS, gt_smem(64 * NB), st>>>(a);
   PILE_CHECK_LAUNCH();
   return 0;
 }
 
-int launch_lin_tc_edge(const float* x, const float* img, const float* bias, const float* wd, const float* dens, int relu,
-                       float* y, const int* rowptr, int B, int N, int Hp, cudaStream_t st) {
+template <bool EDGE>
+static int launch_lin_tc_any(const LinTcArgs& a, int Hp, cudaStream_t st) {
   switch (Hp / 64) {
-    case 1: return launch_lin_tc_nb<1>(x, img, bias, wd, dens, relu, y, rowptr, B, N, st);
-    case 2: return launch_lin_tc_nb<2>(x, img, bias, wd, dens, relu, y, rowptr, B, N, st);
-    case 3: return launch_lin_tc_nb<3>(x, img, bias, wd, dens, relu, y, rowptr, B, N, st);
-    case 4: return launch_lin_tc_nb<4>(x, img, bias, wd, dens, relu, y, rowptr, B, N, st);
+    case 1: return launch_lin_tc_nb<1, EDGE>(a, st);
+    case 2: return launch_lin_tc_nb<2, EDGE>(a, st);
+    case 3: return launch_lin_tc_nb<3, EDGE>(a, st);
+    case 4: return launch_lin_tc_nb<4, EDGE>(a, st);
   }
   return (int)cudaErrorInvalidValue;
+}
+
+int launch_lin_tc_edge(const float* x, const float* img, const float* bias, const float* wd, const float* dens, int relu,
+                       float* y, const int* rowptr, int B, int N, int Hp, cudaStream_t st) {
+  LinTcArgs a{};
+  a.nsrc = 1; a.x[0] = x; a.img[0] = reinterpret_cast<const uint8_t*>(img);
+  a.bias = bias; a.wd = wd; a.dens = dens; a.res = nullptr; a.y = y; a.rowptr = rowptr; a.relu = relu; a.B = B; a.N = N;
+  return launch_lin_tc_any<true>(a, Hp, st);
+}
+
+// particle rows: up to two sources, optional residual
+int launch_lin_tc_node(const float* x0, const float* img0, const float* x1, const float* img1, const float* bias,
+                       const float* wd, const float* dens, const float* res, int relu, float* y, int B, int N, int Hp,
+                       cudaStream_t st) {
+  LinTcArgs a{};
+  a.nsrc = x1 ? 2 : 1;
+  a.x[0] = x0; a.img[0] = reinterpret_cast<const uint8_t*>(img0);
+  a.x[1] = x1; a.img[1] = reinterpret_cast<const uint8_t*>(img1);
+  a.bias = bias; a.wd = wd; a.dens = dens; a.res = res; a.y = y; a.rowptr = nullptr; a.relu = relu; a.B = B; a.N = N;
+  return launch_lin_tc_any<false>(a, Hp, st);
 }
 
 }  // namespace general

@@ -153,6 +153,9 @@ size_t tc_image_floats(int Hp);
 int launch_tc_image(const float* Wt, int Hp, float* img, cudaStream_t st);
 int launch_lin_tc_edge(const float* x, const float* img, const float* bias, const float* wd, const float* dens, int relu,
                        float* y, const int* rowptr, int B, int N, int Hp, cudaStream_t st);
+int launch_lin_tc_node(const float* x0, const float* img0, const float* x1, const float* img1, const float* bias,
+                       const float* wd, const float* dens, const float* res, int relu, float* y, int B, int N, int Hp,
+                       cudaStream_t st);
 }  // namespace general
 int launch_general_forward_relations(const float* wpack, int H, const float* attr, const float* dens, const float* s_cur,
                                      const float* s_delta, const int* rowptr, const int* col, const int* row, int B,

@@ -265,7 +265,14 @@ def test_inference_forward_equals_training_forward(nf, N, B):
     assert all(np.array_equal(a, b) for a, b in zip(rel_fast, rel_slow))
     moved = (slow.detach() - args[1]).cpu().numpy()
     err = np.abs((fast - slow.detach()).cpu().numpy()).max() / max(np.abs(moved).max(), 1e-30)
-    assert err < 5e-6, err
+    # FP32 on both sides: summation order only.  On the tensor-core layers (bf16 hi / lo split, 2^-16 per product) the
+    # measured difference is 1.1e-5 .. 1.4e-5 of the particle MOTION and 2e-6 .. 6e-6 of the positions -- what the width-64
+    # tensor engines show; BASELINE's bar is 1e-4 of the positions after one step
+    on_tc = ops.get_tensor_cores() != 0 and B * 10 * N >= 4096
+    tol = 5e-5 if on_tc else 5e-6
+    assert err < tol, err
+    pos_err = np.abs((fast - slow.detach()).cpu().numpy()).max() / np.abs(slow.detach().cpu().numpy()).max()
+    assert pos_err < (2e-5 if on_tc else 2e-6), pos_err
     slow.sum().backward()                                   # and the taped one still backpropagates
     assert torch.isfinite(s_req.grad).all()
     # the GEMM-engine selector: FP32 CUDA cores (0) must agree with the tensor cores, and where the batch is large
@@ -278,7 +285,7 @@ def test_inference_forward_equals_training_forward(nf, N, B):
     finally:
         ops.set_tensor_cores(keep)
     err32 = np.abs((fast - fp32).cpu().numpy()).max() / max(np.abs(moved).max(), 1e-30)
-    assert err32 < 5e-6, err32
+    assert err32 < tol, err32
     if keep != 0 and B * 10 * N >= 4096:
         assert not torch.equal(fast, fp32)
     else:
