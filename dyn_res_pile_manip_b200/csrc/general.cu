@@ -826,10 +826,12 @@ int forward_body(const float* wpack, int Hp, const float* attr, const float* den
   float* img[NIMG] = {};
   if (tc) {
     const int wslot[NIMG] = {W_RE1T, W_RE2T, W_ET, W_PE1T, W_RT, W_ST, W_PT, W_AT, W_V0T};
+    long long off[NIMG];
     for (int i = 0; i < NIMG; ++i) {
       img[i] = t.M[1] + (size_t)R * Hp + i * tc_image_floats(Hp);
-      if ((e = launch_tc_image(W(wslot[i]), Hp, img[i], st))) return e;
+      off[i] = slot_offset(wslot[i], Hp);
     }
+    if ((e = launch_tc_images(wpack, off, NIMG, Hp, img[0], st))) return e;
   }
   {  // particle encoder
     LinArgs a = lin_base(B, N, nb, t.csr);
@@ -846,12 +848,15 @@ int forward_body(const float* wpack, int Hp, const float* attr, const float* den
   }
   {  // relation encoder
     LinArgs a = lin_base(B, N, nb, t.csr);
-    a.x8 = t.Y0; a.w8 = W(W_RE0T); a.bias = W(B_RE0); a.y = t.R1; a.relu = 1;
-    if ((e = lin<true>(a, st))) return e;
     if (tc) {
-      if ((e = launch_lin_tc_edge(t.R1, img[I_RE1], W(B_RE1), nullptr, nullptr, 1, t.R2, t.csr.rowptr, B, N, Hp, st))) return e;
+      // RE0 (K = 8) is computed inside the RE1 kernel while it builds its A tiles: R1 never exists in memory
+      if ((e = launch_lin_tc_edge(nullptr, img[I_RE1], W(B_RE1), nullptr, nullptr, 1, t.R2, t.csr.rowptr, B, N, Hp, st, t.Y0,
+                                  W(W_RE0T), W(B_RE0))))
+        return e;
       if ((e = launch_lin_tc_edge(t.R2, img[I_RE2], W(B_RE2), nullptr, nullptr, 1, t.R3, t.csr.rowptr, B, N, Hp, st))) return e;
     } else {
+      a.x8 = t.Y0; a.w8 = W(W_RE0T); a.bias = W(B_RE0); a.y = t.R1; a.relu = 1;
+      if ((e = lin<true>(a, st))) return e;
       a = lin_base(B, N, nb, t.csr);
       a.nsrc = 1; a.src[0] = {t.R1, W(W_RE1T), 0}; a.bias = W(B_RE1); a.y = t.R2; a.relu = 1;
       if ((e = lin<true>(a, st))) return e;

@@ -32,9 +32,15 @@ __host__ __device__ constexpr uint32_t gt_smem(int Hp) { return 2 * A_BYTES + 2 
 
 // Wt: fp32 [Hp in][Hp out] (the forward image of general.cu) -> per K block kb: hi then lo canonical image of the B operand
 // [N = Hp outputs x K = 64 inputs]: bf16 index (k / 8) * (8 Hp) + (n / 8) * 64 + (n % 8) * 8 + (k % 8)
-__global__ void k_g_tc_image(const float* __restrict__ Wt, int Hp, __nv_bfloat16* __restrict__ img) {
+struct TcImages {
+  static constexpr int MAXN = 12;
+  const float* src[MAXN];
+};
+__global__ void k_g_tc_image(const TcImages im, int Hp, __nv_bfloat16* __restrict__ img0) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Hp * Hp) return;
+  const float* __restrict__ Wt = im.src[blockIdx.y];
+  __nv_bfloat16* __restrict__ img = img0 + (size_t)blockIdx.y * 2 * Hp * Hp;
   const int kin = idx / Hp, n = idx - kin * Hp;
   const float w = Wt[idx];
   const __nv_bfloat16 hi = __float2bfloat16_rn(w);
@@ -65,6 +71,44 @@ __device__ __forceinline__ void load_block_to_tile(const float* __restrict__ x, 
   }
 }
 
+// the same A tile block, computed instead of loaded: columns [col0, col0 + 64) of ReLU(x8 W8 + b8), x8 [*, 8] rows
+__device__ __forceinline__ void input_block_to_tile(const float* __restrict__ x8, const float* __restrict__ w8,
+                                                    const float* __restrict__ b8, long long row0, int nrows, int ld, int col0,
+                                                    int t, uint8_t* a_hi, uint8_t* a_lo) {
+  const int w = t >> 5, lane = t & 31;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {          // this thread's two rows
+    const int row = w * 16 + h * 8 + (lane & 7);
+    float in[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) in[i] = 0.f;
+    const bool ok = row < nrows;
+    if (ok) {
+      const float4 u = ld4(x8 + (row0 + row) * 8), v = ld4(x8 + (row0 + row) * 8 + 4);
+      in[0] = u.x; in[1] = u.y; in[2] = u.z; in[3] = u.w; in[4] = v.x; in[5] = v.y; in[6] = v.z; in[7] = v.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {        // and two of the eight K chunks per row
+      const int kc = c * 4 + (lane >> 3);
+      const float* wc = w8 + col0 + kc * 8;
+      float o[8];
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(b8 + col0 + kc * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(b8 + col0 + kc * 8 + 4));
+      o[0] = b0.x; o[1] = b0.y; o[2] = b0.z; o[3] = b0.w; o[4] = b1.x; o[5] = b1.y; o[6] = b1.z; o[7] = b1.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wc + (long long)j * ld));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wc + (long long)j * ld + 4));
+        o[0] = fmaf(in[j], w0.x, o[0]); o[1] = fmaf(in[j], w0.y, o[1]); o[2] = fmaf(in[j], w0.z, o[2]); o[3] = fmaf(in[j], w0.w, o[3]);
+        o[4] = fmaf(in[j], w1.x, o[4]); o[5] = fmaf(in[j], w1.y, o[5]); o[6] = fmaf(in[j], w1.z, o[6]); o[7] = fmaf(in[j], w1.w, o[7]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = ok ? fmaxf(o[i], 0.f) : 0.f;
+      store_chunk(a_hi, a_lo, (row >> 3) * A_SBO + (row & 7) * 16 + kc * A_LBO, o);
+    }
+  }
+}
+
 struct LinTcArgs {
   int nsrc;                 // 1 or 2 sources
   const float* x[2];        // [rows, Hp]
@@ -76,6 +120,11 @@ struct LinTcArgs {
   float* y;
   const int* rowptr;        // EDGE: relation rows, tiled per sample
   int relu, B, N;
+  // optional: source 0 is not read but computed on the fly, x_0 = ReLU(x8 W8 + b8) -- the narrow input layer in front of
+  // this one (RE0 in front of RE1): its [rows, Hp] output never goes through HBM
+  const float* x8;          // [rows, 8] or nullptr
+  const float* w8;          // [8][Hp]
+  const float* b8;          // [Hp]
 };
 
 template <int NB, bool EDGE>
@@ -137,7 +186,10 @@ __global__ void __launch_bounds__(GT_THREADS, 2) k_g_lin_tc(const LinTcArgs a) {
           tc::mbar_expect_tx(&hdr->w_bar, WROW);
           tc::bulk_g2s(w_sm, a.img[s] + (size_t)kb * WROW, WROW, &hdr->w_bar);
         }
-        load_block_to_tile(a.x[s], row0, nrows, Hp, kb * 64, t, a_hi, a_lo);
+        if (s == 0 && a.x8)
+          input_block_to_tile(a.x8, a.w8, a.b8, row0, nrows, Hp, kb * 64, t, a_hi, a_lo);
+        else
+          load_block_to_tile(a.x[s], row0, nrows, Hp, kb * 64, t, a_hi, a_lo);
         tc::fence_async_smem();
         tc::fence_before_sync();          // this thread's tcgen05.ld of the previous tile are complete
         __syncthreads();
@@ -222,8 +274,13 @@ __global__ void __launch_bounds__(GT_THREADS, 2) k_g_lin_tc(const LinTcArgs a) {
 
 size_t tc_image_floats(int Hp) { return (size_t)Hp * Hp; }          // hi + lo bf16 per weight = one float's worth
 
-int launch_tc_image(const float* Wt, int Hp, float* img, cudaStream_t st) {
-  k_g_tc_image<<<(Hp * Hp + 255) / 256, 256, 0, st>>>(Wt, Hp, reinterpret_cast<__nv_bfloat16*>(img));
+// `n` images in one launch: image i from wpack + slot_off[i] to img0 + i * Hp * Hp floats
+int launch_tc_images(const float* wpack, const long long* slot_off, int n, int Hp, float* img0, cudaStream_t st) {
+  if (n > TcImages::MAXN) return (int)cudaErrorInvalidValue;
+  TcImages im;
+  for (int i = 0; i < n; ++i) im.src[i] = wpack + slot_off[i];
+  const dim3 grid((Hp * Hp + 255) / 256, n);
+  k_g_tc_image<<<grid, 256, 0, st>>>(im, Hp, reinterpret_cast<__nv_bfloat16*>(img0));
   PILE_CHECK_LAUNCH();
   return 0;
 }
@@ -256,8 +313,10 @@ static int launch_lin_tc_any(const LinTcArgs& a, int Hp, cudaStream_t st) {
 }
 
 int launch_lin_tc_edge(const float* x, const float* img, const float* bias, const float* wd, const float* dens, int relu,
-                       float* y, const int* rowptr, int B, int N, int Hp, cudaStream_t st) {
+                       float* y, const int* rowptr, int B, int N, int Hp, cudaStream_t st, const float* x8, const float* w8,
+                       const float* b8) {
   LinTcArgs a{};
+  a.x8 = x8; a.w8 = w8; a.b8 = b8;
   a.nsrc = 1; a.x[0] = x; a.img[0] = reinterpret_cast<const uint8_t*>(img);
   a.bias = bias; a.wd = wd; a.dens = dens; a.res = nullptr; a.y = y; a.rowptr = rowptr; a.relu = relu; a.B = B; a.N = N;
   return launch_lin_tc_any<true>(a, Hp, st);

@@ -150,9 +150,10 @@ int launch_general_forward(const float* wpack, int H, const float* attr, const f
 // tensor-core form of the wide relation-side layers of the general-width engine (general_tc.cu), inference only
 namespace general {
 size_t tc_image_floats(int Hp);
-int launch_tc_image(const float* Wt, int Hp, float* img, cudaStream_t st);
+int launch_tc_images(const float* wpack, const long long* slot_off, int n, int Hp, float* img0, cudaStream_t st);
 int launch_lin_tc_edge(const float* x, const float* img, const float* bias, const float* wd, const float* dens, int relu,
-                       float* y, const int* rowptr, int B, int N, int Hp, cudaStream_t st);
+                       float* y, const int* rowptr, int B, int N, int Hp, cudaStream_t st, const float* x8 = nullptr,
+                       const float* w8 = nullptr, const float* b8 = nullptr);
 int launch_lin_tc_node(const float* x0, const float* img0, const float* x1, const float* img1, const float* bias,
                        const float* wd, const float* dens, const float* res, int relu, float* y, int B, int N, int Hp,
                        cudaStream_t st);
