@@ -726,7 +726,8 @@ def plan_latency(model, planner, env, goal, dev, args):
                              "forward_backward_ms": sorted(fb[2:])[len(fb[2:]) // 2],
                              "particle_steps_per_s": s2 * n2 / (sorted(fw[2:])[len(fw[2:]) // 2] * 1e-3),
                              "workload": "one model step, 256 samples x 100 particles, nf_effect = 150 (padded to 192) on the "
-                                         "general-width engine: forward (no_grad: hoisted inference form); forward + backward with all 18 weight gradients"}
+                                         "general-width engine: forward (no_grad: hoisted inference form, Hp-wide layers on tcgen05); forward + backward with all 18 "
+                                         "weight gradients (FP32 CUDA cores)"}
     del wmodel
 
     # the other planner-side piece of an MPC step: RGB-D observation -> 30 particle
