@@ -52,11 +52,12 @@ __global__ void k_g_tc_image(const TcImages im, int Hp, __nv_bfloat16* __restric
 }
 
 // rows [row0, row0 + nrows) x columns [col0, col0 + 64) of a row-major [*, ld] array -> hi/lo A tile (rows past nrows are
-// zero).  A warp instruction covers 8 rows x 128 bytes (whole lines); conflict-free on the shared-memory side.
-__device__ __forceinline__ void load_block_to_tile(const float* __restrict__ x, long long row0, int nrows, int ld, int col0,
-                                                   int t, uint8_t* a_hi, uint8_t* a_lo) {
+// zero), in two halves so that the global loads of the NEXT block are in flight while the tensor core works on this one:
+// block_issue (32 registers per thread; a warp instruction covers 8 rows x 128 bytes, whole lines) and block_commit (split +
+// conflict-free 16-byte shared-memory stores).
+__device__ __forceinline__ void block_issue(const float* __restrict__ x, long long row0, int nrows, int ld, int col0, int t,
+                                            float (&o)[4][8]) {
   const int w = t >> 5, lane = t & 31;
-  float o[4][8];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int row = w * 16 + (j >> 1) * 8 + (lane & 7), kc = (j & 1) * 4 + (lane >> 3);
@@ -64,6 +65,9 @@ __device__ __forceinline__ void load_block_to_tile(const float* __restrict__ x, 
     for (int i = 0; i < 8; ++i) o[j][i] = 0.f;
     if (row < nrows) ld8(x + (row0 + row) * ld + col0 + kc * 8, o[j]);
   }
+}
+__device__ __forceinline__ void block_commit(const float (&o)[4][8], int t, uint8_t* a_hi, uint8_t* a_lo) {
+  const int w = t >> 5, lane = t & 31;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int row = w * 16 + (j >> 1) * 8 + (lane & 7), kc = (j & 1) * 4 + (lane >> 3);
@@ -177,6 +181,9 @@ __global__ void __launch_bounds__(GT_THREADS, 2) k_g_lin_tc(const LinTcArgs a) {
     }
     if (nrows <= 0) continue;          // CTA-uniform
     int step = 0;
+    const int nsteps = a.nsrc * NB;
+    float blk[4][8];          // the block of the step ahead
+    if (!a.x8) block_issue(a.x[0], row0, nrows, Hp, 0, t, blk);
 #pragma unroll 1
     for (int s = 0; s < a.nsrc; ++s) {
 #pragma unroll 1
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) k_g_lin_tc(const LinTcArgs a) {
         if (s == 0 && a.x8)
           input_block_to_tile(a.x8, a.w8, a.b8, row0, nrows, Hp, kb * 64, t, a_hi, a_lo);
         else
-          load_block_to_tile(a.x[s], row0, nrows, Hp, kb * 64, t, a_hi, a_lo);
+          block_commit(blk, t, a_hi, a_lo);
         tc::fence_async_smem();
         tc::fence_before_sync();          // this thread's tcgen05.ld of the previous tile are complete
         __syncthreads();
@@ -209,6 +216,11 @@ __global__ void __launch_bounds__(GT_THREADS, 2) k_g_lin_tc(const LinTcArgs a) {
           }
           if (el) tc::mma_commit(&hdr->mma_bar);
           __syncwarp();
+        }
+        // the next step's rows: on their way while the tensor core works
+        if (step + 1 < nsteps) {
+          const int s1 = kb + 1 < NB ? s : s + 1, kb1 = kb + 1 < NB ? kb + 1 : 0;
+          if (!(s1 == 0 && a.x8)) block_issue(a.x[s1], row0, nrows, Hp, kb1 * 64, t, blk);
         }
         tc::mbar_wait(&hdr->mma_bar, mph);
         mph ^= 1;
@@ -248,11 +260,17 @@ __global__ void __launch_bounds__(GT_THREADS, 2) k_g_lin_tc(const LinTcArgs a) {
           }
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float add = a.bias ? __ldg(a.bias + c0 + j) : 0.f;
-          if (a.wd) add = fmaf(d, __ldg(a.wd + c0 + j), add);
-          v[j] += add;
-          if (a.relu) v[j] = fmaxf(v[j], 0.f);
+        for (int j = 0; j < 16; j += 4) {
+          float4 add = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.wd) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.wd + c0 + j));
+            add.x = fmaf(d, w4.x, add.x); add.y = fmaf(d, w4.y, add.y); add.z = fmaf(d, w4.z, add.z); add.w = fmaf(d, w4.w, add.w);
+          }
+          v[j] += add.x; v[j + 1] += add.y; v[j + 2] += add.z; v[j + 3] += add.w;
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         stage_put16(a_hi, r, half * 32 + q * 16, v);          // the slots this thread just read
       }
